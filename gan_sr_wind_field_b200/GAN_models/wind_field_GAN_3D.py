@@ -1,0 +1,388 @@
+"""``wind_field_GAN_3D``: the GAN training step that drives the hot path.
+
+Public surface, loss definitions and schedule follow GAN_models/wind_field_GAN_3D.py of the reference
+(constructor :30-205, ``feed_xy_niter`` :207-219, ``optimize_parameters`` / ``validation`` :621-625, loss
+dicts :680-693, ``update_learning_rate`` :695-697, ``count_params`` :699-712).  What differs is *how* the step
+is executed:
+
+* G and D are the drop-in modules running on ``libwindsr.so``;
+* the pixel loss, both 9-channel Jacobians, the 8 global maxes and the 4 MSE sums are ONE fused stencil pass
+  (``ops.WindLossFn``); the scalar formula on top is a handful of 0-d tensor ops;
+* the schedule is decided from the host-side iteration counter and the 8 ``isnan/isinf`` probes collapse to a
+  single host read per G step (the reference syncs >= 9 times per step);
+* label noise is sampled on the device;
+* with ``torch.distributed`` initialised the step is batch-sharded data parallel: gradients of the network
+  being updated are averaged with a bucketed NCCL all-reduce overlapped with backward (``parallel.GradSync``).
+  BatchNorm statistics, RaGAN batch means and the loss normalisers stay per-rank (stock DDP semantics; see
+  DESIGN.md §multi-GPU for the exactness statement).
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.optim.lr_scheduler as lr_scheduler
+
+from .. import ops
+from ..CNN_models.Discriminator_3D import Discriminator_3D
+from ..CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+from ..parallel import GradSync
+from ..tools import initialization, trainingtricks
+from .baseGAN import BaseGAN
+
+_G_LOSS_KEYS = ("total", "adversarial", "pix", "xy_gradient", "z_gradient", "divergence", "xy_divergence",
+                "feature_D")
+
+
+def _zero():
+    return torch.zeros(1)
+
+
+class wind_field_GAN_3D(BaseGAN):
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.train_G_loss_dict = {k: _zero() for k in _G_LOSS_KEYS}
+        self.validation_G_loss_dict = {k: _zero() for k in _G_LOSS_KEYS}
+        self.D_loss_dict = {"train_loss": _zero(), "validation_loss": _zero()}
+        self.hist_dict = {k: _zero() for k in ("val_grad_G_first_layer", "val_grad_G_last_layer",
+                                               "val_weight_G_first_layer", "val_weight_G_last_layer",
+                                               "SR_pix_distribution", "D_pred_HR", "D_pred_SR")}
+        for k in ("val_grad_D_first_layer", "val_grad_D_last_layer", "val_weight_D_first_layer",
+                  "val_weight_D_last_layer"):
+            self.hist_dict[k] = torch.tensor(-1.0)
+        self.metrics_dict = {k: _zero() for k in ("val_PSNR", "Trilinear_PSNR", "pix_loss_unscaled",
+                                                  "trilinear_pix_loss")}
+        self.batch_size = 1
+        self.max_diff_squared = torch.tensor(4.0, device=self.device)  # HR is in [-1, 1]
+        self.epsilon_PSNR = torch.tensor(1e-8, device=self.device)
+        self.feature_extractor = None
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+
+        g, gan = cfg.generator, cfg.gan_config
+        in_ch = (g.in_num_ch + int(bool(gan.include_pressure)) + int(bool(gan.include_z_channel))
+                 + int(bool(gan.include_above_ground_channel)))
+        self.G = Generator_3D(
+            in_ch, g.out_num_ch, g.num_features, g.num_RRDB, upscale=cfg.scale, hr_kern_size=g.hr_kern_size,
+            number_of_RDB_convs=g.num_RDB_convs, RDB_gc=g.RDB_growth_chan, lff_kern_size=g.lff_kern_size,
+            RDB_residual_scaling=g.RDB_res_scaling, RRDB_residual_scaling=g.RRDB_res_scaling,
+            act_type=g.act_type, device=self.device, number_of_z_layers=gan.number_of_z_layers,
+            conv_mode=gan.conv_mode, use_mixed_precision=g.use_mixed_precision,
+            terrain_number_of_features=g.terrain_number_of_features,
+            dropout_probability=g.dropout_probability, max_norm=g.max_norm,
+        ).to(self.device, non_blocking=True)
+        initialization.init_weights(self.G, scale=g.weight_init_scale)
+        self.conv_mode = g.conv_mode
+        self.use_D_feature_extractor_cost = gan.use_D_feature_extractor_cost
+        self.D = None
+        self.sync_G = self.sync_D = None
+        if not cfg.is_train:
+            return
+
+        d = cfg.discriminator
+        self.D = Discriminator_3D(
+            d.in_num_ch, d.num_features, feat_kern_size=d.feat_kern_size, normalization_type=d.norm_type,
+            act_type=d.act_type, mode=d.layer_mode, device=self.device,
+            number_of_z_layers=gan.number_of_z_layers, conv_mode=gan.conv_mode,
+            use_mixed_precision=d.use_mixed_precision, enable_slicing=gan.enable_slicing,
+            dropout_probability=d.dropout_probability,
+        ).to(self.device, non_blocking=True)
+        initialization.init_weights(self.D, scale=d.weight_init_scale)
+
+        t = cfg.training
+        self.optimizer_G = torch.optim.Adam(self.G.parameters(), lr=t.learning_rate_g,
+                                            weight_decay=t.adam_weight_decay_g, betas=(t.adam_beta1_g, 0.999))
+        self.optimizer_D = torch.optim.Adam(self.D.parameters(), lr=t.learning_rate_d,
+                                            weight_decay=t.adam_weight_decay_d, betas=(t.adam_beta1_d, 0.999))
+        self.optimizers += [self.optimizer_G, self.optimizer_D]
+        if t.multistep_lr_steps:
+            self.scheduler_G = lr_scheduler.MultiStepLR(self.optimizer_G, t.multistep_lr_steps, gamma=t.lr_gamma)
+            self.scheduler_D = lr_scheduler.MultiStepLR(self.optimizer_D, t.multistep_lr_steps, gamma=t.lr_gamma)
+            self.schedulers += [self.scheduler_G, self.scheduler_D]
+        if t.pixel_criterion in (None, "none"):
+            self.pixel_criterion = None
+        elif t.pixel_criterion in ("l1", "l2"):
+            self.pixel_criterion = t.pixel_criterion
+        else:
+            raise NotImplementedError("Only l1 and l2 (MSE) loss have been implemented for pixel loss, not "
+                                      f"{t.pixel_criterion}")
+        if t.gan_type not in ("relativistic", "relativisticavg"):
+            raise NotImplementedError(f"Only relativistic and relativisticavg GAN are implemented, not {t.gan_type}")
+        self.criterion = nn.BCEWithLogitsLoss()
+        if self.world_size > 1:
+            self.sync_G = GradSync(self.G.parameters())
+            self.sync_D = GradSync(self.D.parameters())
+
+    # ---------------------------------------------------------------------------------------------------
+    def feed_xy_niter(self, x, y, niter, d_g_train_ratio, d_g_train_period):
+        self.x, self.y = x, y
+        self.niter = niter
+        self._niter_host = int(niter)
+        self.d_g_train_ratio = d_g_train_ratio
+        self.d_g_train_period = d_g_train_period
+
+    # ---------------------------------------------------------------------------------------------------
+    def _noise(self, sigma, shape, it):
+        return trainingtricks.instance_noise(torch.tensor(sigma, device=self.device), shape, it, self.niter,
+                                             device=self.device)
+
+    def D_forward(self, HR, fake_HR, it, train_D: bool):
+        """D on the real and generated batch (wind_field_GAN_3D.py:221-304): train mode + sigma 1 noise in D
+        steps; eval mode (BN running stats, no dropout) + sigma 2 noise, real branch detached, in G steps."""
+        noisy = self.cfg.training.use_instance_noise
+        if train_D:
+            self.D.train()
+            y_pred = self.D(HR + self._noise(1.0, HR.size(), it) if noisy else HR).squeeze()
+            fake_in = fake_HR.detach()
+            return y_pred, self.D(fake_in + self._noise(1.0, HR.size(), it) if noisy else fake_in).squeeze()
+        self.D.eval()
+        with torch.no_grad():
+            y_pred = self.D(HR + self._noise(2.0, HR.size(), it) if noisy else HR).squeeze()
+        return y_pred, self.D(fake_HR + self._noise(2.0, HR.size(), it) if noisy else fake_HR).squeeze()
+
+    # ---------------------------------------------------------------------------------------------------
+    def _adversarial(self, first, second, generator_side: bool):
+        """relativistic / relativistic-average BCE terms (wind_field_GAN_3D.py:353-368, 545-563)."""
+        kind = self.cfg.training.gan_type
+        if kind == "relativistic":
+            return self.criterion(first - second, self.HR_labels)
+        return (self.criterion(first - torch.mean(second), self.HR_labels)
+                + self.criterion(second - torch.mean(first), self.fake_HR_labels)) / 2.0
+
+    def wind_loss_terms(self, HR, fake_HR, Z):
+        """pixel + the four physics terms, unweighted, from one fused stencil pass.
+        Returns (pix, xy_gradient, z_gradient, divergence, xy_divergence)."""
+        if HR.shape[1] != 3 or fake_HR.shape[1] != 3:
+            raise NotImplementedError("the fused wind loss expects exactly the 3 wind components (all shipped "
+                                      "configs: out_num_ch = 3)")
+        s = ops.windloss_slots(HR, fake_HR, Z, self.x, self.y)
+        cnt = float(HR.shape[0] * HR.shape[2] * HR.shape[3] * HR.shape[4])
+        norm = [torch.maximum(s[6 + 2 * k], s[7 + 2 * k] / 100) for k in range(4)]
+        xy = s[0] / (6.0 * cnt) / (norm[0] * norm[0])
+        zg = s[1] / (3.0 * cnt) / (norm[1] * norm[1])
+        div = s[2] / cnt / (norm[2] * norm[2])
+        dxy = s[3] / cnt / (norm[3] * norm[3])
+        if self.pixel_criterion == "l1":
+            pix = s[4] / (3.0 * cnt)
+        elif self.pixel_criterion == "l2":
+            pix = s[5] / (3.0 * cnt)
+        else:
+            pix = torch.zeros((), device=self.device)
+        return pix, xy, zg, div, dxy
+
+    def calculate_optimize_and_log_G_loss(self, HR, fake_HR, Z, y_pred, fake_y_pred, training_iteration: bool):
+        t = self.cfg.training
+        adv = self._adversarial(fake_y_pred, y_pred, True) * t.adversarial_loss_weight
+        feat = torch.zeros(1, device=self.device)
+        if self.feature_extractor is not None:
+            with torch.no_grad():
+                f_real = self.feature_extractor(HR)
+            feat = F.mse_loss(self.feature_extractor(fake_HR).float(), f_real.float())
+        feat = feat * t.feature_D_loss_weight
+        pix, xy, zg, div, dxy = self.wind_loss_terms(HR, fake_HR, Z)
+        pix = pix * t.pixel_loss_weight
+        xy = xy * t.gradient_xy_loss_weight
+        zg = zg * t.gradient_z_loss_weight
+        div = div * t.divergence_loss_weight
+        dxy = dxy * t.xy_divergence_loss_weight
+        base = adv + pix + feat
+        physics = xy + zg + div + dxy
+        # one host read decides both guards of the reference (:434-443 and :457)
+        ok_physics, ok_base = torch.stack([torch.isfinite(physics).all(), torch.isfinite(base).all()]).tolist()
+        loss_G = base + physics if ok_physics else base
+        if training_iteration:
+            if self.sync_G is not None:
+                self.sync_G.begin()
+            loss_G.backward()
+            if self.sync_G is not None:
+                self.sync_G.finish()
+            if ok_base:  # loss_G is finite (the reference's second guard, :457)
+                self.optimizer_G.step()
+        d = self.train_G_loss_dict if training_iteration else self.validation_G_loss_dict
+        d.update(total=loss_G, adversarial=adv, pix=pix, xy_gradient=xy, z_gradient=zg, divergence=div,
+                 xy_divergence=dxy, feature_D=feat)
+        if not training_iteration:
+            self.metrics_dict["pix_loss_unscaled"] = pix / t.pixel_loss_weight
+            self.hist_dict["SR_pix_distribution"] = fake_HR.detach().cpu().numpy()
+        return loss_G
+
+    def update_G(self, LR, HR, Z, it, training_iteration: bool):
+        if training_iteration:
+            self.G.train()
+            fake_HR = self.G(LR, Z)
+            for p in self.D.parameters():
+                p.requires_grad = False
+            self.G.zero_grad(set_to_none=True)
+            y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
+            self.calculate_optimize_and_log_G_loss(HR, fake_HR, Z, y_pred, fake_y_pred, True)
+        else:
+            self.G.eval()
+            with torch.no_grad():
+                fake_HR = self.G(LR, Z)
+                y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
+                self.calculate_optimize_and_log_G_loss(HR, fake_HR, Z, y_pred, fake_y_pred, False)
+        return fake_HR
+
+    def update_D(self, HR, fake_HR, it, training_epoch: bool):
+        if training_epoch:
+            for p in self.D.parameters():
+                p.requires_grad = True
+            self.optimizer_D.zero_grad(set_to_none=True)
+            y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=True)
+        else:
+            with torch.no_grad():  # the reference validates D in train mode too (:542-543)
+                y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=True)
+        loss_D = self._adversarial(y_pred, fake_y_pred, False)
+        if self.cfg.training.gan_type == "relativisticavg" and self._labels_are_exactly_point_nine:
+            loss_D = loss_D - 0.1985
+        if training_epoch:
+            if self.sync_D is not None:
+                self.sync_D.begin()
+            loss_D.backward()
+            if self.sync_D is not None:
+                self.sync_D.finish()
+            self.optimizer_D.step()
+        if training_epoch:
+            self.D_loss_dict["train_loss"] = loss_D
+        else:
+            self.D_loss_dict["validation_loss"] = loss_D
+            self.hist_dict["D_pred_HR"] = torch.sigmoid(y_pred.detach()).cpu().numpy()[None]
+            self.hist_dict["D_pred_SR"] = torch.sigmoid(fake_y_pred.detach()).cpu().numpy()[None]
+
+    # ---------------------------------------------------------------------------------------------------
+    def is_G_iteration(self, it: int) -> bool:
+        """Alternating blocks of ``d_g_train_period`` iterations (wind_field_GAN_3D.py:585-587)."""
+        return (int(it) // self.d_g_train_period) % (self.d_g_train_ratio + 1) == 0
+
+    def compute_losses_and_optimize(self, LR, HR, Z, it, training_iteration: bool = False):
+        self.batch_size = HR.size(0)
+        it_host = int(it)
+        it_dev = torch.tensor(float(it_host), device=self.device)
+        self.make_new_labels(it_host)
+        if self.use_D_feature_extractor_cost and it_host % self.cfg.training.feature_D_update_period == 0:
+            self.feature_extractor = copy.deepcopy(self.D.features)
+            for p in self.feature_extractor.parameters():
+                p.requires_grad = False
+        if training_iteration:
+            if self.is_G_iteration(it_host):
+                self.update_G(LR, HR, Z, it_dev, True)
+            else:
+                with torch.no_grad():
+                    self.G.eval()
+                    fake_HR = self.G(LR, Z)
+                self.update_D(HR, fake_HR, it_dev, True)
+            return
+        fake_HR = self.update_G(LR, HR, Z, it_dev, False)
+        self.update_D(HR, fake_HR, it_dev, False)
+        (self.metrics_dict["val_PSNR"], self.metrics_dict["Trilinear_PSNR"]) = compute_PSNR_for_SR_and_trilinear(
+            LR, HR, fake_HR, self.max_diff_squared, self.epsilon_PSNR, interpolate=True, device=self.device,
+            scale=self.cfg.scale)
+        tri = F.interpolate(LR[:, :3], scale_factor=(self.cfg.scale, self.cfg.scale, 1), mode="trilinear",
+                            align_corners=True)
+        self.metrics_dict["trilinear_pix_loss"] = (F.l1_loss(HR, tri) if self.pixel_criterion != "l2"
+                                                   else F.mse_loss(HR, tri))
+
+    def optimize_parameters(self, LR, HR, Z, it):
+        self.compute_losses_and_optimize(LR, HR, Z, it, training_iteration=True)
+
+    def validation(self, LR, HR, Z, it):
+        self.compute_losses_and_optimize(LR, HR, Z, it, training_iteration=False)
+
+    # ---------------------------------------------------------------------------------------------------
+    def make_new_labels(self, it):
+        """Real / fake target vectors (wind_field_GAN_3D.py:627-678): optional flip, one-sided smoothing that
+        anneals 0.9 -> 1.0 over ``niter``, optional Gaussian label noise."""
+        t = self.cfg.training
+        real_is_true = not t.flip_labels
+        real, fake = 1.0, 0.0
+        frac = float(it) / float(self._niter_host)
+        if t.use_one_sided_label_smoothing and t.flip_labels:
+            fake = 0.1 - 0.1 * frac
+        elif t.use_one_sided_label_smoothing:
+            real = 0.9 + 0.1 * frac
+        std = 0.05 if t.use_noisy_labels else 0.0
+        mk = lambda kind: trainingtricks.noisy_labels(kind, self.batch_size, noise_stddev=std,
+                                                      true_label_val=real, false_label_val=fake,
+                                                      device=self.device).squeeze()
+        self.HR_labels = mk(real_is_true)
+        self.fake_HR_labels = mk(not real_is_true)
+        if std == 0.0:
+            # float32(0.9 + 0.1*frac) == float32(0.9) exactly as the reference's device-side comparison sees it
+            target = (real if real_is_true else fake)
+            self._labels_are_exactly_point_nine = bool(torch.tensor(target, dtype=torch.float32)
+                                                       == torch.tensor(0.9, dtype=torch.float32))
+        else:
+            self._labels_are_exactly_point_nine = bool(torch.all(self.HR_labels == 0.9))
+
+    # ---------------------------------------------------------------------------------------------------
+    def get_G_train_loss_dict_ref(self):
+        return self.train_G_loss_dict
+
+    def get_G_val_loss_dict_ref(self):
+        return self.validation_G_loss_dict
+
+    def get_D_loss_dict_ref(self):
+        return self.D_loss_dict
+
+    def get_hist_dict_ref(self):
+        return self.hist_dict
+
+    def get_metrics_dict_ref(self):
+        return self.metrics_dict
+
+    def update_learning_rate(self):
+        for s in self.schedulers:
+            s.step()
+
+    def count_params(self):
+        return (sum(p.numel() for p in self.G.parameters()), sum(p.numel() for p in self.D.parameters()))
+
+    def count_trainable_params(self):
+        return (sum(p.numel() for p in self.G.parameters() if p.requires_grad),
+                sum(p.numel() for p in self.D.parameters() if p.requires_grad))
+
+    def __str__(self):
+        g, d = self.count_params()
+        gt, dt = self.count_trainable_params()
+        bar = "*---------------*"
+        return (f"{bar}\nGenerator:\n{g} params, {gt} trainable\n\n{self.G}\n\n"
+                f"{bar}\nDiscriminator:\n{d} params, {dt} trainable\n\n{self.D}\n")
+
+
+def calculate_PSNR(HR, fake_HR, max_diff_squared=torch.tensor(4.0), epsilon_PSNR=torch.tensor(1e-8),
+                   device=torch.device("cpu")):
+    """10 log10(max^2 / (batch-mean squared error + eps)) (wind_field_GAN_3D.py:730-742), kept on device."""
+    voxels = HR.shape[0] * HR.shape[2] * HR.shape[3] * HR.shape[4]
+    mse = torch.sum((HR - fake_HR) ** 2) / voxels
+    return 10.0 * torch.log10(max_diff_squared / (mse + epsilon_PSNR))
+
+
+def compute_PSNR_for_SR_and_trilinear(LR, HR, fake_HR, max_diff_squared, epsilon_PSNR, interpolate=False,
+                                      device=torch.device("cpu"), scale=4):
+    psnr = calculate_PSNR(HR, fake_HR, max_diff_squared, epsilon_PSNR, device=device)
+    if not interpolate:
+        return psnr
+    tri = F.interpolate(LR[:, :3], scale_factor=(scale, scale, 1), mode="trilinear", align_corners=True)
+    return psnr, calculate_PSNR(HR, tri, max_diff_squared, epsilon_PSNR, device=device)
+
+
+def get_norm_factors_of_gradients(HR_wind_gradient, SR_wind_gradient):
+    """The four loss normalisers from materialised Jacobians (wind_field_GAN_3D.py:773-814); the training step
+    itself uses the fused slots instead.  Note the z-gradient max is taken WITHOUT abs, like the reference."""
+
+    def div(g):
+        return g[:, 0] + g[:, 4] + g[:, 8]
+
+    def dxy(g):
+        return g[:, 0] + g[:, 4]
+
+    pairs = [
+        (HR_wind_gradient[:, :6].abs().max(), SR_wind_gradient[:, :6].abs().max()),
+        (HR_wind_gradient[:, 6:].max(), SR_wind_gradient[:, 6:].max()),
+        (div(HR_wind_gradient).abs().max(), div(SR_wind_gradient).abs().max()),
+        (dxy(HR_wind_gradient).abs().max(), dxy(SR_wind_gradient).abs().max()),
+    ]
+    return [torch.max(h, s / 100) for h, s in pairs]

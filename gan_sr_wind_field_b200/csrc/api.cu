@@ -1,0 +1,305 @@
+// api.cu — the extern "C" boundary declared in include/windsr.h: argument validation, path selection
+// (CUDA-core FFMA vs tcgen05) and launch.  No torch types, no allocation, no exceptions cross this file.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace ws {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int validate_shape(const ws_conv_shape* s) {
+  WS_REQUIRE(s != nullptr, "null conv shape");
+  WS_REQUIRE(s->n > 0 && s->x > 0 && s->y > 0 && s->z > 0, "conv shape: non-positive volume");
+  WS_REQUIRE(s->cin > 0 && s->cout > 0, "conv shape: non-positive channels");
+  WS_REQUIRE(s->kx > 0 && s->ky > 0 && s->kz > 0 && s->sx > 0 && s->sy > 0 && s->sz > 0,
+             "conv shape: bad kernel/stride");
+  WS_REQUIRE(s->px >= 0 && s->py >= 0 && s->pz >= 0, "conv shape: negative padding");
+  WS_REQUIRE(s->x + 2 * s->px >= s->kx && s->y + 2 * s->py >= s->ky && s->z + 2 * s->pz >= s->kz,
+             "conv shape: kernel larger than padded input");
+  return 0;
+}
+
+// implemented in the other translation units
+int simt_conv_fwd(const ConvGeom&, const View&, const float*, const View&, const Epi&, cudaStream_t);
+int simt_conv_dgrad(const ConvGeom&, const View&, const float*, const View&, const Epi&, cudaStream_t);
+int simt_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
+size_t simt_wgrad_workspace_bytes(const ConvGeom&);
+int bias_grad(const View&, float*, int, int, long long, int, cudaStream_t);
+bool tc_view_ok(const View&, int);
+int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t);
+int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
+size_t tc_wgrad_workspace_bytes(const ConvGeom&);
+int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
+int copy_launch(const View&, const View&, int, int, long long, cudaStream_t);
+int axpby_launch(const View&, float, const View&, float, const View&, int, int, long long, cudaStream_t);
+int lrelu_bwd_launch(const View&, const View&, float, const float*, const float*, const View&, int, int,
+                     long long, cudaStream_t);
+int upsample_fwd_launch(const View&, const View&, int, int, int, int, int, cudaStream_t);
+int upsample_bwd_launch(const View&, const View&, int, int, int, int, int, cudaStream_t);
+int bn_finalize_launch(const float*, const float*, long long, int, const float*, const float*, float, float,
+                       float*, float*, float*, float*, float*, float*, cudaStream_t);
+int scale_shift_lrelu_launch(const View&, const float*, const float*, float, const View&, int, int, long long,
+                             cudaStream_t);
+int bn_bwd_reduce_launch(const View&, const View&, const View&, const float*, const float*, float, float*,
+                         float*, int, int, long long, cudaStream_t);
+int bn_bwd_apply_launch(const View&, const View&, const View&, const float*, const float*, const float*,
+                        const float*, const float*, float, long long, const View&, int, int, long long,
+                        cudaStream_t);
+int axis_coeffs_launch(const float*, int, float*, cudaStream_t);
+int wind_gradient_launch(const View&, const View&, const float*, const float*, const View&, int, int, int, int,
+                         cudaStream_t);
+int windloss_fwd_launch(const View&, const View&, const View&, const float*, const float*, int, int, int, int,
+                        float*, long long*, cudaStream_t);
+int windloss_bwd_launch(const View&, const View&, const View&, const float*, const float*, int, int, int, int,
+                        const float*, const long long*, const View&, void*, size_t, cudaStream_t);
+
+static int device_cc_major() {
+  static int major = -1;
+  if (major < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    major = prop.major;
+  }
+  return major;
+}
+
+// Bring-up / bisection switches (read once): WS_DISABLE_TC=1 forces the CUDA-core family everywhere,
+// WS_DISABLE_TC_{FWD,DGRAD,WGRAD,STRIDED}=1 do so for one kernel class.
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+static bool tc_disabled(const char* which) {
+  static const bool all = env_flag("WS_DISABLE_TC");
+  static const bool fwd = env_flag("WS_DISABLE_TC_FWD"), dgrad = env_flag("WS_DISABLE_TC_DGRAD");
+  static const bool wgrad = env_flag("WS_DISABLE_TC_WGRAD"), strided = env_flag("WS_DISABLE_TC_STRIDED");
+  if (all) return true;
+  switch (which[0]) {
+    case 'f': return fwd;
+    case 'd': return dgrad;
+    case 'w': return wgrad;
+    case 's': return strided;
+  }
+  return false;
+}
+static bool is_strided(const ConvGeom& g) { return g.sx != 1 || g.sy != 1 || g.sz != 1; }
+
+static int fwd_path(const ConvGeom& g, const View& in, int math) {
+  if (math != WS_MATH_BF16) return WS_PATH_SIMT;
+  if (tc_disabled("fwd") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
+  if (device_cc_major() != 10) return WS_PATH_SIMT;
+  if (!tc_view_ok(in, g.cin)) return WS_PATH_SIMT;
+  if (g.zo > 128) return WS_PATH_SIMT;
+  return WS_PATH_TCGEN05;
+}
+static int dgrad_path(const ConvGeom& g, const View& dy, int math) {
+  if (math != WS_MATH_BF16) return WS_PATH_SIMT;
+  if (tc_disabled("dgrad")) return WS_PATH_SIMT;
+  if (device_cc_major() != 10) return WS_PATH_SIMT;
+  if (g.sx != 1 || g.sy != 1 || g.sz != 1) return WS_PATH_SIMT;
+  if (!tc_view_ok(dy, g.cout)) return WS_PATH_SIMT;
+  if (g.z > 128) return WS_PATH_SIMT;
+  return WS_PATH_TCGEN05;
+}
+static int wgrad_path(const ConvGeom& g, const View& in, const View& dy, int math) {
+  if (math != WS_MATH_BF16) return WS_PATH_SIMT;
+  if (tc_disabled("wgrad") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
+  if (device_cc_major() != 10) return WS_PATH_SIMT;
+  if (!tc_view_ok(in, g.cin) || !tc_view_ok(dy, g.cout)) return WS_PATH_SIMT;
+  if (g.cin > 256 && g.cout > 256) return WS_PATH_SIMT;
+  return WS_PATH_TCGEN05;
+}
+
+}  // namespace ws
+
+using namespace ws;
+
+extern "C" {
+
+int ws_version(void) { return WS_VERSION; }
+const char* ws_last_error(void) { return g_err; }
+int ws_device_supports_tcgen05(void) { return device_cc_major() == 10 ? 1 : 0; }
+
+size_t ws_packed_weight_bytes(const ws_conv_shape* s, int kind) {
+  if (!s) return 0;
+  size_t taps = (size_t)s->kx * s->ky * s->kz;
+  switch (kind) {
+    case WS_PACK_SIMT_FWD:
+    case WS_PACK_SIMT_DGRAD:
+      return taps * s->cin * s->cout * sizeof(float);
+    case WS_PACK_TC_FWD:
+      return taps * (size_t)((s->cout + 15) / 16 * 16) * (size_t)((s->cin + 7) / 8 * 8) * 2;
+    case WS_PACK_TC_DGRAD:
+      return taps * (size_t)((s->cin + 15) / 16 * 16) * (size_t)((s->cout + 7) / 8 * 8) * 2;
+  }
+  return 0;
+}
+
+int ws_pack_weights(const float* w, const ws_conv_shape* s, int kind, void* packed, void* stream) {
+  if (int e = validate_shape(s)) return e;
+  WS_REQUIRE(w && packed, "ws_pack_weights: null pointer");
+  WS_REQUIRE(kind >= WS_PACK_SIMT_FWD && kind <= WS_PACK_TC_DGRAD, "ws_pack_weights: bad kind %d", kind);
+  return pack_weights_launch(w, ConvGeom(*s), kind, packed, (cudaStream_t)stream);
+}
+
+int ws_conv3d_fwd_path(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* out, int math) {
+  if (validate_shape(s) || !in) return WS_PATH_NONE;
+  (void)out;
+  return fwd_path(ConvGeom(*s), View(in), math);
+}
+int ws_conv3d_dgrad_path(const ws_conv_shape* s, const ws_tensor* dy, const ws_tensor* dx, int math) {
+  if (validate_shape(s) || !dy) return WS_PATH_NONE;
+  (void)dx;
+  return dgrad_path(ConvGeom(*s), View(dy), math);
+}
+int ws_conv3d_wgrad_path(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, int math) {
+  if (validate_shape(s) || !in || !dy) return WS_PATH_NONE;
+  return wgrad_path(ConvGeom(*s), View(in), View(dy), math);
+}
+
+int ws_conv3d_fwd(const ws_conv_shape* s, const ws_tensor* in, const void* packed_w, const ws_tensor* out,
+                  const ws_epilogue* ep, int math, void* stream) {
+  if (int e = validate_shape(s)) return e;
+  WS_REQUIRE(in && in->ptr && out && out->ptr && packed_w, "ws_conv3d_fwd: null pointer");
+  ConvGeom g(*s);
+  View vin(in), vout(out);
+  Epi e(ep, g.cout);
+  if (fwd_path(g, vin, math) == WS_PATH_TCGEN05)
+    return tc_conv_launch(g, 0, vin, packed_w, vout, e, (cudaStream_t)stream);
+  return simt_conv_fwd(g, vin, (const float*)packed_w, vout, e, (cudaStream_t)stream);
+}
+
+int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* packed_w, const ws_tensor* dx,
+                    const ws_epilogue* ep, int math, void* stream) {
+  if (int e = validate_shape(s)) return e;
+  WS_REQUIRE(dy && dy->ptr && dx && dx->ptr && packed_w, "ws_conv3d_dgrad: null pointer");
+  ConvGeom g(*s);
+  View vdy(dy), vdx(dx);
+  Epi e(ep, g.cin);
+  if (dgrad_path(g, vdy, math) == WS_PATH_TCGEN05)
+    return tc_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
+  return simt_conv_dgrad(g, vdy, (const float*)packed_w, vdx, e, (cudaStream_t)stream);
+}
+
+size_t ws_conv3d_wgrad_workspace_bytes(const ws_conv_shape* s, int math) {
+  if (!s) return 0;
+  (void)math;
+  ws_conv_shape t = *s;
+  return (size_t)t.kx * t.ky * t.kz * t.cin * t.cout * sizeof(float);
+}
+
+int ws_conv3d_wgrad(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, float* dw, float* db,
+                    int accumulate, int math, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = validate_shape(s)) return e;
+  WS_REQUIRE(in && in->ptr && dy && dy->ptr, "ws_conv3d_wgrad: null pointer");
+  ConvGeom g(*s);
+  View vin(in), vdy(dy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (db) {
+    if (int e = bias_grad(vdy, db, g.n, g.cout, g.vout(), accumulate, st)) return e;
+  }
+  if (!dw) return 0;
+  if (wgrad_path(g, vin, vdy, math) == WS_PATH_TCGEN05)
+    return tc_conv_wgrad(g, vin, vdy, dw, accumulate, workspace, workspace_bytes, st);
+  return simt_conv_wgrad(g, vin, vdy, dw, accumulate, workspace, workspace_bytes, st);
+}
+
+int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,
+                               void* stream) {
+  WS_REQUIRE(in && in->ptr && out && out->ptr, "ws_upsample_nearest_xy_fwd: null pointer");
+  return upsample_fwd_launch(View(in), View(out), n, c, x, y, z, (cudaStream_t)stream);
+}
+int ws_upsample_nearest_xy_bwd(const ws_tensor* dout, const ws_tensor* din, int n, int c, int x, int y, int z,
+                               void* stream) {
+  WS_REQUIRE(dout && dout->ptr && din && din->ptr, "ws_upsample_nearest_xy_bwd: null pointer");
+  return upsample_bwd_launch(View(dout), View(din), n, c, x, y, z, (cudaStream_t)stream);
+}
+
+int ws_copy(const ws_tensor* src, const ws_tensor* dst, int n, int c, int64_t v, void* stream) {
+  WS_REQUIRE(src && src->ptr && dst && dst->ptr, "ws_copy: null pointer");
+  return copy_launch(View(src), View(dst), n, c, v, (cudaStream_t)stream);
+}
+int ws_axpby(const ws_tensor* x1, float a, const ws_tensor* x2, float b, const ws_tensor* y, int n, int c,
+             int64_t v, void* stream) {
+  WS_REQUIRE(x1 && x1->ptr && y && y->ptr, "ws_axpby: null pointer");
+  return axpby_launch(View(x1), a, View(x2), b, View(y), n, c, v, (cudaStream_t)stream);
+}
+int ws_lrelu_bwd(const ws_tensor* dy, const ws_tensor* y, float slope, const float* chan_scale,
+                 const float* oscale, const ws_tensor* g, int n, int c, int64_t v, void* stream) {
+  WS_REQUIRE(dy && dy->ptr && y && y->ptr && g && g->ptr, "ws_lrelu_bwd: null pointer");
+  return lrelu_bwd_launch(View(dy), View(y), slope, chan_scale, oscale, View(g), n, c, v, (cudaStream_t)stream);
+}
+
+int ws_bn_finalize(const float* sum, const float* sqsum, int64_t count, int c, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  WS_REQUIRE(sum && sqsum && scale && shift && c > 0 && count > 0, "ws_bn_finalize: bad arguments");
+  return bn_finalize_launch(sum, sqsum, count, c, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                            shift, save_mean, save_invstd, (cudaStream_t)stream);
+}
+int ws_scale_shift_lrelu(const ws_tensor* x, const float* scale, const float* shift, float slope,
+                         const ws_tensor* y, int n, int c, int64_t v, void* stream) {
+  WS_REQUIRE(x && x->ptr && y && y->ptr && scale && shift, "ws_scale_shift_lrelu: null pointer");
+  return scale_shift_lrelu_launch(View(x), scale, shift, slope, View(y), n, c, v, (cudaStream_t)stream);
+}
+int ws_bn_lrelu_bwd_reduce(const ws_tensor* dy, const ws_tensor* y, const ws_tensor* x, const float* mean,
+                           const float* invstd, float slope, float* sum_g, float* sum_gx, int n, int c,
+                           int64_t v, void* stream) {
+  WS_REQUIRE(dy && y && x && mean && invstd && sum_g && sum_gx, "ws_bn_lrelu_bwd_reduce: null pointer");
+  return bn_bwd_reduce_launch(View(dy), View(y), View(x), mean, invstd, slope, sum_g, sum_gx, n, c, v,
+                              (cudaStream_t)stream);
+}
+int ws_bn_lrelu_bwd_apply(const ws_tensor* dy, const ws_tensor* y, const ws_tensor* x, const float* mean,
+                          const float* invstd, const float* gamma, const float* sum_g, const float* sum_gx,
+                          float slope, int64_t count, const ws_tensor* dx, int n, int c, int64_t v,
+                          void* stream) {
+  WS_REQUIRE(dy && y && x && dx && mean && invstd && sum_g && sum_gx, "ws_bn_lrelu_bwd_apply: null pointer");
+  return bn_bwd_apply_launch(View(dy), View(y), View(x), mean, invstd, gamma, sum_g, sum_gx, slope, count,
+                             View(dx), n, c, v, (cudaStream_t)stream);
+}
+
+int ws_axis_coeffs(const float* coords, int len, float* coef, void* stream) {
+  WS_REQUIRE(coords && coef && len > 0, "ws_axis_coeffs: bad arguments");
+  return axis_coeffs_launch(coords, len, coef, (cudaStream_t)stream);
+}
+int ws_wind_gradient(const ws_tensor* field, const ws_tensor* zalt, const float* coef_x, const float* coef_y,
+                     const ws_tensor* out, int n, int x, int y, int z, void* stream) {
+  WS_REQUIRE(field && field->ptr && zalt && zalt->ptr && out && out->ptr && coef_x && coef_y,
+             "ws_wind_gradient: null pointer");
+  return wind_gradient_launch(View(field), View(zalt), coef_x, coef_y, View(out), n, x, y, z,
+                              (cudaStream_t)stream);
+}
+int ws_windloss_fwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* zalt, const float* coef_x,
+                    const float* coef_y, int n, int x, int y, int z, float* result, int64_t* argmax,
+                    void* stream) {
+  WS_REQUIRE(hr && hr->ptr && sr && sr->ptr && zalt && zalt->ptr && coef_x && coef_y && result,
+             "ws_windloss_fwd: null pointer");
+  WS_REQUIRE((reinterpret_cast<uintptr_t>(result) & 7) == 0, "ws_windloss_fwd: result must be 8-byte aligned");
+  return windloss_fwd_launch(View(hr), View(sr), View(zalt), coef_x, coef_y, n, x, y, z, result,
+                             (long long*)argmax, (cudaStream_t)stream);
+}
+size_t ws_windloss_bwd_workspace_bytes(int n, int x, int y, int z) {
+  return (size_t)n * x * y * z * 9 * sizeof(float);
+}
+int ws_windloss_bwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* zalt, const float* coef_x,
+                    const float* coef_y, int n, int x, int y, int z, const float* coef, const int64_t* argmax,
+                    const ws_tensor* dsr, void* workspace, size_t workspace_bytes, void* stream) {
+  WS_REQUIRE(hr && hr->ptr && sr && sr->ptr && zalt && zalt->ptr && coef_x && coef_y && coef && dsr && dsr->ptr,
+             "ws_windloss_bwd: null pointer");
+  return windloss_bwd_launch(View(hr), View(sr), View(zalt), coef_x, coef_y, n, x, y, z, coef,
+                             (const long long*)argmax, View(dsr), workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+}  // extern "C"

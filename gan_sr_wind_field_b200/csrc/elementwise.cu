@@ -1,0 +1,499 @@
+// elementwise.cu — HBM-bound helpers around the convolutions: weight packing, strided/dtype copies
+// (the dense-concat and layout changes of torch_blocks.py:214,286 / Generator…py:228), axpby, LeakyReLU
+// backward, the x/y nearest upsample and its 2x2 block-sum backward (torch_blocks.py:347), and the
+// BatchNorm3d statistics finalize / apply / backward (torch_blocks.py:24-25).
+#include "common.cuh"
+
+namespace ws {
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(long long total, int per_thread = 1) {
+  long long b = (total + (long long)kBlock * per_thread - 1) / ((long long)kBlock * per_thread);
+  long long cap = 148LL * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------
+// w: (cout, cin, taps) fp32
+__global__ void pack_simt(const float* __restrict__ w, float* __restrict__ p, int cout, int cin, int taps,
+                          int dgrad) {
+  long long total = (long long)cout * cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the packed array
+    if (!dgrad) {  // [tap][cin][cout]
+      int co = (int)(i % cout);
+      long long r = i / cout;
+      int ci = (int)(r % cin);
+      int tap = (int)(r / cin);
+      p[i] = w[((long long)co * cin + ci) * taps + tap];
+    } else {  // [tap][cout][cin]
+      int ci = (int)(i % cin);
+      long long r = i / cin;
+      int co = (int)(r % cout);
+      int tap = (int)(r / cout);
+      p[i] = w[((long long)co * cin + ci) * taps + tap];
+    }
+  }
+}
+
+// tcgen05 packings, bf16, zero padded.
+// fwd:   p[tap][co_pad][ci_pad]          = w[co][ci][tap]
+// dgrad: p[taps-1-tap][ci_pad16][co_pad8] = w[co][ci][tap]   (taps-1-tap == flip of all three axes)
+__global__ void pack_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout, int cin,
+                        int taps, int rows_pad, int cols_pad, int dgrad) {
+  long long total = (long long)taps * rows_pad * cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int col = (int)(i % cols_pad);
+    long long r = i / cols_pad;
+    int row = (int)(r % rows_pad);
+    int tp = (int)(r / rows_pad);
+    float v = 0.f;
+    if (!dgrad) {
+      if (row < cout && col < cin) v = w[((long long)row * cin + col) * taps + tp];
+    } else {
+      if (row < cin && col < cout) v = w[((long long)col * cin + row) * taps + (taps - 1 - tp)];
+    }
+    p[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- copies ------------------------------------------------------------------------------------------
+// generic strided copy; thread index runs over (n, v, c) with c fastest when dst is channels-last,
+// and over (n, c, v) with v fastest when dst is NCXYZ, so the WRITE side is always coalesced.
+__global__ void copy_kernel(View src, View dst, int n, int c, long long v, int c_fastest) {
+  long long total = (long long)n * c * v;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % v;
+      nn = (int)(r / v);
+    } else {
+      vv = i % v;
+      long long r = i / v;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    dst.st(nn, cc, vv, src.ld(nn, cc, vv));
+  }
+}
+
+// both channels-last, same dtype, 16-byte vectors
+__global__ void copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long rows,
+                                int vec_per_row, long long src_row_vecs, long long dst_row_vecs) {
+  long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / vec_per_row;
+    int q = (int)(i % vec_per_row);
+    dst[r * dst_row_vecs + q] = src[r * src_row_vecs + q];
+  }
+}
+
+__global__ void axpby_kernel(View x1, float a, View x2, float b, View y, int n, int c, long long v,
+                             int c_fastest) {
+  long long total = (long long)n * c * v;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % v;
+      nn = (int)(r / v);
+    } else {
+      vv = i % v;
+      long long r = i / v;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    float t = a * x1.ld(nn, cc, vv);
+    if (x2.ptr) t += b * x2.ld(nn, cc, vv);
+    y.st(nn, cc, vv, t);
+  }
+}
+
+__global__ void lrelu_bwd_kernel(View dy, View yv, float slope, const float* __restrict__ chan_scale,
+                                 const float* __restrict__ oscale, View g, int n, int c, long long v,
+                                 int c_fastest) {
+  long long total = (long long)n * c * v;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % v;
+      nn = (int)(r / v);
+    } else {
+      vv = i % v;
+      long long r = i / v;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    float d = dy.ld(nn, cc, vv);
+    float o = yv.ld(nn, cc, vv);
+    float r = o > 0.f ? d : slope * d;
+    if (chan_scale) r *= chan_scale[(long long)nn * c + cc];
+    if (oscale) r *= oscale[cc];
+    g.st(nn, cc, vv, r);
+  }
+}
+
+// ---- nearest upsample x2 in (x, y) -------------------------------------------------------------------
+// Channels-last fast path: one 16-byte vector of channels per thread, each input vector is read once and
+// written to its 2x2 block: algorithmic traffic = 1 read + 4 writes per element.
+__global__ void upsample_fwd_vec(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int x, int y,
+                                 int z, int vec_per_vox, long long in_vs, long long out_vs, long long in_ns,
+                                 long long out_ns) {
+  long long total = (long long)n * x * y * z * vec_per_vox;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % vec_per_vox);
+    long long r = i / vec_per_vox;
+    int zz = (int)(r % z);
+    r /= z;
+    int yy = (int)(r % y);
+    r /= y;
+    int xx = (int)(r % x);
+    int nn = (int)(r / x);
+    uint4 val = in[nn * in_ns + (((long long)xx * y + yy) * z + zz) * in_vs + q];
+    long long Y2 = 2LL * y;
+    long long base = nn * out_ns;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+        out[base + (((2LL * xx + dx) * Y2 + 2 * yy + dy) * z + zz) * out_vs + q] = val;
+  }
+}
+
+__global__ void upsample_fwd_generic(View in, View out, int n, int c, int x, int y, int z, int c_fastest) {
+  long long vo = 4LL * x * y * z;
+  long long total = (long long)n * c * vo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % vo;
+      nn = (int)(r / vo);
+    } else {
+      vv = i % vo;
+      long long r = i / vo;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    int zz = (int)(vv % z);
+    long long r2 = vv / z;
+    int yy = (int)(r2 % (2 * y));
+    int xx = (int)(r2 / (2 * y));
+    long long vi = (((long long)(xx >> 1)) * y + (yy >> 1)) * z + zz;
+    // raw element move keeps the bits exact for equal dtypes
+    if (in.dtype == out.dtype) {
+      if (in.dtype == WS_F32) ((float*)out.ptr)[out.off(nn, cc, vv)] = ((const float*)in.ptr)[in.off(nn, cc, vi)];
+      else ((uint16_t*)out.ptr)[out.off(nn, cc, vv)] = ((const uint16_t*)in.ptr)[in.off(nn, cc, vi)];
+    } else {
+      out.st(nn, cc, vv, in.ld(nn, cc, vi));
+    }
+  }
+}
+
+__global__ void upsample_bwd_generic(View dout, View din, int n, int c, int x, int y, int z, int c_fastest) {
+  long long vi_total = (long long)x * y * z;
+  long long total = (long long)n * c * vi_total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % vi_total;
+      nn = (int)(r / vi_total);
+    } else {
+      vv = i % vi_total;
+      long long r = i / vi_total;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    int zz = (int)(vv % z);
+    long long r2 = vv / z;
+    int yy = (int)(r2 % y);
+    int xx = (int)(r2 / y);
+    long long Y2 = 2LL * y;
+    float s = 0.f;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+        s += dout.ld(nn, cc, ((2LL * xx + dx) * Y2 + 2 * yy + dy) * z + zz);
+    din.st(nn, cc, vv, s);
+  }
+}
+
+// ---- BatchNorm --------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* sum, const float* sqsum, long long count, int c,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* save_mean, float* save_invstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double cnt = (double)count;
+  double mean = (double)sum[i] / cnt;
+  double var = (double)sqsum[i] / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+  scale[i] = g * invstd;
+  shift[i] = b - (float)mean * g * invstd;
+  if (save_mean) save_mean[i] = (float)mean;
+  if (save_invstd) save_invstd[i] = invstd;
+  if (running_mean) {
+    double unbiased = count > 1 ? var * cnt / (cnt - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)mean;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void scale_shift_lrelu_kernel(View x, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, float slope, View y, int n, int c,
+                                         long long v, int c_fastest) {
+  long long total = (long long)n * c * v;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % v;
+      nn = (int)(r / v);
+    } else {
+      vv = i % v;
+      long long r = i / v;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    float t = x.ld(nn, cc, vv) * scale[cc] + shift[cc];
+    y.st(nn, cc, vv, t > 0.f ? t : slope * t);
+  }
+}
+
+// One block per (channel, slice): partial sums of g and g*xhat, then atomics.
+__global__ void bn_bwd_reduce_kernel(View dy, View yv, View x, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float slope, float* sum_g,
+                                     float* sum_gx, int n, int c, long long v, int slices) {
+  int ch = blockIdx.x;
+  int sl = blockIdx.y;
+  long long total = (long long)n * v;
+  long long per = (total + slices - 1) / slices;
+  long long beg = sl * per, end = beg + per < total ? beg + per : total;
+  float m = mean[ch], is = invstd[ch];
+  float sg = 0.f, sgx = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    int nn = (int)(i / v);
+    long long vv = i % v;
+    float d = dy.ld(nn, ch, vv);
+    float o = yv.ld(nn, ch, vv);
+    float g = o > 0.f ? d : slope * d;
+    float xh = (x.ld(nn, ch, vv) - m) * is;
+    sg += g;
+    sgx += g * xh;
+  }
+  __shared__ float r1[32], r2[32];
+  sg = warp_sum(sg);
+  sgx = warp_sum(sgx);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = sg; r2[threadIdx.x >> 5] = sgx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = threadIdx.x < (blockDim.x >> 5) ? r1[threadIdx.x] : 0.f;
+    float b = threadIdx.x < (blockDim.x >> 5) ? r2[threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) { atomicAdd(&sum_g[ch], a); atomicAdd(&sum_gx[ch], b); }
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(View dy, View yv, View x, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                    float slope, float inv_count, View dx, int n, int c, long long v,
+                                    int c_fastest) {
+  long long total = (long long)n * c * v;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int nn, cc;
+    long long vv;
+    if (c_fastest) {
+      cc = (int)(i % c);
+      long long r = i / c;
+      vv = r % v;
+      nn = (int)(r / v);
+    } else {
+      vv = i % v;
+      long long r = i / v;
+      cc = (int)(r % c);
+      nn = (int)(r / c);
+    }
+    float d = dy.ld(nn, cc, vv);
+    float o = yv.ld(nn, cc, vv);
+    float g = o > 0.f ? d : slope * d;
+    float is = invstd[cc];
+    float xh = (x.ld(nn, cc, vv) - mean[cc]) * is;
+    float gm = gamma ? gamma[cc] : 1.f;
+    dx.st(nn, cc, vv, gm * is * (g - sum_g[cc] * inv_count - xh * sum_gx[cc] * inv_count));
+  }
+}
+
+}  // namespace
+
+int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packed, cudaStream_t st) {
+  int taps = g.taps();
+  if (kind == WS_PACK_SIMT_FWD || kind == WS_PACK_SIMT_DGRAD) {
+    long long total = (long long)g.cout * g.cin * taps;
+    pack_simt<<<grid_for(total), kBlock, 0, st>>>(w, (float*)packed, g.cout, g.cin, taps,
+                                                 kind == WS_PACK_SIMT_DGRAD);
+  } else {
+    int dgrad = kind == WS_PACK_TC_DGRAD;
+    int rows = dgrad ? (g.cin + 15) / 16 * 16 : (g.cout + 15) / 16 * 16;
+    int cols = dgrad ? (g.cout + 7) / 8 * 8 : (g.cin + 7) / 8 * 8;
+    long long total = (long long)taps * rows * cols;
+    pack_tc<<<grid_for(total), kBlock, 0, st>>>(w, (__nv_bfloat16*)packed, g.cout, g.cin, taps, rows, cols,
+                                               dgrad);
+  }
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static inline int c_fastest_of(const View& dst) { return dst.cs == 1 ? 1 : 0; }
+
+int copy_launch(const View& src, const View& dst, int n, int c, long long v, cudaStream_t st) {
+  long long total = (long long)n * c * v;
+  if (total <= 0) return 0;
+  // vector fast path: channels-last both sides, same dtype, aligned, contiguous batch
+  int es = src.esize();
+  int per = 16 / es;
+  if (src.dtype == dst.dtype && src.cs == 1 && dst.cs == 1 && c % per == 0 && src.vs % per == 0 &&
+      dst.vs % per == 0 && ((uintptr_t)src.ptr % 16) == 0 && ((uintptr_t)dst.ptr % 16) == 0 &&
+      src.ns == src.vs * v && dst.ns == dst.vs * v) {
+    long long rows = (long long)n * v;
+    int vpr = c / per;
+    copy_vec_kernel<<<grid_for(rows * vpr), kBlock, 0, st>>>((const uint4*)src.ptr, (uint4*)dst.ptr, rows, vpr,
+                                                            src.vs / per, dst.vs / per);
+  } else {
+    copy_kernel<<<grid_for(total), kBlock, 0, st>>>(src, dst, n, c, v, c_fastest_of(dst));
+  }
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int axpby_launch(const View& x1, float a, const View& x2, float b, const View& y, int n, int c, long long v,
+                 cudaStream_t st) {
+  long long total = (long long)n * c * v;
+  if (total <= 0) return 0;
+  axpby_kernel<<<grid_for(total), kBlock, 0, st>>>(x1, a, x2, b, y, n, c, v, c_fastest_of(y));
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lrelu_bwd_launch(const View& dy, const View& yv, float slope, const float* chan_scale, const float* oscale,
+                     const View& g, int n, int c, long long v, cudaStream_t st) {
+  long long total = (long long)n * c * v;
+  if (total <= 0) return 0;
+  lrelu_bwd_kernel<<<grid_for(total), kBlock, 0, st>>>(dy, yv, slope, chan_scale, oscale, g, n, c, v,
+                                                      c_fastest_of(g));
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upsample_fwd_launch(const View& in, const View& out, int n, int c, int x, int y, int z, cudaStream_t st) {
+  long long vi = (long long)x * y * z;
+  if ((long long)n * c * vi <= 0) return 0;
+  int es = in.esize();
+  int per = 16 / es;
+  if (in.dtype == out.dtype && in.cs == 1 && out.cs == 1 && c % per == 0 && in.vs % per == 0 &&
+      out.vs % per == 0 && in.ns % per == 0 && out.ns % per == 0 && ((uintptr_t)in.ptr % 16) == 0 &&
+      ((uintptr_t)out.ptr % 16) == 0) {
+    int vpv = c / per;
+    upsample_fwd_vec<<<grid_for((long long)n * vi * vpv), kBlock, 0, st>>>(
+        (const uint4*)in.ptr, (uint4*)out.ptr, n, x, y, z, vpv, in.vs / per, out.vs / per, in.ns / per,
+        out.ns / per);
+  } else {
+    upsample_fwd_generic<<<grid_for((long long)n * c * vi * 4), kBlock, 0, st>>>(in, out, n, c, x, y, z,
+                                                                                c_fastest_of(out));
+  }
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upsample_bwd_launch(const View& dout, const View& din, int n, int c, int x, int y, int z,
+                        cudaStream_t st) {
+  long long total = (long long)n * c * x * y * z;
+  if (total <= 0) return 0;
+  upsample_bwd_generic<<<grid_for(total), kBlock, 0, st>>>(dout, din, n, c, x, y, z, c_fastest_of(din));
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_finalize_launch(const float* sum, const float* sqsum, long long count, int c, const float* gamma,
+                       const float* beta, float eps, float momentum, float* rm, float* rv, float* scale,
+                       float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sqsum, count, c, gamma, beta, eps, momentum, rm,
+                                                      rv, scale, shift, save_mean, save_invstd);
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int scale_shift_lrelu_launch(const View& x, const float* scale, const float* shift, float slope,
+                             const View& y, int n, int c, long long v, cudaStream_t st) {
+  long long total = (long long)n * c * v;
+  if (total <= 0) return 0;
+  scale_shift_lrelu_kernel<<<grid_for(total), kBlock, 0, st>>>(x, scale, shift, slope, y, n, c, v,
+                                                              c_fastest_of(y));
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_reduce_launch(const View& dy, const View& yv, const View& x, const float* mean,
+                         const float* invstd, float slope, float* sum_g, float* sum_gx, int n, int c,
+                         long long v, cudaStream_t st) {
+  WS_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * c, st));
+  WS_CHECK_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(float) * c, st));
+  long long total = (long long)n * v;
+  int slices = (int)((total + 16383) / 16384);
+  if (slices < 1) slices = 1;
+  if (slices > 64) slices = 64;
+  dim3 grid(c, slices);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, yv, x, mean, invstd, slope, sum_g, sum_gx, n, c, v, slices);
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_apply_launch(const View& dy, const View& yv, const View& x, const float* mean,
+                        const float* invstd, const float* gamma, const float* sum_g, const float* sum_gx,
+                        float slope, long long count, const View& dx, int n, int c, long long v,
+                        cudaStream_t st) {
+  long long total = (long long)n * c * v;
+  if (total <= 0) return 0;
+  bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(dy, yv, x, mean, invstd, gamma, sum_g, sum_gx,
+                                                         slope, 1.f / (float)count, dx, n, c, v,
+                                                         c_fastest_of(dx));
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ws

@@ -1,0 +1,22 @@
+// tmap.cuh — cached cuTensorMapEncodeTiled descriptors shared by the tcgen05 kernels.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace ws {
+
+struct MapKey {
+  uintptr_t ptr;
+  uint64_t dims[5];
+  uint64_t strides[4];  // bytes, dims 1..rank-1
+  uint32_t box[5];
+  uint32_t estr[5];
+  uint32_t rank;
+  uint32_t dtype;
+};
+static_assert(sizeof(MapKey) % 8 == 0, "MapKey must hash as 64-bit words");
+
+// SWIZZLE_128B tiled tensor map for `key` (memset the key to 0 before filling it). Returns 0 on success.
+int get_tensor_map(const MapKey& key, CUtensorMap* out);
+
+}  // namespace ws

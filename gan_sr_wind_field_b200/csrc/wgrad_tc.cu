@@ -1,0 +1,372 @@
+// wgrad_tc.cu — Conv3d weight gradient as a tcgen05 GEMM with MN-major (transposed) operands.
+//
+//   dW[tap][co][ci] = sum_{n, v} dy(n, v, co) * x(n, v (+) tap, ci)
+//
+// Both operands are channels-last activations, so the reduction index (voxels) is the strided one: the
+// TMA boxes {64 ch, bz, by, bx, 1} land as R voxel rows x 128 B, which is exactly the canonical *MN-major*
+// SWIZZLE_128B UMMA tile (64 contiguous M/N elements per row, 8-row K atoms, SBO = 1024 B, LBO = one
+// 64-channel block = R*128 B).  One MMA consumes 16 voxel rows; the tap shift / zero padding / stride of
+// the convolution is again the TMA coordinate, out-of-bounds fill and elementStrides of the x operand.
+//
+// A CTA owns one 128-row M tile, a group of T taps (T * N <= 512 TMEM columns: one fp32 accumulator per
+// tap) and a slice of the voxel tiles (split-K).  The "unshifted" operand tile (dy) is loaded once per voxel
+// tile into its own 2-slot ring and reused by all T taps; the shifted operand streams through a second ring.
+// Partial results are reduced into an fp32 workspace with red.global.add, then a finalize kernel transposes
+// into torch's (cout, cin, kx, ky, kz) layout.
+//
+// Roles may be swapped (M = cin, N = cout) so that the narrow side (e.g. Cout = 32 of the RDB convs,
+// torch_blocks.py:256-267) sits on the UMMA N dimension where it costs proportionally less.
+//
+// Replaces the weight-gradient half of autograd's convolution_backward for torch_blocks.py:17,278 and
+// Generator_3D_Resnet_ESRGAN.py:105.
+#include <cuda.h>
+#include <string.h>
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include <mutex>
+
+namespace ws {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxBSlots = 6;
+
+struct WgParams {
+  int N;                 // batch
+  int bx, by, bz, rows;  // voxel tile (in OUTPUT / dy coordinates); rows % 16 == 0
+  int tiles_x, tiles_y, tiles_z;
+  long long total_tiles;       // N * tiles
+  long long tiles_per_split;
+  int kx, ky, kz, sx, sy, sz, px, py, pz;
+  int taps, taps_per_cta, tap_groups;
+  int m_blocks;          // 64-channel blocks of the M operand actually loaded (1 or 2)
+  int n_blocks;          // 64-channel blocks of the N operand
+  int m0, n0;            // channel offsets of this launch inside the full cout / cin ranges
+  int m_valid, n_valid;  // valid rows / columns of the accumulator
+  int n_umma;
+  int shift_on_m;        // 1: the M operand is x (shifted), 0: the N operand is x
+  int a_slot_bytes, b_slot_bytes, b_slots;
+  uint32_t tmem_cols;
+  // workspace addressing: wsp[tap * tap_stride + m * m_stride + n * n_stride]
+  long long tap_stride, m_stride, n_stride;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+                const WgParams p, float* __restrict__ wsp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  // layout: [A slot 0][A slot 1][B slots...][barriers]
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + 2u * p.a_slot_bytes;
+  const uint32_t bar_off = 2u * p.a_slot_bytes + (uint32_t)p.b_slots * p.b_slot_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (4 + kMaxBSlots + s); };
+  const uint32_t accum_bar = bar_base + 8u * (4 + 2 * kMaxBSlots);
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * kMaxBSlots);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (5 + 2 * kMaxBSlots));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap_group = blockIdx.x;
+  const int split = blockIdx.y;
+  const int tap_lo = tap_group * p.taps_per_cta;
+  const int tap_hi = min(p.taps, tap_lo + p.taps_per_cta);
+  const int ntap = tap_hi - tap_lo;
+  const long long tile_lo = (long long)split * p.tiles_per_split;
+  const long long tile_hi = min(p.total_tiles, tile_lo + p.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmM);
+    ptx::prefetch_tmap(&tmN);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.b_slots; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool has_work = tile_hi > tile_lo && ntap > 0;
+
+  const uint32_t blk_bytes = (uint32_t)p.rows * 128u;  // one 64-channel block of one voxel tile
+  const int tiles_per_n = p.tiles_x * p.tiles_y * p.tiles_z;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      // ===== TMA producer =====
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      // the unshifted operand (dy) is the one that is NOT x
+      const CUtensorMap* tm_fix = p.shift_on_m ? &tmN : &tmM;
+      const CUtensorMap* tm_sh = p.shift_on_m ? &tmM : &tmN;
+      const int fix_blocks = p.shift_on_m ? p.n_blocks : p.m_blocks;
+      const int sh_blocks = p.shift_on_m ? p.m_blocks : p.n_blocks;
+      const int fix_c0 = p.shift_on_m ? p.n0 : p.m0;
+      const int sh_c0 = p.shift_on_m ? p.m0 : p.n0;
+      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+        int t = (int)(tile % tiles_per_n);
+        const int n = (int)(tile / tiles_per_n);
+        const int tz = t % p.tiles_z; t /= p.tiles_z;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int tx = t;
+        const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
+        // fixed operand -> A ring ("A ring" = ring of the unshifted operand regardless of M/N role)
+        ptx::mbar_wait(a_empty(as), aph ^ 1u);
+        ptx::mbar_expect_tx(a_full(as), blk_bytes * fix_blocks);
+        for (int b = 0; b < fix_blocks; ++b)
+          ptx::tma_load_5d(a_base + as * p.a_slot_bytes + b * blk_bytes, tm_fix, a_full(as), fix_c0 + b * 64, z0,
+                           y0, x0, n);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+        for (int tap = tap_lo; tap < tap_hi; ++tap) {
+          const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
+          const int cx = x0 * p.sx - p.px + ti, cy = y0 * p.sy - p.py + tj, cz = z0 * p.sz - p.pz + tl;
+          ptx::mbar_wait(b_empty(bs), bph ^ 1u);
+          ptx::mbar_expect_tx(b_full(bs), blk_bytes * sh_blocks);
+          for (int b = 0; b < sh_blocks; ++b)
+            ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * blk_bytes, tm_sh, b_full(bs), sh_c0 + b * 64, cz,
+                             cy, cx, n);
+          if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int k16 = p.rows / 16;
+      bool first = true;
+      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+        ptx::mbar_wait(a_full(as), aph);
+        const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
+        for (int tp = 0; tp < ntap; ++tp) {
+          ptx::mbar_wait(b_full(bs), bph);
+          ptx::tc_fence_after();
+          const uint32_t sh_addr = b_base + bs * p.b_slot_bytes;
+          const uint32_t m_addr = p.shift_on_m ? sh_addr : fix_addr;
+          const uint32_t n_addr = p.shift_on_m ? fix_addr : sh_addr;
+          for (int k = 0; k < k16; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(m_addr + k * 2048, blk_bytes, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(n_addr + k * 2048, blk_bytes, 1024);
+            ptx::mma_f16_ss(tmem_base + (uint32_t)(tp * p.n_umma), adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(b_empty(bs));
+          if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+        }
+        ptx::mma_commit(a_empty(as));
+        if (++as == 2) { as = 0; aph ^= 1u; }
+        first = false;
+      }
+      ptx::mma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else if (has_work) {
+    // ===== epilogue: TMEM -> red.global.add into the fp32 workspace =====
+    const int sub = warp & 3;
+    const int m = sub * 32 + lane;
+    ptx::mbar_wait(accum_bar, 0);
+    ptx::tc_fence_after();
+    for (int tp = 0; tp < ntap; ++tp) {
+      const int tap = tap_lo + tp;
+      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+        if (c0 >= p.n_valid) break;
+        uint32_t r[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tp * p.n_umma + c0), r);
+        ptx::tmem_ld_wait();
+        if (m < p.m_valid) {
+          float* dst = wsp + (long long)tap * p.tap_stride + (long long)(p.m0 + m) * p.m_stride +
+                       (long long)(p.n0 + c0) * p.n_stride;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.n_valid) atomicAdd(dst + (long long)j * p.n_stride, __uint_as_float(r[j]));
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+  double best = -1.0;
+  bx = by = 1; bz = 16;
+  for (int z = 1; z <= 128; ++z) {
+    if (z > DZ && z != 16) continue;  // allow a padded z only as the fallback
+    if ((z - 1) * sz + 1 > 256) break;
+    for (int y = 1; z * y <= 128; ++y) {
+      if ((y - 1) * sy + 1 > 256) break;
+      if (y > 2 * DY) break;
+      for (int x = 1; z * y * x <= 128; ++x) {
+        if ((x - 1) * sx + 1 > 256) break;
+        if (x > 2 * DX) break;
+        int rows = z * y * x;
+        if (rows % 16) continue;
+        long long tiles = (long long)((DX + x - 1) / x) * ((DY + y - 1) / y) * ((DZ + z - 1) / z);
+        double eff = (double)DX * DY * DZ / ((double)tiles * rows);
+        double score = eff + 1e-4 * rows / 128.0;
+        if (score > best) { best = score; bx = x; by = y; bz = z; }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t tc_wgrad_workspace_bytes(const ConvGeom& g) {
+  return (size_t)g.taps() * g.cin * g.cout * sizeof(float);
+}
+
+// One launch: M rows = channels [m0, m0+m_count) of the M operand, N cols = channels [n0, n0+n_count) of the
+// N operand.  swap == 0: M = cout (dy), N = cin (x).  swap == 1: M = cin (x), N = cout (dy).
+static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* wsp, int swap, int m0,
+                      int m_count, int n0, int n_count, cudaStream_t st) {
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.n;
+  choose_wgrad_tile(g.xo, g.yo, g.zo, g.sx, g.sy, g.sz, p.bx, p.by, p.bz);
+  p.rows = p.bx * p.by * p.bz;
+  p.tiles_x = (g.xo + p.bx - 1) / p.bx;
+  p.tiles_y = (g.yo + p.by - 1) / p.by;
+  p.tiles_z = (g.zo + p.bz - 1) / p.bz;
+  p.total_tiles = (long long)g.n * p.tiles_x * p.tiles_y * p.tiles_z;
+  p.kx = g.kx; p.ky = g.ky; p.kz = g.kz; p.sx = g.sx; p.sy = g.sy; p.sz = g.sz;
+  p.px = g.px; p.py = g.py; p.pz = g.pz;
+  p.taps = g.taps();
+  p.m0 = m0; p.n0 = n0; p.m_valid = m_count; p.n_valid = n_count;
+  p.n_umma = (n_count + 15) / 16 * 16;
+  WS_REQUIRE(m_count <= 128 && p.n_umma <= 256, "wgrad tile too large (%d x %d)", m_count, p.n_umma);
+  p.m_blocks = (m_count + 63) / 64;
+  p.n_blocks = (p.n_umma + 63) / 64;
+  p.shift_on_m = swap;
+  p.taps_per_cta = 512 / p.n_umma;
+  if (p.taps_per_cta > p.taps) p.taps_per_cta = p.taps;
+  p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
+  // balance taps over groups
+  p.taps_per_cta = (p.taps + p.tap_groups - 1) / p.tap_groups;
+  uint32_t cols = 32;
+  while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
+  p.tmem_cols = cols;
+  const int blk = p.rows * 128;
+  const int fix_blocks = swap ? p.n_blocks : p.m_blocks;
+  const int sh_blocks = swap ? p.m_blocks : p.n_blocks;
+  // the M operand tile must always present 2 blocks worth of address space (UMMA M = 128 reads 2 blocks)
+  const int fix_alloc = swap ? p.n_blocks : 2;
+  const int sh_alloc = swap ? 2 : p.n_blocks;
+  p.a_slot_bytes = fix_alloc * blk;
+  p.b_slot_bytes = sh_alloc * blk;
+  int budget = 220 * 1024 - 1024 - 512 - 2 * p.a_slot_bytes;
+  p.b_slots = budget / p.b_slot_bytes;
+  if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
+  WS_REQUIRE(p.b_slots >= 2, "wgrad: shared memory budget too small for 2 operand slots");
+  (void)fix_blocks; (void)sh_blocks;
+
+  // split-K so the grid covers the chip a few times
+  long long base_ctas = p.tap_groups;
+  long long splits = (148LL * 2 + base_ctas - 1) / base_ctas;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+
+  // workspace layout is always [tap][cout][cin]
+  p.tap_stride = (long long)g.cout * g.cin;
+  if (!swap) { p.m_stride = g.cin; p.n_stride = 1; }
+  else { p.m_stride = 1; p.n_stride = g.cin; }
+
+  auto make_map = [&](const View& v, int channels, int X, int Y, int Z, bool strided, CUtensorMap* out) -> int {
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.ptr = reinterpret_cast<uintptr_t>(v.ptr);
+    k.rank = 5; k.dtype = WS_BF16;
+    k.dims[0] = (uint64_t)channels; k.dims[1] = (uint64_t)Z; k.dims[2] = (uint64_t)Y; k.dims[3] = (uint64_t)X;
+    k.dims[4] = (uint64_t)g.n;
+    k.strides[0] = (uint64_t)v.vs * 2;
+    k.strides[1] = (uint64_t)v.vs * 2 * Z;
+    k.strides[2] = (uint64_t)v.vs * 2 * Z * Y;
+    k.strides[3] = (uint64_t)v.ns * 2;
+    int ssx = strided ? g.sx : 1, ssy = strided ? g.sy : 1, ssz = strided ? g.sz : 1;
+    k.box[0] = 64;
+    k.box[1] = (uint32_t)((p.bz - 1) * ssz + 1);
+    k.box[2] = (uint32_t)((p.by - 1) * ssy + 1);
+    k.box[3] = (uint32_t)((p.bx - 1) * ssx + 1);
+    k.box[4] = 1;
+    k.estr[0] = 1; k.estr[1] = (uint32_t)ssz; k.estr[2] = (uint32_t)ssy; k.estr[3] = (uint32_t)ssx; k.estr[4] = 1;
+    return get_tensor_map(k, out);
+  };
+  CUtensorMap tm_x, tm_dy;
+  if (int e = make_map(x, g.cin, g.x, g.y, g.z, true, &tm_x)) return e;
+  if (int e = make_map(dy, g.cout, g.xo, g.yo, g.zo, false, &tm_dy)) return e;
+
+  size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 8 * (6 + 2 * kMaxBSlots) + 1024;
+  static std::once_flag* once = new std::once_flag;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(*once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
+  dim3 grid((unsigned)p.tap_groups, (unsigned)splits);
+  if (!swap) wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_dy, tm_x, p, wsp);
+  else wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_dy, p, wsp);
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void wgrad_tc_finalize(const float* __restrict__ wsp, float* __restrict__ dw, int taps, int cin,
+                                  int cout, int accumulate) {
+  // wsp [tap][co][ci] -> dw [co][ci][tap]
+  long long total = (long long)taps * cin * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int tap = (int)(i % taps);
+    long long r = i / taps;  // co*cin + ci
+    float v = wsp[(long long)tap * cin * cout + r];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, int accumulate, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
+  size_t need = tc_wgrad_workspace_bytes(g);
+  WS_REQUIRE(workspace && workspace_bytes >= need, "wgrad workspace too small: %zu < %zu", workspace_bytes, need);
+  float* wsp = (float*)workspace;
+  WS_CHECK_CUDA(cudaMemsetAsync(wsp, 0, need, st));
+  // Role choice: put the narrower channel count on N when it is much smaller than 128.
+  const bool swap = g.cout < 64 && g.cin >= g.cout;
+  const int mtot = swap ? g.cin : g.cout;
+  const int ntot = swap ? g.cout : g.cin;
+  for (int m0 = 0; m0 < mtot; m0 += 128) {
+    int mc = mtot - m0 < 128 ? mtot - m0 : 128;
+    for (int n0 = 0; n0 < ntot; n0 += 256) {
+      int nc = ntot - n0 < 256 ? ntot - n0 : 256;
+      if (int e = launch_one(g, x, dy, wsp, swap ? 1 : 0, m0, mc, n0, nc, st)) return e;
+    }
+  }
+  long long total = (long long)g.taps() * g.cin * g.cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_tc_finalize<<<blocks, 256, 0, st>>>(wsp, dw, g.taps(), g.cin, g.cout, accumulate);
+  WS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ws

@@ -1,0 +1,679 @@
+"""Host-side operators over the C-ABI: raw launches + the ``torch.autograd.Function``s the drop-in modules use.
+
+Tensors are *logical* (N, C, X, Y, Z) like the reference's; the internal memory format is
+``torch.channels_last_3d`` (N,X,Y,Z,C in memory), bf16 in BF16 mode and fp32 in FP32 mode.  Contiguous NCXYZ
+boundary tensors are read/written in place through strided views — no layout-conversion passes.
+
+Every function here launches hand-written CUDA from ``libwindsr.so`` on ``torch.cuda.current_stream()``;
+nothing falls back to torch/cuDNN arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (MATH_BF16, MATH_FP32, PACK_SIMT_DGRAD, PACK_SIMT_FWD, PACK_TC_DGRAD, PACK_TC_FWD,
+                   PATH_TCGEN05, WsConvShape, WsEpilogue, check, load, null_view, ptr, stream_ptr, view)
+
+# ------------------------------------------------------------------------------------------------------
+# precision
+# ------------------------------------------------------------------------------------------------------
+_PRECISION = "bf16"
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' (CUDA-core FFMA, rel-L2 <= 1e-5 parity mode) or 'bf16' (tcgen05, fp32 accumulate)."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {mode!r}")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+class precision:
+    """Context manager: ``with ops.precision('fp32'): ...``"""
+
+    def __init__(self, mode: str):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def math_mode() -> int:
+    return MATH_BF16 if _PRECISION == "bf16" else MATH_FP32
+
+
+def act_dtype() -> torch.dtype:
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
+# ------------------------------------------------------------------------------------------------------
+# allocation helpers
+# ------------------------------------------------------------------------------------------------------
+def empty_cl(n, c, x, y, z, dtype, device) -> torch.Tensor:
+    """Logical (n,c,x,y,z) tensor in channels_last_3d memory."""
+    return torch.empty((n, x, y, z, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
+
+
+def zeros_cl(n, c, x, y, z, dtype, device) -> torch.Tensor:
+    return torch.zeros((n, x, y, z, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.WindSRError("windsr ops need CUDA tensors: the hot path has no CPU fallback")
+
+
+_triple = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+def make_shape(x_shape, cout, kernel, stride, padding) -> WsConvShape:
+    n, cin, X, Y, Z = x_shape
+    kx, ky, kz = _triple(kernel)
+    sx, sy, sz = _triple(stride)
+    px, py, pz = _triple(padding)
+    return WsConvShape(n, X, Y, Z, cin, cout, kx, ky, kz, sx, sy, sz, px, py, pz)
+
+
+def out_dims(s: WsConvShape) -> Tuple[int, int, int]:
+    return ((s.x + 2 * s.px - s.kx) // s.sx + 1, (s.y + 2 * s.py - s.ky) // s.sy + 1,
+            (s.z + 2 * s.pz - s.kz) // s.sz + 1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# packed-weight cache (fp32 torch-layout Parameter -> kernel operand layout), keyed by parameter version
+# ------------------------------------------------------------------------------------------------------
+class PackedWeights:
+    """Caches the packed copies of one weight Parameter; repacks when the parameter changes
+    (optimizer step / load_state_dict bump ``_version``; ``.to()`` changes ``data_ptr``)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, w: torch.Tensor, shape: WsConvShape, kind: int) -> torch.Tensor:
+        key = kind
+        stamp = (w._version, w.data_ptr(), shape.cin, shape.cout)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        packed = pack_weights(w, shape, kind)
+        self._cache[key] = (stamp, packed)
+        return packed
+
+    def clear(self):
+        self._cache.clear()
+
+
+def pack_weights(w: torch.Tensor, shape: WsConvShape, kind: int) -> torch.Tensor:
+    _require_cuda(w)
+    lib = load()
+    wd = w.detach()
+    if wd.dtype != torch.float32 or not wd.is_contiguous():
+        wd = wd.float().contiguous()
+    nbytes = lib.ws_packed_weight_bytes(C.byref(shape), kind)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    check(lib.ws_pack_weights(wd.data_ptr(), C.byref(shape), kind, packed.data_ptr(), stream_ptr()),
+          "ws_pack_weights")
+    return packed
+
+
+# ------------------------------------------------------------------------------------------------------
+# raw launches
+# ------------------------------------------------------------------------------------------------------
+def _epilogue(bias=None, oscale=None, chan_scale=None, slope=1.0, alpha=1.0, res1=None, beta1=0.0, res2=None,
+              beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=1.0, out2=None, stat_sum=None,
+              stat_sqsum=None) -> WsEpilogue:
+    return WsEpilogue(ptr(bias), ptr(oscale), ptr(chan_scale), slope, alpha, beta1, beta2,
+                      view(res1) if res1 is not None else null_view(),
+                      view(res2) if res2 is not None else null_view(),
+                      view(mask) if mask is not None else null_view(), mask_c0, mask_c1, mask_slope, 0,
+                      view(out2) if out2 is not None else null_view(), ptr(stat_sum), ptr(stat_sqsum))
+
+
+def fwd_path(shape: WsConvShape, x: torch.Tensor, math: Optional[int] = None) -> int:
+    xv = view(x)
+    return load().ws_conv3d_fwd_path(C.byref(shape), C.byref(xv), None, math_mode() if math is None else math)
+
+
+def dgrad_path(shape: WsConvShape, dy: torch.Tensor, math: Optional[int] = None) -> int:
+    dv = view(dy)
+    return load().ws_conv3d_dgrad_path(C.byref(shape), C.byref(dv), None, math_mode() if math is None else math)
+
+
+def wgrad_path(shape: WsConvShape, x: torch.Tensor, dy: torch.Tensor, math: Optional[int] = None) -> int:
+    xv, dv = view(x), view(dy)
+    return load().ws_conv3d_wgrad_path(C.byref(shape), C.byref(xv), C.byref(dv),
+                                       math_mode() if math is None else math)
+
+
+def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], shape: WsConvShape,
+             out: torch.Tensor, math: Optional[int] = None, **ep) -> torch.Tensor:
+    """out = epilogue(conv3d(x, w)); `w` is the fp32 torch-layout weight, packed (and cached) here."""
+    _require_cuda(x)
+    lib = load()
+    math = math_mode() if math is None else math
+    xv, ov = view(x), view(out)
+    path = lib.ws_conv3d_fwd_path(C.byref(shape), C.byref(xv), C.byref(ov), math)
+    kind = PACK_TC_FWD if path == PATH_TCGEN05 else PACK_SIMT_FWD
+    packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
+    e = _epilogue(**ep)
+    check(lib.ws_conv3d_fwd(C.byref(shape), C.byref(xv), packed.data_ptr(), C.byref(ov), C.byref(e), math,
+                            stream_ptr()), "ws_conv3d_fwd")
+    return out
+
+
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], shape: WsConvShape,
+               dx: torch.Tensor, math: Optional[int] = None, **ep) -> torch.Tensor:
+    _require_cuda(dy)
+    lib = load()
+    math = math_mode() if math is None else math
+    dv, xv = view(dy), view(dx)
+    path = lib.ws_conv3d_dgrad_path(C.byref(shape), C.byref(dv), C.byref(xv), math)
+    kind = PACK_TC_DGRAD if path == PATH_TCGEN05 else PACK_SIMT_DGRAD
+    packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
+    e = _epilogue(**ep)
+    check(lib.ws_conv3d_dgrad(C.byref(shape), C.byref(dv), packed.data_ptr(), C.byref(xv), C.byref(e), math,
+                              stream_ptr()), "ws_conv3d_dgrad")
+    return dx
+
+
+_WORKSPACES = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand (stream-ordered reuse is safe on one stream)."""
+    key = (device, stream_ptr())
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, shape: WsConvShape, want_bias: bool = False,
+               math: Optional[int] = None, want_weight: bool = True):
+    """Returns (dw in torch layout fp32 or None, db or None)."""
+    _require_cuda(x)
+    lib = load()
+    math = math_mode() if math is None else math
+    dw = torch.empty((shape.cout, shape.cin, shape.kx, shape.ky, shape.kz), dtype=torch.float32,
+                     device=x.device) if want_weight else None
+    db = torch.empty((shape.cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    nbytes = lib.ws_conv3d_wgrad_workspace_bytes(C.byref(shape), math)
+    wsp = _workspace(nbytes, x.device)
+    xv, dv = view(x), view(dy)
+    check(lib.ws_conv3d_wgrad(C.byref(shape), C.byref(xv), C.byref(dv), ptr(dw), ptr(db), 0, math,
+                              wsp.data_ptr(), wsp.numel(), stream_ptr()), "ws_conv3d_wgrad")
+    return dw, db
+
+
+def copy_(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[...] = src (dtype / layout converting strided copy)."""
+    n, c, x, y, z = src.shape
+    sv, dv = view(src), view(dst)
+    check(load().ws_copy(C.byref(sv), C.byref(dv), n, c, x * y * z, stream_ptr()), "ws_copy")
+    return dst
+
+
+def axpby(x1: torch.Tensor, a: float, x2: Optional[torch.Tensor], b: float, out: torch.Tensor) -> torch.Tensor:
+    n, c, x, y, z = x1.shape
+    v1, v2, vo = view(x1), (view(x2) if x2 is not None else null_view()), view(out)
+    check(load().ws_axpby(C.byref(v1), a, C.byref(v2), b, C.byref(vo), n, c, x * y * z, stream_ptr()), "ws_axpby")
+    return out
+
+
+def lrelu_bwd(dy: torch.Tensor, y: torch.Tensor, slope: float, out: torch.Tensor, chan_scale=None,
+              oscale=None) -> torch.Tensor:
+    n, c, x, yy, z = dy.shape
+    dv, yv, ov = view(dy), view(y), view(out)
+    check(load().ws_lrelu_bwd(C.byref(dv), C.byref(yv), slope, ptr(chan_scale), ptr(oscale), C.byref(ov), n, c,
+                              x * yy * z, stream_ptr()), "ws_lrelu_bwd")
+    return out
+
+
+def upsample_fwd(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    n, c, X, Y, Z = x.shape
+    xv, ov = view(x), view(out)
+    check(load().ws_upsample_nearest_xy_fwd(C.byref(xv), C.byref(ov), n, c, X, Y, Z, stream_ptr()),
+          "ws_upsample_nearest_xy_fwd")
+    return out
+
+
+def upsample_bwd(dout: torch.Tensor, din: torch.Tensor) -> torch.Tensor:
+    n, c, X, Y, Z = din.shape
+    dv, iv = view(dout), view(din)
+    check(load().ws_upsample_nearest_xy_bwd(C.byref(dv), C.byref(iv), n, c, X, Y, Z, stream_ptr()),
+          "ws_upsample_nearest_xy_bwd")
+    return din
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd: generic fused conv block
+# ------------------------------------------------------------------------------------------------------
+def _as_act(x: torch.Tensor) -> torch.Tensor:
+    """Inputs may be fp32 boundary tensors or internal activations; both are consumed in place."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return x
+
+
+class ConvFn(torch.autograd.Function):
+    """y = lrelu(conv(x, w) * oscale + bias) * chan_scale + beta * res
+
+    Covers create_conv_lrelu_layer (torch_blocks.py:5-37) without / with eval-mode BatchNorm, the trunk skip
+    (torch_blocks.py:46), Dropout3d folded into hr_convs.0 (Generator…py:95-104) and the biased hr_convs.2.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, cfg):
+        # cfg: dict(stride, padding, slope, oscale, shift, chan_scale, beta, out, out_dtype, out_contig, cache)
+        x = _as_act(x)
+        shape = make_shape(x.shape, weight.shape[0], weight.shape[2:], cfg["stride"], cfg["padding"])
+        xo, yo, zo = out_dims(shape)
+        out = cfg.get("out")
+        if out is None:
+            dt = cfg.get("out_dtype") or act_dtype()
+            if cfg.get("out_contig"):
+                out = torch.empty((shape.n, shape.cout, xo, yo, zo), dtype=dt, device=x.device)
+            else:
+                out = empty_cl(shape.n, shape.cout, xo, yo, zo, dt, x.device)
+        oscale, shift = cfg.get("oscale"), cfg.get("shift")
+        b = bias if bias is not None else shift
+        conv_fwd(x, weight, cfg.get("cache"), shape, out, bias=b.detach() if b is not None else None,
+                 oscale=oscale, chan_scale=cfg.get("chan_scale"), slope=cfg.get("slope", 1.0),
+                 res1=res, beta1=cfg.get("beta", 1.0) if res is not None else 0.0)
+        ctx.shape = shape
+        ctx.cfg = cfg
+        ctx.has_bias = bias is not None
+        ctx.has_res = res is not None
+        ctx.x_dtype = x.dtype
+        needs_y = cfg.get("slope", 1.0) != 1.0
+        if needs_y and res is not None:
+            raise _lib.WindSRError("ConvFn: activation + residual in one epilogue is not differentiable here")
+        ctx.save_for_backward(x, weight, out if needs_y else None)
+        ctx.mark_non_differentiable()
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        cfg, shape = ctx.cfg, ctx.shape
+        slope = cfg.get("slope", 1.0)
+        chan_scale, oscale = cfg.get("chan_scale"), cfg.get("oscale")
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        dres = None
+        if ctx.has_res and need_r:
+            beta = cfg.get("beta", 1.0)
+            dres = dy if beta == 1.0 else dy * beta
+        # g = dL/d(conv accumulator) in the compute dtype
+        cdt = act_dtype()
+        if slope != 1.0 or chan_scale is not None or oscale is not None or dy.dtype != cdt or \
+                not _linear_voxels(dy):
+            g = empty_cl(*dy.shape, cdt, dy.device)
+            src_y = y if y is not None else dy
+            lrelu_bwd(dy, src_y, slope if y is not None else 1.0, g, chan_scale=chan_scale, oscale=oscale)
+        else:
+            g = dy
+        dx = dw = db = None
+        if need_w or (need_b and ctx.has_bias):
+            dw, db = conv_wgrad(x, g, shape, want_bias=ctx.has_bias and need_b, want_weight=need_w)
+        if need_x:
+            if cfg.get("dx_contig"):
+                dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            else:
+                dx = empty_cl(*x.shape, torch.float32 if cfg.get("dx_f32") else cdt, x.device)
+            conv_dgrad(g, weight, cfg.get("cache"), shape, dx)
+        return dx, dw, db, dres, None
+
+
+def _linear_voxels(t: torch.Tensor) -> bool:
+    try:
+        view(t)
+        return True
+    except _lib.WindSRError:
+        return False
+
+
+def conv_block(x, weight, bias=None, res=None, *, stride=1, padding=0, slope=1.0, oscale=None, shift=None,
+               chan_scale=None, beta=1.0, out=None, out_dtype=None, out_contig=False, cache=None,
+               dx_f32=False, dx_contig=False):
+    cfg = dict(stride=stride, padding=padding, slope=slope, oscale=oscale, shift=shift, chan_scale=chan_scale,
+               beta=beta, out=out, out_dtype=out_dtype, out_contig=out_contig, cache=cache, dx_f32=dx_f32,
+               dx_contig=dx_contig)
+    return ConvFn.apply(x, weight, bias, res, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd: residual dense block (torch_blocks.py:217-290) as ONE node
+# ------------------------------------------------------------------------------------------------------
+class RDBFn(torch.autograd.Function):
+    """x (fp32 trunk state, N,F,X,Y,Z) -> alpha * (LFF(dense(x)) + b) + beta1 * x + beta2 * outer
+
+    The four dense convs write their LeakyReLU'd outputs straight into channel slices of one (F+4*gc)-channel
+    concat buffer (no torch.cat, torch_blocks.py:214); the LFF epilogue applies bias, the 0.2 residual scale
+    and the skip add(s) (torch_blocks.py:285-290, and :328-330 when this is the last RDB of an RRDB).
+    """
+
+    @staticmethod
+    def forward(ctx, x, outer, cfg, *params):
+        # params: w0..w{k-1}, w_lff, b_lff
+        nconv = cfg["nconv"]
+        ws, w_lff, b_lff = params[:nconv], params[nconv], params[nconv + 1]
+        caches = cfg["caches"]
+        slope = cfg["slope"]
+        n, f, X, Y, Z = x.shape
+        gc = ws[0].shape[0] if nconv else 0
+        ctot = f + nconv * gc
+        cdt = act_dtype()
+        buf = empty_cl(n, ctot, X, Y, Z, cdt, x.device)
+        copy_(x, buf[:, :f])
+        k = ws[0].shape[2] if nconv else 1
+        pad = (k - 1) // 2
+        for i in range(nconv):
+            cin = f + i * gc
+            shape = make_shape((n, cin, X, Y, Z), gc, (k, k, k), 1, pad)
+            conv_fwd(buf[:, :cin], ws[i], caches[i], shape, buf[:, cin:cin + gc], slope=slope)
+        kl = w_lff.shape[2]
+        shape_l = make_shape((n, ctot, X, Y, Z), f, (kl, kl, kl), 1, (kl - 1) // 2)
+        out = empty_cl(n, f, X, Y, Z, torch.float32, x.device)
+        conv_fwd(buf, w_lff, caches[nconv], shape_l, out, bias=b_lff.detach() if b_lff is not None else None,
+                 alpha=cfg["alpha"], res1=x, beta1=cfg["beta1"], res2=outer,
+                 beta2=cfg["beta2"] if outer is not None else 0.0)
+        ctx.cfg = cfg
+        ctx.dims = (n, f, X, Y, Z, gc, ctot, k, kl)
+        ctx.has_outer = outer is not None
+        ctx.save_for_backward(buf, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        buf, *params = ctx.saved_tensors
+        cfg = ctx.cfg
+        nconv = cfg["nconv"]
+        ws, w_lff, b_lff = params[:nconv], params[nconv], params[nconv + 1]
+        caches, slope = cfg["caches"], cfg["slope"]
+        n, f, X, Y, Z, gc, ctot, k, kl = ctx.dims
+        cdt = act_dtype()
+        dev = dy.device
+        need = ctx.needs_input_grad
+        need_params = any(need[3:])
+        # gradient through the LFF: d(acc) = alpha * dy
+        g_l = empty_cl(n, f, X, Y, Z, cdt, dev)
+        axpby(dy, cfg["alpha"], None, 0.0, g_l)
+        shape_l = make_shape((n, ctot, X, Y, Z), f, (kl, kl, kl), 1, (kl - 1) // 2)
+        grads = [None] * (nconv + 2)
+        if need_params:
+            dw, db = conv_wgrad(buf, g_l, shape_l, want_bias=b_lff is not None)
+            grads[nconv], grads[nconv + 1] = dw, db
+        dbuf = empty_cl(n, ctot, X, Y, Z, torch.float32, dev)
+        conv_dgrad(g_l, w_lff, caches[nconv], shape_l, dbuf)
+        pad = (k - 1) // 2
+        for i in range(nconv - 1, -1, -1):
+            cin = f + i * gc
+            shape = make_shape((n, cin, X, Y, Z), gc, (k, k, k), 1, pad)
+            g = empty_cl(n, gc, X, Y, Z, cdt, dev)
+            lrelu_bwd(dbuf[:, cin:cin + gc], buf[:, cin:cin + gc], slope, g)
+            if need_params:
+                grads[i], _ = conv_wgrad(buf[:, :cin], g, shape)
+            d_in = dbuf[:, :cin]
+            conv_dgrad(g, ws[i], caches[i], shape, d_in, res1=d_in, beta1=1.0)
+        dx = None
+        if need[0]:
+            dx = empty_cl(n, f, X, Y, Z, torch.float32, dev)
+            axpby(dbuf[:, :f], 1.0, dy, cfg["beta1"], dx)
+        douter = None
+        if ctx.has_outer and need[1]:
+            douter = dy if cfg["beta2"] == 1.0 else dy * cfg["beta2"]
+        return (dx, douter, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd: nearest upsample, concat, elementwise
+# ------------------------------------------------------------------------------------------------------
+class UpsampleFn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=(2,2,1), mode='nearest') (torch_blocks.py:347); backward = 2x2 block sum."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, c, X, Y, Z = x.shape
+        contig = x.is_contiguous() and not x.permute(0, 2, 3, 4, 1).is_contiguous()
+        out = (torch.empty((n, c, 2 * X, 2 * Y, Z), dtype=x.dtype, device=x.device) if contig
+               else empty_cl(n, c, 2 * X, 2 * Y, Z, x.dtype, x.device))
+        upsample_fwd(x, out)
+        ctx.in_shape = x.shape
+        ctx.contig = contig
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, X, Y, Z = ctx.in_shape
+        din = (torch.empty(ctx.in_shape, dtype=dy.dtype, device=dy.device) if ctx.contig
+               else empty_cl(n, c, X, Y, Z, dy.dtype, dy.device))
+        upsample_bwd(dy, din)
+        return din
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat((a, b), 1) (Generator…py:228) where a and b were already written into slices of `buf`."""
+
+    @staticmethod
+    def forward(ctx, a, b, buf):
+        ctx.ca = a.shape[1]
+        return buf.detach()
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy[:, :ctx.ca], dy[:, ctx.ca:], None
+
+
+class AxpbyFn(torch.autograd.Function):
+    """a*x + b*y with one kernel (RRDB / skip adds, torch_blocks.py:46,330)."""
+
+    @staticmethod
+    def forward(ctx, x, y, a, b):
+        out = empty_cl(*x.shape, x.dtype, x.device)
+        axpby(x, a, y, b, out)
+        ctx.ab = (a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        a, b = ctx.ab
+        return (d if a == 1.0 else d * a), (d if b == 1.0 else d * b), None, None
+
+
+class ChanScaleFn(torch.autograd.Function):
+    """Standalone Dropout3d: x * scale[n, c] (Generator…py:70-74, Discriminator_3D.py:178-182)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        out = empty_cl(*x.shape, x.dtype, x.device)
+        lrelu_bwd(x, x, 1.0, out, chan_scale=scale)
+        ctx.save_for_backward(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        (scale,) = ctx.saved_tensors
+        g = empty_cl(*d.shape, d.dtype, d.device)
+        lrelu_bwd(d, d, 1.0, g, chan_scale=scale)
+        return g, None
+
+
+class LReluFn(torch.autograd.Function):
+    """Standalone LeakyReLU (only reached when a caller slices a block apart)."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        out = empty_cl(*x.shape, x.dtype, x.device)
+        lrelu_bwd(x, x, slope, out)  # x>0 ? x : slope*x
+        ctx.save_for_backward(out)
+        ctx.slope = slope
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        (y,) = ctx.saved_tensors
+        g = empty_cl(*d.shape, d.dtype, d.device)
+        lrelu_bwd(d, y, ctx.slope, g)
+        return g, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd: conv + BatchNorm3d(train) + LeakyReLU  (discriminator blocks, torch_blocks.py:372-521)
+# ------------------------------------------------------------------------------------------------------
+class ConvBNLReluFn(torch.autograd.Function):
+    """Training-mode BatchNorm3d: the conv epilogue accumulates per-channel sum / sum-of-squares of its raw
+    fp32 accumulators, ws_bn_finalize turns them into scale/shift (+ running-stat update), a second
+    elementwise pass normalises and applies LeakyReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, cfg):
+        lib = load()
+        x = _as_act(x)
+        shape = make_shape(x.shape, weight.shape[0], weight.shape[2:], cfg["stride"], cfg["padding"])
+        xo, yo, zo = out_dims(shape)
+        c = shape.cout
+        dev = x.device
+        cdt = act_dtype()
+        raw = empty_cl(shape.n, c, xo, yo, zo, cdt, dev)
+        stats = torch.zeros((2, c), dtype=torch.float32, device=dev)
+        conv_fwd(x, weight, cfg.get("cache"), shape, raw, stat_sum=stats[0], stat_sqsum=stats[1])
+        aux = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
+        count = shape.n * xo * yo * zo
+        check(lib.ws_bn_finalize(stats[0].data_ptr(), stats[1].data_ptr(), count, c, ptr(gamma), ptr(beta),
+                                 cfg["eps"], cfg["momentum"], ptr(running_mean), ptr(running_var),
+                                 aux[0].data_ptr(), aux[1].data_ptr(), aux[2].data_ptr(), aux[3].data_ptr(),
+                                 stream_ptr()), "ws_bn_finalize")
+        y = empty_cl(shape.n, c, xo, yo, zo, cdt, dev)
+        rv, yv = view(raw), view(y)
+        check(lib.ws_scale_shift_lrelu(C.byref(rv), aux[0].data_ptr(), aux[1].data_ptr(), cfg["slope"],
+                                       C.byref(yv), shape.n, c, xo * yo * zo, stream_ptr()),
+              "ws_scale_shift_lrelu")
+        ctx.shape, ctx.cfg, ctx.count = shape, cfg, count
+        ctx.save_for_backward(x, weight, gamma, raw, y, aux)
+        ctx.mark_non_differentiable()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = load()
+        x, weight, gamma, raw, y, aux = ctx.saved_tensors
+        shape, cfg = ctx.shape, ctx.cfg
+        c = shape.cout
+        dev = dy.device
+        cdt = act_dtype()
+        n, _, xo, yo, zo = y.shape
+        v = xo * yo * zo
+        sums = torch.empty((2, c), dtype=torch.float32, device=dev)
+        dv, yv, rv = view(dy), view(y), view(raw)
+        check(lib.ws_bn_lrelu_bwd_reduce(C.byref(dv), C.byref(yv), C.byref(rv), aux[2].data_ptr(),
+                                         aux[3].data_ptr(), cfg["slope"], sums[0].data_ptr(), sums[1].data_ptr(),
+                                         n, c, v, stream_ptr()), "ws_bn_lrelu_bwd_reduce")
+        g = empty_cl(n, c, xo, yo, zo, cdt, dev)
+        gv = view(g)
+        check(lib.ws_bn_lrelu_bwd_apply(C.byref(dv), C.byref(yv), C.byref(rv), aux[2].data_ptr(),
+                                        aux[3].data_ptr(), ptr(gamma), sums[0].data_ptr(), sums[1].data_ptr(),
+                                        cfg["slope"], ctx.count, C.byref(gv), n, c, v, stream_ptr()),
+              "ws_bn_lrelu_bwd_apply")
+        need_x, need_w, need_g, need_b = ctx.needs_input_grad[:4]
+        dx = dw = None
+        if need_w:
+            dw, _ = conv_wgrad(x, g, shape)
+        if need_x:
+            dx = empty_cl(*x.shape, cdt, dev)
+            conv_dgrad(g, weight, cfg.get("cache"), shape, dx)
+        dgamma = sums[1].clone() if need_g else None
+        dbeta = sums[0].clone() if need_b else None
+        return dx, dw, dgamma, dbeta, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# wind-field loss stencils
+# ------------------------------------------------------------------------------------------------------
+_COEF_CACHE = {}
+
+
+def axis_coeffs(coords: torch.Tensor) -> torch.Tensor:
+    """6 floats per grid point: forward-form and linear-form 3-point coefficients of
+    torch.gradient(spacing=coords) (process_data.py:303)."""
+    key = (coords.data_ptr(), coords._version, coords.numel(), str(coords.device))
+    hit = _COEF_CACHE.get(key)
+    if hit is not None:
+        return hit
+    c32 = coords.detach().to(torch.float32).contiguous()
+    coef = torch.empty((coords.numel(), 6), dtype=torch.float32, device=coords.device)
+    check(load().ws_axis_coeffs(c32.data_ptr(), c32.numel(), coef.data_ptr(), stream_ptr()), "ws_axis_coeffs")
+    if len(_COEF_CACHE) > 64:
+        _COEF_CACHE.clear()
+    _COEF_CACHE[key] = coef
+    return coef
+
+
+def wind_gradient(field: torch.Tensor, x: torch.Tensor, y: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+    """calculate_gradient_of_wind_field (process_data.py:301-313): (N,3,X,Y,Z) -> (N,9,X,Y,Z), no autograd."""
+    _require_cuda(field)
+    n, c, X, Y, Zn = field.shape
+    if c != 3:
+        raise _lib.WindSRError("wind_gradient expects the 3 wind components")
+    out = torch.empty((n, 9, X, Y, Zn), dtype=torch.float32, device=field.device)
+    cx, cy = axis_coeffs(x), axis_coeffs(y)
+    fv, zv, ov = view(field.float()), view(Z.float()), view(out)
+    check(load().ws_wind_gradient(C.byref(fv), C.byref(zv), cx.data_ptr(), cy.data_ptr(), C.byref(ov), n, X, Y,
+                                  Zn, stream_ptr()), "ws_wind_gradient")
+    return out
+
+
+class WindLossFn(torch.autograd.Function):
+    """One fused pass over HR, SR, Z -> the 16-slot vector of sums and maxes (windsr.h WS_WL_*).
+
+    The scalar loss formula (normalisers, weights, NaN guard — wind_field_GAN_3D.py:388-454) is written with
+    ordinary torch scalar ops on these slots; autograd hands dL/d(slot) back to ``backward``, which is exactly
+    the coefficient vector ws_windloss_bwd needs, including the path through SR_max/100.
+    """
+
+    @staticmethod
+    def forward(ctx, hr, sr, Z, x, y):
+        _require_cuda(sr)
+        n, c, X, Y, Zn = sr.shape
+        hr3 = hr[:, :3]
+        result = torch.empty((_lib.WL_RESULT_FLOATS,), dtype=torch.float32, device=sr.device)
+        argmax = torch.empty((4,), dtype=torch.int64, device=sr.device)
+        cx, cy = axis_coeffs(x), axis_coeffs(y)
+        hv, sv, zv = view(hr3), view(sr), view(Z)
+        check(load().ws_windloss_fwd(C.byref(hv), C.byref(sv), C.byref(zv), cx.data_ptr(), cy.data_ptr(), n, X,
+                                     Y, Zn, result.data_ptr(), argmax.data_ptr(), stream_ptr()),
+              "ws_windloss_fwd")
+        ctx.save_for_backward(hr3, sr, Z, cx, cy, argmax)
+        return result[:_lib.WL_SLOTS].clone()
+
+    @staticmethod
+    def backward(ctx, dres):
+        hr3, sr, Z, cx, cy, argmax = ctx.saved_tensors
+        n, c, X, Y, Zn = sr.shape
+        coef = torch.zeros((_lib.WLB_SLOTS,), dtype=torch.float32, device=sr.device)
+        coef[0:6] = dres[0:6]
+        coef[6:10] = dres[7:14:2]  # SR max slots 7, 9, 11, 13
+        dsr = torch.empty(sr.shape, dtype=torch.float32, device=sr.device)
+        nbytes = load().ws_windloss_bwd_workspace_bytes(n, X, Y, Zn)
+        wsp = torch.empty(nbytes, dtype=torch.uint8, device=sr.device)
+        hv, sv, zv, dv = view(hr3), view(sr), view(Z), view(dsr)
+        check(load().ws_windloss_bwd(C.byref(hv), C.byref(sv), C.byref(zv), cx.data_ptr(), cy.data_ptr(), n, X, Y,
+                                     Zn, coef.data_ptr(), argmax.data_ptr(), C.byref(dv), wsp.data_ptr(),
+                                     wsp.numel(), stream_ptr()), "ws_windloss_bwd")
+        return None, dsr, None, None, None
+
+
+def windloss_slots(hr, sr, Z, x, y) -> torch.Tensor:
+    return WindLossFn.apply(hr, sr.float() if sr.dtype != torch.float32 else sr, Z.float(), x, y)

@@ -1,0 +1,23 @@
+"""GAN training tricks with the reference's semantics (tools/trainingtricks.py:18-58), kept on the device
+(the reference samples label noise on the CPU and copies it over: two H2D copies per step)."""
+import torch
+
+
+def noisy_labels(label_type, batch_size, noise_stddev=0.05, false_label_val=0.0, true_label_val=1.0,
+                 val_lower_lim=0.0, val_upper_lim=1.0, device=torch.device("cpu")):
+    """Gaussian-perturbed real/fake label vector of length ``batch_size``, clamped to [lower, upper]."""
+    std = float(noise_stddev)
+    if std > 0.0:
+        label = torch.normal(mean=0.0, std=torch.full((int(batch_size),), std)).to(device)
+    else:
+        # torch.normal with std 0 returns the mean; skip the host RNG round trip
+        label = torch.zeros(int(batch_size), device=device)
+    label = label + (true_label_val if label_type else false_label_val)
+    return torch.clamp(label, min=float(val_lower_lim), max=float(val_upper_lim))
+
+
+def instance_noise(sigma_base, shape, it, niter, device=torch.device("cpu")):
+    """U[0,1) * sqrt(sigma_base * (1 - (it-1)/niter)) — uniform, as the reference actually draws it
+    (trainingtricks.py:56)."""
+    noise = torch.rand(shape, device=device)
+    return noise * torch.sqrt(sigma_base * (1 - (it - 1) / niter))

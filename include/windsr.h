@@ -1,0 +1,231 @@
+/*
+ * windsr.h — C-ABI of the B200-native (sm_100a) hot path for GAN_SR_wind_field.
+ *
+ * The reference (jacobwulffwold/GAN_SR_wind_field) is pure Python and reaches the GPU only through
+ * stock torch ops, so it has no FFI of its own.  Every entry point below therefore cites the reference
+ * *call site* whose arithmetic it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 on success, non-zero on failure (ws_last_error() has the message);
+ *     nothing throws or exits across the ABI;
+ *   - no allocation inside: workspaces are passed in (ws_*_workspace_bytes gives the size);
+ *   - every launch goes to the cudaStream_t passed as `void* stream` (re-entrant per stream);
+ *   - activations are addressed through ws_tensor views, so both the reference's logical
+ *     (N,C,X,Y,Z) layout and the internal channels-last (N,X,Y,Z,C) layout (and channel slices of
+ *     a wider dense-concat buffer) are expressible without copies.
+ */
+#ifndef WINDSR_H_
+#define WINDSR_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WS_VERSION 1
+
+/* element types of activation tensors */
+enum { WS_F32 = 0, WS_BF16 = 1 };
+
+/* arithmetic mode of a convolution pass (north-star tolerances 1e-5 / 2e-3 / 2e-2) */
+enum {
+  WS_MATH_FP32 = 0, /* CUDA-core FFMA, fp32 accumulate: the 1e-5 parity mode and the narrow layers     */
+  WS_MATH_TF32 = 1, /* tcgen05 kind::tf32 on fp32 activations                                            */
+  WS_MATH_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulators)                          */
+};
+
+/* which kernel family a call resolved to (ws_conv3d_*_path); tests assert on it */
+enum { WS_PATH_NONE = 0, WS_PATH_SIMT = 1, WS_PATH_TCGEN05 = 2 };
+
+/* weight packings (ws_pack_weights) */
+enum {
+  WS_PACK_SIMT_FWD = 0,   /* fp32 [tap][cin][cout]                 B operand of fwd on CUDA cores        */
+  WS_PACK_SIMT_DGRAD = 1, /* fp32 [tap][cout][cin]                 B operand of dgrad on CUDA cores       */
+  WS_PACK_TC_FWD = 2,     /* bf16 [tap][cout_pad16][cin_pad8]      K-major B operand for tcgen05 fwd      */
+  WS_PACK_TC_DGRAD = 3    /* bf16 [flipped tap][cin_pad16][cout_pad8]  K-major B operand for tcgen05 dgrad */
+};
+
+/* A view of a 5-D activation: element (n, c, v) with v = (x*Y + y)*Z + z lives at
+ *   ptr + n*nstride + v*vstride + c*cstride   (strides in ELEMENTS of dtype).
+ * channels-last:  vstride = C_total, cstride = 1, nstride = V*C_total   (ptr may point at a channel offset)
+ * reference NCXYZ: vstride = 1, cstride = V, nstride = C*V */
+typedef struct ws_tensor {
+  void* ptr;
+  int32_t dtype;
+  int32_t _pad;
+  int64_t nstride;
+  int64_t vstride;
+  int64_t cstride;
+} ws_tensor;
+
+/* Geometry of one Conv3d layer as torch.nn.Conv3d defines it (torch_blocks.py:17,278;
+ * Generator_3D_Resnet_ESRGAN.py:105): input (n, cin, x, y, z) -> output (n, cout, xo, yo, zo),
+ * xo = (x + 2*px - kx)/sx + 1 etc. */
+typedef struct ws_conv_shape {
+  int32_t n, x, y, z;
+  int32_t cin, cout;
+  int32_t kx, ky, kz;
+  int32_t sx, sy, sz;
+  int32_t px, py, pz;
+} ws_conv_shape;
+
+/* Fused epilogue applied to each accumulator element acc(n, c, v):
+ *   t = acc * (oscale ? oscale[c] : 1) + (bias ? bias[c] : 0)
+ *   t = t > 0 ? t : lrelu_slope * t                     (lrelu_slope == 1 -> identity)
+ *   t = t * (chan_scale ? chan_scale[n*C + c] : 1)      (Dropout3d mask * 1/(1-p), Generator…py:70-74)
+ *   y = alpha * t + beta1 * res1(n,c,v) + beta2 * res2(n,c,v)
+ *   if (mask.ptr && mask_c0 <= c < mask_c1)  y *= (mask(n,c,v) > 0 ? 1 : mask_slope)   (LeakyReLU backward
+ *                                               of the producer layer, fused into this dgrad)
+ *   out(n,c,v) = y;  out2(n,c,v) = y (optional second dtype/layout)
+ *   stat_sum[c] += t_preact, stat_sqsum[c] += t_preact^2 over (n,v)   (BatchNorm3d batch statistics of the
+ *                                               raw conv output, torch_blocks.py:24-25; taken before lrelu)
+ * This covers: conv+LeakyReLU (torch_blocks.py:35), the RDB dense-concat slice write (:214, out = channel
+ * slice of the concat buffer), LFF bias + 0.2*residual + x (:278-290), RRDB 0.2*residual + x (:328-330),
+ * the trunk skip x + module(x) (:46), and hr_convs.2 bias (Generator…py:105-110). */
+typedef struct ws_epilogue {
+  const float* bias;
+  const float* oscale;
+  const float* chan_scale;
+  float lrelu_slope;
+  float alpha;
+  float beta1;
+  float beta2;
+  ws_tensor res1;
+  ws_tensor res2;
+  ws_tensor mask;
+  int32_t mask_c0, mask_c1;
+  float mask_slope;
+  int32_t _pad;
+  ws_tensor out2;
+  float* stat_sum;
+  float* stat_sqsum;
+} ws_epilogue;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int ws_version(void);
+const char* ws_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05 path usable) */
+int ws_device_supports_tcgen05(void);
+
+/* ---- weights ---------------------------------------------------------------------------------- */
+/* bytes of a packed weight buffer of the given kind */
+size_t ws_packed_weight_bytes(const ws_conv_shape* s, int pack_kind);
+/* w: torch layout (cout, cin, kx, ky, kz) fp32 (state_dict layout) -> packed */
+int ws_pack_weights(const float* w, const ws_conv_shape* s, int pack_kind, void* packed, void* stream);
+
+/* ---- Conv3d passes (replace nn.Conv3d forward + autograd convolution_backward; torch_blocks.py:17) */
+int ws_conv3d_fwd_path(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* out, int math);
+int ws_conv3d_dgrad_path(const ws_conv_shape* s, const ws_tensor* dy, const ws_tensor* dx, int math);
+int ws_conv3d_wgrad_path(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, int math);
+
+/* out = epilogue(conv(in, W)).  `packed_w` must be the packing matching ws_conv3d_fwd_path(). */
+int ws_conv3d_fwd(const ws_conv_shape* s, const ws_tensor* in, const void* packed_w, const ws_tensor* out,
+                  const ws_epilogue* ep, int math, void* stream);
+/* dx = epilogue(conv_transpose(dy, W)) : gradient w.r.t. the conv input.  `dx` channel count = cin.
+ * Use ep->res1 = dx, beta1 = 1 to accumulate into an existing gradient (dense-concat backward). */
+int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* packed_w, const ws_tensor* dx,
+                    const ws_epilogue* ep, int math, void* stream);
+/* dw (torch layout (cout,cin,kx,ky,kz) fp32) = [accumulate ? dw : 0] + sum_{n,v} dy(n,co,v) * in(n,ci,v (+) tap)
+ * db (optional, [cout]) likewise gets sum dy. workspace: ws_conv3d_wgrad_workspace_bytes(). */
+size_t ws_conv3d_wgrad_workspace_bytes(const ws_conv_shape* s, int math);
+int ws_conv3d_wgrad(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, float* dw, float* db,
+                    int accumulate, int math, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- nearest upsample (x2 in x and y, z untouched): nn.Upsample(scale_factor=(2,2,1)) torch_blocks.py:347 */
+/* in: (n, c, x, y, z) view, out: (n, c, 2x, 2y, z) view; bit-exact gather out[x,y,z] = in[x/2, y/2, z] */
+int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,
+                               void* stream);
+/* din[x,y,z] = sum of the 2x2 block of dout */
+int ws_upsample_nearest_xy_bwd(const ws_tensor* dout, const ws_tensor* din, int n, int c, int x, int y, int z,
+                               void* stream);
+
+/* ---- elementwise helpers -------------------------------------------------------------------------- */
+/* dst(n,c,v) = src(n,c,v) with dtype/layout conversion (the torch.cat / clone / layout changes of
+ * torch_blocks.py:214,286 and Generator…py:228 expressed as strided copies) */
+int ws_copy(const ws_tensor* src, const ws_tensor* dst, int n, int c, int64_t v, void* stream);
+/* y = a*x1 + b*x2 (x2 optional) */
+int ws_axpby(const ws_tensor* x1, float a, const ws_tensor* x2, float b, const ws_tensor* y, int n, int c,
+             int64_t v, void* stream);
+/* g = dy * (y > 0 ? 1 : slope) * (chan_scale ? chan_scale[n*C+c] : 1) * (oscale ? oscale[c] : 1):
+ * LeakyReLU backward from the saved OUTPUT (torch_blocks.py:35), with the Dropout3d channel scale
+ * (Generator…py:70-74) and an eval-mode BatchNorm scale folded in. */
+int ws_lrelu_bwd(const ws_tensor* dy, const ws_tensor* y, float slope, const float* chan_scale,
+                 const float* oscale, const ws_tensor* g, int n, int c, int64_t v, void* stream);
+
+/* ---- BatchNorm3d (torch_blocks.py:24-25; defaults eps 1e-5, momentum 0.1, affine) ------------------ */
+/* From per-channel sum / sum-of-squares of the raw conv output over `count` elements:
+ * scale[c] = gamma/sqrt(var_biased+eps), shift[c] = beta - mean*scale; save_mean/save_invstd for backward;
+ * running stats updated with the unbiased variance when running_mean != NULL. */
+int ws_bn_finalize(const float* sum, const float* sqsum, int64_t count, int c, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* y = lrelu(x*scale[c] + shift[c]) */
+int ws_scale_shift_lrelu(const ws_tensor* x, const float* scale, const float* shift, float slope,
+                         const ws_tensor* y, int n, int c, int64_t v, void* stream);
+/* Backward of y = lrelu(bn(x)) in training mode. pass 1 accumulates per-channel sums
+ * sum_g = sum g, sum_gx = sum g*xhat with g = dy*(y>0?1:slope);  pass 2 writes
+ * dx = gamma*invstd*(g - sum_g/count - xhat*sum_gx/count).  dgamma = sum_gx, dbeta = sum_g. */
+int ws_bn_lrelu_bwd_reduce(const ws_tensor* dy, const ws_tensor* y, const ws_tensor* x, const float* mean,
+                           const float* invstd, float slope, float* sum_g, float* sum_gx, int n, int c,
+                           int64_t v, void* stream);
+int ws_bn_lrelu_bwd_apply(const ws_tensor* dy, const ws_tensor* y, const ws_tensor* x, const float* mean,
+                          const float* invstd, const float* gamma, const float* sum_g, const float* sum_gx,
+                          float slope, int64_t count, const ws_tensor* dx, int n, int c, int64_t v,
+                          void* stream);
+
+/* ---- wind-field loss stencils (process_data.py:273-313; wind_field_GAN_3D.py:377-424,773-814) ----- */
+/* Result slots of ws_windloss_fwd (float[WS_WL_SLOTS]) */
+enum {
+  WS_WL_SUM_XY = 0,    /* sum over ch 0-5 of (dSR - dHR)^2                      (count 6*N*V) */
+  WS_WL_SUM_Z = 1,     /* sum over ch 6-8                                        (count 3*N*V) */
+  WS_WL_SUM_DIV = 2,   /* sum (divSR - divHR)^2, div = ch0+ch4+ch8              (count N*V)   */
+  WS_WL_SUM_DIVXY = 3, /* sum (ch0+ch4 difference)^2                            (count N*V)   */
+  WS_WL_SUM_PIX_L1 = 4,/* sum |HR - SR| over the 3 wind channels                (count 3*N*V) */
+  WS_WL_SUM_PIX_L2 = 5,/* sum (HR - SR)^2                                                     */
+  WS_WL_MAX_HR_XY = 6, WS_WL_MAX_SR_XY = 7,     /* max |.| over ch 0-5                          */
+  WS_WL_MAX_HR_Z = 8, WS_WL_MAX_SR_Z = 9,       /* max (no abs!) over ch 6-8 (wind_field_GAN_3D.py:780-781) */
+  WS_WL_MAX_HR_DIV = 10, WS_WL_MAX_SR_DIV = 11, /* max |ch0+ch4+ch8|                            */
+  WS_WL_MAX_HR_DIVXY = 12, WS_WL_MAX_SR_DIVXY = 13,
+  WS_WL_SLOTS = 16,        /* floats holding results                                                   */
+  WS_WL_RESULT_FLOATS = 64 /* size of the `result` buffer: slots + internal fp64/u64 reduction scratch */
+};
+/* Coefficient slots of ws_windloss_bwd (device float[WS_WLB_SLOTS]) */
+enum {
+  WS_WLB_DSUM_XY = 0, WS_WLB_DSUM_Z = 1, WS_WLB_DSUM_DIV = 2, WS_WLB_DSUM_DIVXY = 3, /* dL/d(sum_k)      */
+  WS_WLB_DSUM_PIX_L1 = 4, WS_WLB_DSUM_PIX_L2 = 5,
+  WS_WLB_DMAX_SR_XY = 6, WS_WLB_DMAX_SR_Z = 7, WS_WLB_DMAX_SR_DIV = 8, WS_WLB_DMAX_SR_DIVXY = 9, /* dL/d(SR max_k),
+                                   non-zero only when SR_max/100 > HR_max (wind_field_GAN_3D.py:805-814) */
+  WS_WLB_SLOTS = 12
+};
+/* Per-axis 3-point coefficients of torch.gradient(spacing=coords, edge_order=1) (process_data.py:303).
+ * coef has 6*len floats: [6i+0..2] the forward form (a,b,c on f[i-1],f[i],f[i+1]; at the two edge points
+ * slot 1 holds the spacing used as divisor), [6i+3..5] the same row as plain linear coefficients. */
+int ws_axis_coeffs(const float* coords, int len, float* coef, void* stream);
+/* 9-channel Jacobian of a wind field (calculate_gradient_of_wind_field, process_data.py:301-313):
+ * field (n,3,x,y,z), zalt (n,1,x,y,z) raw altitude, out (n,9,x,y,z): ch 0-2 d/dx, 3-5 d/dy, 6-8 d/dz. */
+int ws_wind_gradient(const ws_tensor* field, const ws_tensor* zalt, const float* coef_x, const float* coef_y,
+                     const ws_tensor* out, int n, int x, int y, int z, void* stream);
+/* One fused pass over HR, SR, Z: all sums and maxes above, nothing materialised.  `result` is a device
+ * buffer of WS_WL_RESULT_FLOATS floats, 8-byte aligned; the call initialises it itself on `stream`.
+ * argmax[4] (device int64, optional): flat index of the element attaining each SR max (xy, z: index into
+ * the virtual (n,9,v) SR Jacobian; div, divxy: voxel index n*V+v), needed when the normaliser's gradient
+ * flows through SR_max/100. */
+int ws_windloss_fwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* zalt, const float* coef_x,
+                    const float* coef_y, int n, int x, int y, int z, float* result, int64_t* argmax,
+                    void* stream);
+/* dSR(n,3,v) = sum_k coef[DSUM_k] * d(sum_k)/dSR + coef[DSUM_PIX_L1] * sign(SR-HR)
+ *             + coef[DSUM_PIX_L2] * 2(SR-HR) + sum_k coef[DMAX_SR_k] * d(SR max_k)/dSR.
+ * coef: device float[WS_WLB_SLOTS].  workspace: ws_windloss_bwd_workspace_bytes() = 9*N*V floats. */
+size_t ws_windloss_bwd_workspace_bytes(int n, int x, int y, int z);
+int ws_windloss_bwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* zalt, const float* coef_x,
+                    const float* coef_y, int n, int x, int y, int z, const float* coef,
+                    const int64_t* argmax, const ws_tensor* dsr, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WINDSR_H_ */

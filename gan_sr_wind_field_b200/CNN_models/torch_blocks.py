@@ -65,8 +65,8 @@ class Conv3d(nn.Module):
 
     def __deepcopy__(self, memo):
         # the packed-weight cache is device scratch, not state (deepcopy: wind_field_GAN_3D.py:581)
-        new = Conv3d(self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding,
-                     bias=self.bias is not None)
+        new = type(self)(self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding,
+                         bias=self.bias is not None)
         new.weight = nn.Parameter(self.weight.detach().clone(), requires_grad=self.weight.requires_grad)
         if self.bias is not None:
             new.bias = nn.Parameter(self.bias.detach().clone(), requires_grad=self.bias.requires_grad)
@@ -86,6 +86,14 @@ class Conv3d(nn.Module):
 
     def forward(self, x):
         return self.run(x)
+
+
+class DenseConv3d(Conv3d):
+    """The Conv3d inside an ``RDB_Conv``.  The reference wraps every RDB_Conv in ``torch.jit.script``
+    (torch_blocks.py:259), which turns its layers into ``RecursiveScriptModule``s — so the class-name match of
+    ``init_weights`` (tools/initialization.py:16) silently SKIPS the 4 x 48 dense convs and they keep
+    nn.Conv3d's default Kaiming-uniform initialisation.  A distinct class name reproduces that behaviour under
+    both the reference's and this package's ``init_weights`` (and keeps the seeded RNG stream aligned)."""
 
 
 class LeakyReLU(nn.Module):
@@ -197,9 +205,10 @@ class ConvBlock(nn.Sequential):
 def create_conv_lrelu_layer(in_channels, out_channels, kernel_size, stride=1, padding=1,
                             lrelu_negative_slope=0.2, normalization_type="", layer_type=Conv3d, lrelu=True):
     """torch_blocks.py:5-37 (3-D only)."""
-    if layer_type not in (Conv3d, nn.Conv3d):
+    if layer_type not in (Conv3d, DenseConv3d, nn.Conv3d):
         raise NotImplementedError("only 3-D convolutions are on the hot path (SURVEY §2)")
-    layers = [Conv3d(in_channels, out_channels, kernel_size, stride, padding, bias=False)]
+    cls = DenseConv3d if layer_type is DenseConv3d else Conv3d
+    layers = [cls(in_channels, out_channels, kernel_size, stride, padding, bias=False)]
     if normalization_type:
         if normalization_type == "batch":
             layers.append(BatchNorm3d(out_channels))
@@ -261,7 +270,7 @@ class RDB_Conv(nn.Module):
         super().__init__()
         self.conv = create_conv_lrelu_layer(in_channels, out_channels, kernel_size, stride=1,
                                             padding=(kernel_size - 1) // 2,
-                                            lrelu_negative_slope=lrelu_negative_slope, layer_type=layer_type)
+                                            lrelu_negative_slope=lrelu_negative_slope, layer_type=DenseConv3d)
 
     def forward(self, x):
         n, c, X, Y, Z = x.shape

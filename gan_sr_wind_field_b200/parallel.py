@@ -51,11 +51,19 @@ class GradSync:
             for p in b.params:
                 self._where[p] = b
         self._active = False
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self._params = params
+        self._hooks = {}
+
+    def _ensure_hooks(self):
+        # hooks can only be attached while a parameter requires grad (D's are frozen during G steps)
+        for p in self._params:
+            if p.requires_grad and p not in self._hooks:
+                self._hooks[p] = p.register_post_accumulate_grad_hook(self._on_grad)
 
     def begin(self):
         """Arm the hooks for one backward pass."""
         self._active = self.world > 1
+        self._ensure_hooks()
         for b in self.buckets:
             b.pending = sum(1 for p in b.params if p.requires_grad)
             b.work = None
@@ -109,6 +117,6 @@ class GradSync:
             b.work = None
 
     def remove(self):
-        for h in self._hooks:
+        for h in self._hooks.values():
             h.remove()
-        self._hooks = []
+        self._hooks = {}

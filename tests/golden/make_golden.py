@@ -24,7 +24,7 @@ from GAN_models.wind_field_GAN_3D import get_norm_factors_of_gradients, wind_fie
 
 
 def npd(sd, prefix):
-    return {f"{prefix}{k}": v.detach().numpy() for k, v in sd.items()}
+    return {f"{prefix}{k}": v.detach().clone().numpy() for k, v in sd.items()}
 
 
 def save(name, **arrays):

@@ -1,0 +1,194 @@
+"""GPU parity of the drop-in modules, the fused wind loss and the GAN step against the golden fixtures produced
+by the unmodified reference (tests/golden/make_golden.py) and against the CPU oracle at full size.
+Tolerances are the north star's: rel-L2 <= 1e-5 (FP32 mode) / 2e-2 (BF16 mode); where a quantity is the result
+of a long fp32 reduction chain re-associated by the GPU (gradients through ~50 layers, BatchNorm statistics) the
+FP32 bound is stated next to the assertion."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import GOLDEN, TOL, load_npz, rel_l2, sd_from, small_generator_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+def _generator(sd):
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    G = Generator_3D(**small_generator_kwargs()).cuda()
+    G.load_state_dict(sd)
+    return G
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_generator_forward_backward_vs_golden(mode):
+    from gan_sr_wind_field_b200 import ops
+    z = load_npz("generator_small.npz")
+    G = _generator(sd_from(z, "sd/"))
+    G.train()
+    LR = torch.from_numpy(z["LR"]).cuda().requires_grad_(True)
+    Z = torch.from_numpy(z["Z"]).cuda()
+    with ops.precision(mode):
+        out = G(LR, Z)
+        assert out.shape == z["out"].shape and out.dtype == torch.float32 and out.is_contiguous()
+        (out * torch.from_numpy(z["r"]).cuda()).sum().backward()
+    tol = TOL[mode]
+    assert rel_l2(out, z["out"]) <= tol
+    gtol = 5e-5 if mode == "fp32" else tol  # fp32: ~50-layer gradient chain, re-associated fp32 sums
+    assert rel_l2(LR.grad, z["grad_LR"]) <= gtol
+    params = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith("grad/"):
+            assert rel_l2(params[k[5:]].grad, z[k]) <= gtol, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["slicing", "full"])
+def test_discriminator_vs_golden(tag, mode):
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.Discriminator_3D import Discriminator_3D
+    z = load_npz(f"discriminator_{tag}.npz")
+    D = Discriminator_3D(3, 4, enable_slicing=(tag == "slicing"), dropout_probability=0.0).cuda()
+    D.load_state_dict(sd_from(z, "sd/"))
+    x = torch.from_numpy(z["x"].astype(np.float32)).cuda().requires_grad_(True)
+    tol = TOL[mode]
+    with ops.precision(mode):
+        D.train()
+        out = D(x)
+        out.sum().backward()
+        assert rel_l2(out, z["out_train"]) <= (1e-4 if mode == "fp32" else 5 * tol)  # 10 BatchNorms in series
+        sd = D.state_dict()
+        for k in z.files:
+            if k.startswith("after/"):
+                assert rel_l2(sd[k[6:]], z[k]) <= (1e-5 if mode == "fp32" else tol), k
+        gtol = 2e-4 if mode == "fp32" else 5 * tol
+        assert rel_l2(x.grad[:, :, ::4, ::4, :], z["grad_x_sub"]) <= gtol
+        params = dict(D.named_parameters())
+        for k in z.files:
+            if k.startswith("grad/"):
+                assert rel_l2(params[k[5:]].grad, z[k]) <= gtol, k
+        D.eval()
+        with torch.no_grad():
+            out_eval = D(x.detach())
+        assert rel_l2(out_eval, z["out_eval_after"]) <= (1e-4 if mode == "fp32" else 5 * tol)
+
+
+def test_wind_gradient_and_loss_vs_golden():
+    from gan_sr_wind_field_b200 import ops
+    z = load_npz("windloss.npz")
+    HR, Z, x, y = (torch.from_numpy(z[k]).cuda() for k in ("HR", "Z", "x", "y"))
+    # the 9-channel Jacobian itself (calculate_gradient_of_wind_field): same operation order as torch -> ~1 ulp
+    assert rel_l2(ops.wind_gradient(HR, x, y, Z), z["jac_HR"]) <= 1e-6
+    assert rel_l2(ops.wind_gradient(torch.from_numpy(z["SR"]).cuda(), x, y, Z), z["jac_SR"]) <= 1e-6
+    w = z["weights"].tolist()
+    cnt = float(HR.shape[0] * HR.shape[2] * HR.shape[3] * HR.shape[4])
+    for sr_key, sfx in (("SR", ""), ("SR2", "2")):
+        SR = torch.from_numpy(z[sr_key]).cuda().requires_grad_(True)
+        s = ops.windloss_slots(HR, SR, Z, x, y)
+        norm = [torch.maximum(s[6 + 2 * k], s[7 + 2 * k] / 100) for k in range(4)]
+        assert np.allclose([float(n) for n in norm], z["norms" + sfx], rtol=1e-6)
+        terms = [s[4] / (3 * cnt), s[0] / (6 * cnt) / norm[0] ** 2, s[1] / (3 * cnt) / norm[1] ** 2,
+                 s[2] / cnt / norm[2] ** 2, s[3] / cnt / norm[3] ** 2]
+        assert np.allclose([float(t) for t in terms], z["terms" + sfx], rtol=1e-5)
+        total = sum(wi * ti for wi, ti in zip(w, terms))
+        total.backward()
+        assert abs(float(total) - float(z["total" + sfx])) <= 1e-5 * abs(float(z["total" + sfx]))
+        assert rel_l2(SR.grad, z["dSR" + sfx]) <= 1e-5  # includes the path through SR_max/100 for SR2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_gan_step_vs_golden(mode):
+    """One G step and one D step of wind_field_GAN_3D.optimize_parameters against the reference's."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.config.config import Config
+    from gan_sr_wind_field_b200.GAN_models.wind_field_GAN_3D import wind_field_GAN_3D
+    z = load_npz("gan_step.npz")
+    cfg = Config(os.path.join(GOLDEN, "configs", "tiny_gan.ini"))
+    cfg.is_train, cfg.gpu_id, cfg.device = True, 0, torch.device("cuda:0")
+    gan = wind_field_GAN_3D(cfg)
+    gan.G.load_state_dict(sd_from(z, "G0/"))
+    gan.D.load_state_dict(sd_from(z, "D0/"))
+    LR, HR, Z, x, y = (torch.from_numpy(z[k]).cuda() for k in ("LR", "HR", "Z", "x", "y"))
+    gan.feed_xy_niter(x, y, torch.tensor(cfg.training.niter, device="cuda"), cfg.training.d_g_train_ratio,
+                      cfg.training.d_g_train_period)
+    tol = 1e-4 if mode == "fp32" else TOL[mode]
+    with ops.precision(mode):
+        gan.optimize_parameters(LR, HR, Z, 1)  # G step
+        for k, v in gan.get_G_train_loss_dict_ref().items():
+            ref = float(z[f"G_step/loss/{k}"])
+            assert abs(float(v) - ref) <= tol * max(abs(ref), 1e-3), (k, float(v), ref)
+        pg = dict(gan.G.named_parameters())
+        for k in z.files:
+            if k.startswith("G_step/grad/"):
+                assert rel_l2(pg[k[12:]].grad, z[k]) <= (2e-4 if mode == "fp32" else 2.5 * tol), k
+        gan.optimize_parameters(LR, HR, Z, 2)  # D step
+        ref = float(z["D_step/loss"])
+        assert abs(float(gan.get_D_loss_dict_ref()["train_loss"]) - ref) <= (1e-4 if mode == "fp32" else 0.05) * abs(ref)
+        if mode == "fp32":
+            pd_ = dict(gan.D.named_parameters())
+            for k in z.files:
+                if k.startswith("D_step/grad/"):
+                    assert rel_l2(pd_[k[12:]].grad, z[k]) <= 5e-3, k
+            # Adam's first step moves every weight by ~lr*sign(g): compare the update, not the tiny gradients
+            for k in z.files:
+                if k.startswith("G_step/param/"):
+                    name = k[13:]
+                    upd = pg[name].detach().cpu() - torch.from_numpy(z[f"G0/{name}"])
+                    ref_upd = torch.from_numpy(z[k]) - torch.from_numpy(z[f"G0/{name}"])
+                    assert rel_l2(upd, ref_upd) <= 0.05, name
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_full_size_upscale8_generator_vs_oracle(mode):
+    """BASELINE.json config #1 shapes: the shipped upscale8 architecture (128 features, 16 RRDBs, 5x5x5 HR convs),
+    LR (1,4,16,16,10) -> SR (1,3,128,128,10), against the CPU oracle with the same weights."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    from gan_sr_wind_field_b200.tools import initialization
+    from oracle import wind_oracle as wo
+    torch.manual_seed(2001)
+    G = Generator_3D(4, 3, 128, 16, upscale=8, hr_kern_size=5, lff_kern_size=1, dropout_probability=0.1)
+    initialization.init_weights(G, 0.1)
+    G.eval()
+    LR, HR, Z, x, y = wo.synthetic_batch(1, hr_xy=128, nz=10, scale=8, seed=2001)
+    with torch.no_grad():
+        ref = wo.generator_forward(G.state_dict(), LR, Z)
+    G.cuda()
+    with ops.precision(mode), torch.no_grad():
+        out = G(LR.cuda(), Z.cuda())
+    assert out.shape == (1, 3, 128, 128, 10)
+    assert rel_l2(out, ref) <= TOL[mode]
+
+
+def test_size_independent_properties_full_size():
+    """At the full 144-channel 128x128x10 shape (too slow for the CPU oracle in backward): linearity of the
+    tensor-core conv in its input, and <dy, conv(x)> == <dgrad(dy), x> == <wgrad(x, dy), w> (adjointness)."""
+    from gan_sr_wind_field_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, c, vol = 1, 144, (128, 128, 10)
+    with ops.precision("bf16"):
+        mk = lambda *s: torch.randn(*s, generator=g, device="cuda")
+        xa = ops.empty_cl(n, c, *vol, torch.bfloat16, "cuda")
+        xb = ops.empty_cl(n, c, *vol, torch.bfloat16, "cuda")
+        xa.copy_(mk(n, c, *vol))
+        xb.copy_(mk(n, c, *vol))
+        w = (mk(c, c, 5, 5, 5) / (c * 125) ** 0.5).bfloat16().float()  # bf16-exact weights
+        shape = ops.make_shape(xa.shape, c, (5, 5, 5), 1, 2)
+        ya, yb, yab = (ops.empty_cl(n, c, *vol, torch.float32, "cuda") for _ in range(3))
+        ops.conv_fwd(xa, w, None, shape, ya)
+        ops.conv_fwd(xb, w, None, shape, yb)
+        xs = ops.empty_cl(n, c, *vol, torch.bfloat16, "cuda")
+        xs.copy_((xa.float() + xb.float()) * 0.5)  # may round; compare against the rounded sum
+        ops.conv_fwd(xs, w, None, shape, yab)
+        xs_exact = xs.float()
+        lin = rel_l2(yab, (ya + yb) * 0.5)
+        assert lin <= 1e-2, lin
+        dy = ops.empty_cl(n, c, *vol, torch.bfloat16, "cuda")
+        dy.copy_(mk(n, c, *vol))
+        dx = ops.empty_cl(n, c, *vol, torch.float32, "cuda")
+        ops.conv_dgrad(dy, w, None, shape, dx)
+        dw, _ = ops.conv_wgrad(xa, dy, shape)
+        lhs = float((dy.float() * ya).sum())
+        assert abs(float((dx * xa.float()).sum()) - lhs) <= 2e-3 * abs(lhs)
+        assert abs(float((dw * w).sum()) - lhs) <= 2e-3 * abs(lhs)

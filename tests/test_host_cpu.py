@@ -1,0 +1,238 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/windsr.h declares,
+the drop-in modules keep the reference's constructors / state_dict keys / seeded initialisation, the ini reader
+matches the reference's, the product path refuses to run without CUDA (no fallback), and the data-parallel
+gradient exchange averages correctly (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import refshim
+from tests.util import GOLDEN, ROOT, load_npz, sd_from, small_generator_kwargs
+
+needs_reference = pytest.mark.skipif(not refshim.available(), reason="reference not mounted")
+CONFIGS = os.path.join(GOLDEN, "configs")
+
+
+def test_library_exports_every_declared_symbol():
+    from gan_sr_wind_field_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "windsr.h")).read()
+    declared = set(re.findall(r"\b(ws_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ws_tensor", "ws_conv_shape", "ws_epilogue"}
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().ws_version() == 1
+    # struct layouts agree with the header (sizes the C side was compiled with)
+    assert ctypes.sizeof(_lib.WsTensor) == 40 and ctypes.sizeof(_lib.WsConvShape) == 60
+    assert ctypes.sizeof(_lib.WsEpilogue) == 3 * 8 + 4 * 4 + 3 * 40 + 16 + 40 + 16
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    from gan_sr_wind_field_b200 import _lib, ops
+    x = torch.zeros(1, 16, 2, 2, 2)
+    w = torch.zeros(8, 16, 3, 3, 3)
+    shape = ops.make_shape(x.shape, 8, (3, 3, 3), 1, 1)
+    with pytest.raises(_lib.WindSRError):
+        ops.conv_fwd(x, w, None, shape, torch.zeros(1, 8, 2, 2, 2))
+    with pytest.raises(_lib.WindSRError):
+        ops.wind_gradient(torch.zeros(1, 3, 4, 4, 4), torch.arange(4.0), torch.arange(4.0), torch.zeros(1, 1, 4, 4, 4))
+    pkg = os.path.join(ROOT, "gan_sr_wind_field_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "cudnn" not in text.lower() or f.endswith(".py") and "no cudnn" in text.lower() or \
+                    "cuDNN" in text and "fallback" in text, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from gan_sr_wind_field_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libwindsr.so")
+    with pytest.raises(_lib.WindSRError):
+        _lib.load()
+
+
+def test_state_dict_keys_and_sizes():
+    from gan_sr_wind_field_b200.CNN_models.Discriminator_3D import Discriminator_3D
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    z = load_npz("generator_small.npz")
+    ref_sd = sd_from(z, "sd/")
+    G = Generator_3D(**small_generator_kwargs())
+    mine = G.state_dict()
+    assert list(mine.keys()) == list(ref_sd.keys())
+    assert all(mine[k].shape == ref_sd[k].shape for k in mine)
+    G.load_state_dict(ref_sd)  # strict
+    # the shipped upscale8 architecture: 298 tensors / 35 211 939 params; D: 59 / 12 308 009
+    Gf = Generator_3D(4, 3, 128, 16, upscale=8, hr_kern_size=5, lff_kern_size=1, dropout_probability=0.1)
+    assert len(Gf.state_dict()) == 298 and sum(p.numel() for p in Gf.parameters()) == 35_211_939
+    assert Gf.state_dict()["hr_convs.0.0.weight"].shape == (144, 144, 5, 5, 5)
+    assert Gf.state_dict()["model.1.module.3.RDBs.2.conv3.conv.0.weight"].shape == (32, 224, 3, 3, 3)
+    Df = Discriminator_3D(3, 32)
+    assert len(Df.state_dict()) == 59 and sum(p.numel() for p in Df.parameters()) == 12_308_009
+    for tag, slicing in (("full", False), ("slicing", True)):
+        ref_d = sd_from(load_npz(f"discriminator_{tag}.npz"), "sd/")
+        D = Discriminator_3D(3, 4, enable_slicing=slicing)
+        assert list(D.state_dict().keys()) == list(ref_d.keys())
+        D.load_state_dict(ref_d)
+    # attribute surface callers touch (plot_data.py:773-778, wind_field_GAN_3D.py:581)
+    import copy
+    assert isinstance(Gf.model[:2], torch.nn.Sequential) and isinstance(Gf.hr_convs[:-2], torch.nn.Sequential)
+    feats = copy.deepcopy(Df.features)
+    assert sum(p.numel() for p in feats.parameters()) == sum(p.numel() for p in Df.features.parameters())
+    assert "Conv3d" in str(Gf) and Gf.max_norm == 1.0
+
+
+@needs_reference
+def test_seeded_construction_equals_reference():
+    """Same seed -> bit-identical initial parameters (constructor RNG order + init_weights class-name match)."""
+    refshim.activate()
+    from CNN_models.Discriminator_3D import Discriminator_3D as RefD
+    from CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D as RefG
+    import tools.initialization as ref_init
+    from gan_sr_wind_field_b200.CNN_models.Discriminator_3D import Discriminator_3D
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    from gan_sr_wind_field_b200.tools import initialization
+    kw = small_generator_kwargs()
+    torch.manual_seed(5)
+    a = RefG(*[kw[k] for k in ("in_channels", "out_channels", "number_of_features", "number_of_RRDBs")],
+             **{k: v for k, v in kw.items() if k not in ("in_channels", "out_channels", "number_of_features",
+                                                          "number_of_RRDBs")})
+    ref_init.init_weights(a, 0.1)
+    torch.manual_seed(5)
+    b = Generator_3D(**kw)
+    initialization.init_weights(b, 0.1)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    for slicing in (False, True):
+        torch.manual_seed(6)
+        a = RefD(3, 4, enable_slicing=slicing)
+        ref_init.init_weights(a, 0.2)
+        torch.manual_seed(6)
+        b = Discriminator_3D(3, 4, enable_slicing=slicing)
+        initialization.init_weights(b, 0.2)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_constructor_errors_match_reference_behaviour():
+    from gan_sr_wind_field_b200.CNN_models import torch_blocks as tb
+    with pytest.raises(ValueError):
+        tb.RDB(16, 8, 5, lff_kern_size=2, mode="3D")
+    with pytest.raises(NotImplementedError):
+        tb.create_discriminator_block(3, 8, feat_kern_size=7, mode="3D")
+    with pytest.raises(NotImplementedError):
+        tb.create_conv_lrelu_layer(3, 8, 3, normalization_type="layer")
+    with pytest.raises(NotImplementedError):
+        tb.RDB(16, 8, 5, mode="weird")
+
+
+def test_config_reader_on_shipped_inis():
+    from gan_sr_wind_field_b200.config.config import Config
+    cfg = Config(os.path.join(CONFIGS, "upscale8_pix4_no_adv_no_slicing.ini"))
+    assert cfg.scale == 8 and cfg.gpu_id == 0
+    g, t = cfg.generator, cfg.training
+    assert (g.num_features, g.num_RRDB, g.hr_kern_size, g.lff_kern_size, g.RDB_growth_chan) == (128, 16, 5, 1, 32)
+    assert g.conv_mode is None and cfg.gan_config.conv_mode == "3D" and g.dropout_probability == 0.1
+    assert t.multistep_lr_steps == [10000, 30000, 50000, 70000, 100000] and t.d_g_train_ratio == 0
+    assert (t.pixel_loss_weight, t.gradient_xy_loss_weight, t.gradient_z_loss_weight) == (0.136, 3.064, 0.0)
+    assert cfg.dataset_train.batch_size == 8 and cfg.gan_config.enable_slicing is False
+    local = Config(os.path.join(CONFIGS, "wind_field_GAN_3D_config_local.ini"))
+    assert local.scale == 4 and local.gan_config.enable_slicing is True and local.dataset_train.batch_size == 1
+    with pytest.raises(FileNotFoundError):
+        Config("/nonexistent.ini")
+
+
+@needs_reference
+def test_config_reader_equals_reference():
+    refshim.activate()
+    import config.config as ref_config
+    from gan_sr_wind_field_b200.config.config import Config
+    for name in sorted(os.listdir(CONFIGS)):
+        path = os.path.join(CONFIGS, name)
+        ref, mine = ref_config.Config(path), Config(path)
+        for attr in ("name", "model", "scale", "gpu_id", "use_tensorboard_logger", "load_model_from_save"):
+            assert getattr(ref, attr) == getattr(mine, attr), (name, attr)
+        for sec in ("env", "gan_config", "generator", "discriminator", "training", "dataset_train", "dataset_val",
+                    "dataset_test"):
+            r, m = getattr(ref, sec), getattr(mine, sec)
+            assert (r is None) == (m is None), (name, sec)
+            if r is None:
+                continue
+            for k, v in vars(r).items():
+                assert getattr(m, k) == v, (name, sec, k, v, getattr(m, k))
+
+
+def test_schedule_and_labels():
+    """G/D alternation in blocks of d_g_train_period and the one-sided label smoothing ramp
+    (wind_field_GAN_3D.py:585-587, 627-678), decided on the host without touching the device."""
+    from gan_sr_wind_field_b200.config.config import Config
+    from gan_sr_wind_field_b200.GAN_models.wind_field_GAN_3D import wind_field_GAN_3D
+    cfg = Config(os.path.join(CONFIGS, "tiny_gan.ini"))
+    cfg.is_train, cfg.device = True, torch.device("cpu")
+    gan = wind_field_GAN_3D(cfg)
+    gan.feed_xy_niter(torch.arange(4.0), torch.arange(4.0), torch.tensor(100), 1, 2)
+    assert [gan.is_G_iteration(i) for i in range(8)] == [True, True, False, False, True, True, False, False]
+    gan.batch_size = 3
+    gan.make_new_labels(0)
+    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.9)) and gan._labels_are_exactly_point_nine
+    gan.make_new_labels(50)
+    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.95)) and not gan._labels_are_exactly_point_nine
+    assert torch.equal(gan.fake_HR_labels, torch.zeros(3))
+    assert gan.count_params() == (sum(p.numel() for p in gan.G.parameters()),
+                                  sum(p.numel() for p in gan.D.parameters()))
+
+
+_DDP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from gan_sr_wind_field_b200.parallel import GradSync
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 1))
+frozen = net[2].bias
+frozen.requires_grad = False                      # like D's parameters during a G step
+sync = GradSync(net.parameters(), bucket_bytes=256)   # several small buckets
+data = torch.randn(world, 5, 8, generator=torch.Generator().manual_seed(1))
+sync.begin()
+net(data[rank]).pow(2).mean().backward()
+sync.finish()
+# reference: mean over ranks of the per-rank gradients, computed locally
+ref = [torch.zeros_like(p) for p in net.parameters()]
+for r in range(world):
+    net2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 1))
+    net2.load_state_dict(net.state_dict())
+    net2[2].bias.requires_grad = False
+    net2(data[r]).pow(2).mean().backward()
+    for acc, p in zip(ref, net2.parameters()):
+        if p.grad is not None:
+            acc += p.grad / world
+ok = all((p.grad is None and not p.requires_grad) or torch.allclose(p.grad, r_, atol=1e-6)
+         for p, r_ in zip(net.parameters(), ref))
+# a second step re-arms cleanly
+net.zero_grad(set_to_none=True)
+sync.begin(); net(data[rank]).pow(2).mean().backward(); sync.finish()
+ok = ok and all((p.grad is None) or torch.allclose(p.grad, r_, atol=1e-6) for p, r_ in zip(net.parameters(), ref))
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+def test_grad_sync_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_DDP_WORKER)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env))
+    codes = [p.wait(timeout=180) for p in procs]
+    assert codes == [0, 0], codes

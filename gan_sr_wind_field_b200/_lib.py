@@ -53,6 +53,7 @@ SYMBOLS = [
     ("ws_version", _I, []),
     ("ws_last_error", C.c_char_p, []),
     ("ws_device_supports_tcgen05", _I, []),
+    ("ws_launch_count", _L, []),
     ("ws_packed_weight_bytes", _Z, [_SP, _I]),
     ("ws_pack_weights", _I, [_P, _SP, _I, _P, _P]),
     ("ws_conv3d_fwd_path", _I, [_SP, _TP, _TP, _I]),

@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary declared in include/windsr.h: argument validation, path selection
 // (CUDA-core FFMA vs tcgen05) and launch.  No torch types, no allocation, no exceptions cross this file.
+#include <atomic>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -15,6 +16,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int validate_shape(const ws_conv_shape* s) {
   WS_REQUIRE(s != nullptr, "null conv shape");
@@ -130,6 +134,7 @@ extern "C" {
 int ws_version(void) { return WS_VERSION; }
 const char* ws_last_error(void) { return g_err; }
 int ws_device_supports_tcgen05(void) { return device_cc_major() == 10 ? 1 : 0; }
+int64_t ws_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 size_t ws_packed_weight_bytes(const ws_conv_shape* s, int kind) {
   if (!s) return 0;

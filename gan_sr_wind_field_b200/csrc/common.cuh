@@ -9,6 +9,7 @@
 namespace ws {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n);
 
 #define WS_CHECK_CUDA(expr)                                                                  \
   do {                                                                                       \
@@ -17,6 +18,13 @@ void set_error(const char* fmt, ...);
       ws::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return 1;                                                                              \
     }                                                                                        \
+  } while (0)
+
+// after every kernel launch: count it (ws_launch_count) and surface launch errors
+#define WS_POST_LAUNCH(n)                 \
+  do {                                    \
+    ws::count_launch(n);                  \
+    WS_CHECK_CUDA(cudaGetLastError());    \
   } while (0)
 
 #define WS_REQUIRE(cond, ...)      \

@@ -480,7 +480,7 @@ int launch_igemm(const ConvGeom& g, const View& src, const float* w, const View&
   else if (CN > 8) WS_LAUNCH(128, 16, 4, 2);
   else WS_LAUNCH(256, 8, 4, 2);
 #undef WS_LAUNCH
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -502,7 +502,7 @@ size_t simt_wgrad_workspace_bytes(const ConvGeom& g) {
 int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumulate, cudaStream_t st) {
   if (c <= 0) return 0;
   bias_grad_kernel<<<c, 512, 0, st>>>(dy, db, n, c, v, accumulate);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -512,7 +512,7 @@ int wgrad_finalize_launch(const float* wsp, float* dw, int taps, int cin, int co
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_finalize<<<blocks, 256, 0, st>>>(wsp, dw, taps, cin, cout, accumulate);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -552,7 +552,7 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   else if (bm == 4 && bn == 16) WS_WG(4, 16, 1, 1);
   else WS_WG(4, 4, 1, 1);
 #undef WS_WG
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
 }
 

@@ -447,7 +447,7 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
   WS_REQUIRE(smem <= 227 * 1024, "tcgen05 conv: smem request %zu too large", smem);
   dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y * p.tiles_z), (unsigned)n_tiles);
   conv3d_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p, dst, ep);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 

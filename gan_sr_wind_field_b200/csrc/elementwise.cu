@@ -375,7 +375,7 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
     pack_tc<<<grid_for(total), kBlock, 0, st>>>(w, (__nv_bfloat16*)packed, g.cout, g.cin, taps, rows, cols,
                                                dgrad);
   }
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -397,7 +397,7 @@ int copy_launch(const View& src, const View& dst, int n, int c, long long v, cud
   } else {
     copy_kernel<<<grid_for(total), kBlock, 0, st>>>(src, dst, n, c, v, c_fastest_of(dst));
   }
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -406,7 +406,7 @@ int axpby_launch(const View& x1, float a, const View& x2, float b, const View& y
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
   axpby_kernel<<<grid_for(total), kBlock, 0, st>>>(x1, a, x2, b, y, n, c, v, c_fastest_of(y));
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -416,7 +416,7 @@ int lrelu_bwd_launch(const View& dy, const View& yv, float slope, const float* c
   if (total <= 0) return 0;
   lrelu_bwd_kernel<<<grid_for(total), kBlock, 0, st>>>(dy, yv, slope, chan_scale, oscale, g, n, c, v,
                                                       c_fastest_of(g));
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -436,7 +436,7 @@ int upsample_fwd_launch(const View& in, const View& out, int n, int c, int x, in
     upsample_fwd_generic<<<grid_for((long long)n * c * vi * 4), kBlock, 0, st>>>(in, out, n, c, x, y, z,
                                                                                 c_fastest_of(out));
   }
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -445,7 +445,7 @@ int upsample_bwd_launch(const View& dout, const View& din, int n, int c, int x, 
   long long total = (long long)n * c * x * y * z;
   if (total <= 0) return 0;
   upsample_bwd_generic<<<grid_for(total), kBlock, 0, st>>>(dout, din, n, c, x, y, z, c_fastest_of(din));
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -454,7 +454,7 @@ int bn_finalize_launch(const float* sum, const float* sqsum, long long count, in
                        float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sqsum, count, c, gamma, beta, eps, momentum, rm,
                                                       rv, scale, shift, save_mean, save_invstd);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -464,7 +464,7 @@ int scale_shift_lrelu_launch(const View& x, const float* scale, const float* shi
   if (total <= 0) return 0;
   scale_shift_lrelu_kernel<<<grid_for(total), kBlock, 0, st>>>(x, scale, shift, slope, y, n, c, v,
                                                               c_fastest_of(y));
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -479,7 +479,7 @@ int bn_bwd_reduce_launch(const View& dy, const View& yv, const View& x, const fl
   if (slices > 64) slices = 64;
   dim3 grid(c, slices);
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, yv, x, mean, invstd, slope, sum_g, sum_gx, n, c, v, slices);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -492,7 +492,7 @@ int bn_bwd_apply_launch(const View& dy, const View& yv, const View& x, const flo
   bn_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(dy, yv, x, mean, invstd, gamma, sum_g, sum_gx,
                                                          slope, 1.f / (float)count, dx, n, c, v,
                                                          c_fastest_of(dx));
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 

@@ -327,7 +327,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   dim3 grid((unsigned)p.tap_groups, (unsigned)splits);
   if (!swap) wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_dy, tm_x, p, wsp);
   else wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_dy, p, wsp);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -365,7 +365,7 @@ int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, i
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_tc_finalize<<<blocks, 256, 0, st>>>(wsp, dw, g.taps(), g.cin, g.cout, accumulate);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 

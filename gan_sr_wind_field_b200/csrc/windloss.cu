@@ -390,7 +390,7 @@ inline int grid_for(long long total) {
 int axis_coeffs_launch(const float* coords, int len, float* coef, cudaStream_t st) {
   if (len <= 0) return 0;
   axis_coeffs_kernel<<<(len + 127) / 128, 128, 0, st>>>(coords, len, coef);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -399,7 +399,7 @@ int wind_gradient_launch(const View& f, const View& zalt, const float* cx, const
   long long total = (long long)n * x * y * z;
   if (total <= 0) return 0;
   wind_gradient_kernel<<<grid_for(total), kBlock, 0, st>>>(f, zalt, cx, cy, out, n, x, y, z);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -414,7 +414,7 @@ int windloss_fwd_launch(const View& hr, const View& sr, const View& zalt, const 
   if (total > 0)
     windloss_fwd_kernel<<<grid_for(total), kBlock, 0, st>>>(hr, sr, zalt, cx, cy, n, x, y, z, scratch);
   windloss_finalize_kernel<<<1, 32, 0, st>>>(scratch, result, argmax);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(3);
   return 0;
 }
 
@@ -429,7 +429,7 @@ int windloss_bwd_launch(const View& hr, const View& sr, const View& zalt, const 
   float* G = (float*)workspace;
   windloss_bwd_G_kernel<<<grid_for(total), kBlock, 0, st>>>(hr, sr, zalt, cx, cy, n, x, y, z, coef, argmax, G);
   windloss_bwd_apply_kernel<<<grid_for(total), kBlock, 0, st>>>(hr, sr, zalt, cx, cy, n, x, y, z, coef, G, dsr);
-  WS_CHECK_CUDA(cudaGetLastError());
+  WS_POST_LAUNCH(2);
   return 0;
 }
 

@@ -157,6 +157,42 @@ def wgrad_path(shape: WsConvShape, x: torch.Tensor, dy: torch.Tensor, math: Opti
                                        math_mode() if math is None else math)
 
 
+# Optional in-stream timing of selected launches (bench.py's roofline leg): CUDA events recorded on the
+# launching stream right around the kernel, nothing else changes.
+_KERNEL_TIMER = None
+
+
+def set_kernel_timer(predicate) -> None:
+    """predicate(kind, shape) -> bool selects launches ('fwd' | 'dgrad' | 'wgrad'); None switches it off."""
+    global _KERNEL_TIMER
+    _KERNEL_TIMER = (predicate, []) if predicate is not None else None
+
+
+def kernel_timer_events():
+    return _KERNEL_TIMER[1] if _KERNEL_TIMER is not None else []
+
+
+class _timed:
+    def __init__(self, kind, shape):
+        self.on = _KERNEL_TIMER is not None and _KERNEL_TIMER[0](kind, shape)
+
+    def __enter__(self):
+        if self.on:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.t1.record()
+            _KERNEL_TIMER[1].append((self.t0, self.t1))
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by libwindsr.so in this process so far."""
+    return int(load().ws_launch_count())
+
+
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], shape: WsConvShape,
              out: torch.Tensor, math: Optional[int] = None, **ep) -> torch.Tensor:
     """out = epilogue(conv3d(x, w)); `w` is the fp32 torch-layout weight, packed (and cached) here."""
@@ -168,8 +204,9 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], s
     kind = PACK_TC_FWD if path == PATH_TCGEN05 else PACK_SIMT_FWD
     packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
     e = _epilogue(**ep)
-    check(lib.ws_conv3d_fwd(C.byref(shape), C.byref(xv), packed.data_ptr(), C.byref(ov), C.byref(e), math,
-                            stream_ptr()), "ws_conv3d_fwd")
+    with _timed("fwd", shape):
+        check(lib.ws_conv3d_fwd(C.byref(shape), C.byref(xv), packed.data_ptr(), C.byref(ov), C.byref(e), math,
+                                stream_ptr()), "ws_conv3d_fwd")
     return out
 
 
@@ -183,8 +220,9 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights]
     kind = PACK_TC_DGRAD if path == PATH_TCGEN05 else PACK_SIMT_DGRAD
     packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
     e = _epilogue(**ep)
-    check(lib.ws_conv3d_dgrad(C.byref(shape), C.byref(dv), packed.data_ptr(), C.byref(xv), C.byref(e), math,
-                              stream_ptr()), "ws_conv3d_dgrad")
+    with _timed("dgrad", shape):
+        check(lib.ws_conv3d_dgrad(C.byref(shape), C.byref(dv), packed.data_ptr(), C.byref(xv), C.byref(e), math,
+                                  stream_ptr()), "ws_conv3d_dgrad")
     return dx
 
 
@@ -213,8 +251,9 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, shape: WsConvShape, want_bias:
     nbytes = lib.ws_conv3d_wgrad_workspace_bytes(C.byref(shape), math)
     wsp = _workspace(nbytes, x.device)
     xv, dv = view(x), view(dy)
-    check(lib.ws_conv3d_wgrad(C.byref(shape), C.byref(xv), C.byref(dv), ptr(dw), ptr(db), 0, math,
-                              wsp.data_ptr(), wsp.numel(), stream_ptr()), "ws_conv3d_wgrad")
+    with _timed("wgrad", shape):
+        check(lib.ws_conv3d_wgrad(C.byref(shape), C.byref(xv), C.byref(dv), ptr(dw), ptr(db), 0, math,
+                                  wsp.data_ptr(), wsp.numel(), stream_ptr()), "ws_conv3d_wgrad")
     return dw, db
 
 

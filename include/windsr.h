@@ -109,6 +109,8 @@ int ws_version(void);
 const char* ws_last_error(void);
 /* 1 if the current device is compute capability 10.x (tcgen05 path usable) */
 int ws_device_supports_tcgen05(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t ws_launch_count(void);
 
 /* ---- weights ---------------------------------------------------------------------------------- */
 /* bytes of a packed weight buffer of the given kind */

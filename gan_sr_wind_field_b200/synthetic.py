@@ -18,7 +18,8 @@ def _smooth(shape, gen, device, passes=2):
     f = torch.randn(shape, generator=gen, device=device)
     for _ in range(passes):
         n, c = shape[:2]
-        f = F.avg_pool3d(f.reshape(n * c, 1, *shape[2:]), (5, 5, 3), stride=1, padding=(2, 2, 1),
+        kz = 3 if shape[4] >= 3 else 1
+        f = F.avg_pool3d(f.reshape(n * c, 1, *shape[2:]), (5, 5, kz), stride=1, padding=(2, 2, kz // 2),
                          count_include_pad=False).reshape(shape)
     return f / f.abs().amax().clamp_min(1e-6)
 

@@ -432,12 +432,15 @@ __global__ void wgrad_finalize(const float* __restrict__ wsp, float* __restrict_
   }
 }
 
-// db[c] = (accumulate ? db[c] : 0) + sum_{n,v} dy(n,c,v)
-__global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, long long v, int accumulate) {
+// db[c] += sum over one slice of (n,v) of dy(n,c,v); grid (channels, slices), db pre-zeroed unless accumulating
+__global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, long long v, int slices) {
   int ch = blockIdx.x;
-  float s = 0.f;
   long long total = (long long)n * v;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+  long long per = (total + slices - 1) / slices;
+  long long beg = (long long)blockIdx.y * per;
+  long long end = beg + per < total ? beg + per : total;
+  float s = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
     int nn = (int)(i / v);
     long long vv = i % v;
     s += dy.ld(nn, ch, vv);
@@ -449,7 +452,7 @@ __global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, 
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) db[ch] = accumulate ? db[ch] + t : t;
+    if (threadIdx.x == 0) atomicAdd(&db[ch], t);
   }
 }
 
@@ -501,7 +504,14 @@ size_t simt_wgrad_workspace_bytes(const ConvGeom& g) {
 
 int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumulate, cudaStream_t st) {
   if (c <= 0) return 0;
-  bias_grad_kernel<<<c, 512, 0, st>>>(dy, db, n, c, v, accumulate);
+  if (!accumulate) WS_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
+  long long total = (long long)n * v;
+  int slices = (int)((total + 8191) / 8192);
+  int max_slices = (148 * 8 + c - 1) / c;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  dim3 grid(c, slices);
+  bias_grad_kernel<<<grid, 256, 0, st>>>(dy, db, n, c, v, slices);
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -101,13 +101,18 @@ class PackedWeights:
     def __init__(self):
         self._cache = {}
 
-    def get(self, w: torch.Tensor, shape: WsConvShape, kind: int) -> torch.Tensor:
-        key = kind
+    def get(self, w: torch.Tensor, shape: WsConvShape, kind: int, pad_cout: int = 0) -> torch.Tensor:
+        """``pad_cout`` > w.shape[0]: pack as if the layer had that many output channels (extra filters zero) —
+        lets the 3-channel hr_convs.2 run its dgrad / wgrad on the tensor-core kernels (UMMA needs K, N >= 16)."""
+        key = (kind, pad_cout)
         stamp = (w._version, w.data_ptr(), shape.cin, shape.cout)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
-        packed = pack_weights(w, shape, kind)
+        src = w
+        if pad_cout > w.shape[0]:
+            src = torch.cat((w.detach(), w.new_zeros((pad_cout - w.shape[0],) + tuple(w.shape[1:]))), 0)
+        packed = pack_weights(src, shape, kind)
         self._cache[key] = (stamp, packed)
         return packed
 
@@ -211,14 +216,17 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], s
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], shape: WsConvShape,
-               dx: torch.Tensor, math: Optional[int] = None, **ep) -> torch.Tensor:
+               dx: torch.Tensor, math: Optional[int] = None, pad_cout: int = 0, **ep) -> torch.Tensor:
+    """``shape.cout`` must already be the padded count when ``pad_cout`` is used (dy has that many channels)."""
     _require_cuda(dy)
     lib = load()
     math = math_mode() if math is None else math
     dv, xv = view(dy), view(dx)
     path = lib.ws_conv3d_dgrad_path(C.byref(shape), C.byref(dv), C.byref(xv), math)
     kind = PACK_TC_DGRAD if path == PATH_TCGEN05 else PACK_SIMT_DGRAD
-    packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
+    if cache is None:
+        cache = PackedWeights()
+    packed = cache.get(w, shape, kind, pad_cout=pad_cout)
     e = _epilogue(**ep)
     with _timed("dgrad", shape):
         check(lib.ws_conv3d_dgrad(C.byref(shape), C.byref(dv), packed.data_ptr(), C.byref(xv), C.byref(e), math,
@@ -365,14 +373,27 @@ class ConvFn(torch.autograd.Function):
         else:
             g = dy
         dx = dw = db = None
+        pad_cout = 0
+        if (cdt == torch.bfloat16 and shape.cout < 16 <= shape.cin and x.dtype == torch.bfloat16
+                and (shape.sx, shape.sy, shape.sz) == (1, 1, 1)):
+            # narrow output (hr_convs.2: 144 -> 3): zero-pad the gradient to 16 channels so dgrad and wgrad run on
+            # the tensor-core kernels instead of the CUDA-core family
+            pad_cout = 16
+            gp = zeros_cl(g.shape[0], pad_cout, *g.shape[2:], cdt, g.device)
+            copy_(g, gp[:, :shape.cout])
+            g = gp
+            shape = make_shape(x.shape, pad_cout, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
         if need_w or (need_b and ctx.has_bias):
             dw, db = conv_wgrad(x, g, shape, want_bias=ctx.has_bias and need_b, want_weight=need_w)
+            if pad_cout:
+                dw = dw[:weight.shape[0]].contiguous() if dw is not None else None
+                db = db[:weight.shape[0]].contiguous() if db is not None else None
         if need_x:
             if cfg.get("dx_contig"):
                 dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
             else:
                 dx = empty_cl(*x.shape, torch.float32 if cfg.get("dx_f32") else cdt, x.device)
-            conv_dgrad(g, weight, cfg.get("cache"), shape, dx)
+            conv_dgrad(g, weight, cfg.get("cache"), shape, dx, pad_cout=pad_cout)
         return dx, dw, db, dres, None
 
 

@@ -40,6 +40,8 @@ size_t simt_wgrad_workspace_bytes(const ConvGeom&);
 int bias_grad(const View&, float*, int, int, long long, int, cudaStream_t);
 bool tc_view_ok(const View&, int);
 int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t);
+int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t);
+bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
 int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
@@ -180,8 +182,13 @@ int ws_conv3d_fwd(const ws_conv_shape* s, const ws_tensor* in, const void* packe
   ConvGeom g(*s);
   View vin(in), vout(out);
   Epi e(ep, g.cout);
-  if (fwd_path(g, vin, math) == WS_PATH_TCGEN05)
+  if (fwd_path(g, vin, math) == WS_PATH_TCGEN05) {
+    if (tc2_enabled()) {
+      int r = tc2_conv_launch(g, 0, vin, packed_w, vout, e, (cudaStream_t)stream);
+      if (r >= 0) return r;  // -1: geometry not covered by the halo-tile kernel
+    }
     return tc_conv_launch(g, 0, vin, packed_w, vout, e, (cudaStream_t)stream);
+  }
   return simt_conv_fwd(g, vin, (const float*)packed_w, vout, e, (cudaStream_t)stream);
 }
 
@@ -192,8 +199,13 @@ int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* pac
   ConvGeom g(*s);
   View vdy(dy), vdx(dx);
   Epi e(ep, g.cin);
-  if (dgrad_path(g, vdy, math) == WS_PATH_TCGEN05)
+  if (dgrad_path(g, vdy, math) == WS_PATH_TCGEN05) {
+    if (tc2_enabled()) {
+      int r = tc2_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
+      if (r >= 0) return r;
+    }
     return tc_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
+  }
   return simt_conv_dgrad(g, vdy, (const float*)packed_w, vdx, e, (cudaStream_t)stream);
 }
 

@@ -106,51 +106,54 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;
   const uint32_t b_bytes = (uint32_t)p.n_umma * 128u;
 
+  // Both loops run warp-uniformly and elect one lane only around UTMALDG / UTCHMMA (see conv_tc2.cu).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
-        const int cx = x0 * p.sx - p.px + ti;
-        const int cy = y0 * p.sy - p.py + tj;
-        const int cz = z0 * p.sz - p.pz + tl;
-        for (int ch = 0; ch < p.kchunks; ++ch) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tap = 0; tap < taps; ++tap) {
+      const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
+      const int cx = x0 * p.sx - p.px + ti;
+      const int cy = y0 * p.sy - p.py + tj;
+      const int cz = z0 * p.sz - p.pz + tl;
+      for (int ch = 0; ch < p.kchunks; ++ch) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (ptx::elect_one()) {
           const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-          const uint32_t b_dst = a_dst + kABytes;
           ptx::mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
           ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), ch * 64, cz, cy, cx, n);
-          ptx::tma_load_3d(b_dst, &tmB, full_bar(stage), ch * 64, n0, tap);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          ptx::tma_load_3d(a_dst + kABytes, &tmB, full_bar(stage), ch * 64, n0, tap);
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
-      const uint32_t idesc = ptx::make_idesc(/*bf16*/ 1u, 128u, (uint32_t)p.n_umma, 0u, 0u);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int ch = it % p.kchunks;
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-        const uint32_t b_addr = a_addr + kABytes;
-        const int nk = (ch == p.kchunks - 1) ? p.last_k16 : 4;
-        for (int k = 0; k < nk; ++k) {
-          const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          ptx::mma_f16_ss(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        ptx::mma_commit(empty_bar(stage));  // slot free once these MMAs retire
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      ptx::mma_commit(accum_bar);  // accumulator complete
     }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = ptx::make_idesc(/*bf16*/ 1u, 128u, (uint32_t)p.n_umma, 0u, 0u);
+    const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int ch = it % p.kchunks;
+      ptx::mbar_wait(full_bar(stage), phase);
+      ptx::tc_fence_after();
+      const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+      const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3fffu);
+      const uint64_t bdesc = desc_hi | (uint64_t)(((a_addr + kABytes) >> 4) & 0x3fffu);
+      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : 4;
+      const uint32_t acc0 = it > 0 ? 1u : 0u;
+      if (ptx::elect_one()) {
+        ptx::mma_f16_ss(tmem_base, adesc, bdesc, idesc, acc0);
+        if (nk > 1) ptx::mma_f16_ss(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+        if (nk > 2) ptx::mma_f16_ss(tmem_base, adesc + 4, bdesc + 4, idesc, 1u);
+        if (nk > 3) ptx::mma_f16_ss(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
+        ptx::mma_commit(empty_bar(stage));  // slot free once these MMAs retire
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+    if (ptx::elect_one()) ptx::mma_commit(accum_bar);  // accumulator complete
     __syncwarp();
   } else {
     // ===== epilogue: TMEM -> registers -> fused epilogue -> global =====

@@ -1,0 +1,386 @@
+// conv_tc2.cu — second-generation tcgen05 implicit-GEMM Conv3d (stride 1, forward and data-gradient) built
+// around a TMA-staged **halo tile** of the voxel grid.
+//
+// Round-1 profiling showed conv_tc.cu (one TMA box per tap) to be bound by the L2 -> SMEM fabric: hr_convs.0
+// moved 130 GB per launch at 9.7 TB/s for 36 % tensor utilisation.  Here a CTA owns `tx` consecutive x-slabs of
+// by*Z voxels (rows ordered x slowest, then y, then z) and, per (ky, kz, 64-channel chunk), loads ONE activation
+// box {64 ch, Z, by, tx+kx-1, 1} — the output slabs plus the x halo — with TMA zero fill supplying the conv
+// padding.  Inside that box the kx taps along x are just UMMA descriptor start offsets of ti*by*Z rows
+// (by*Z % 8 == 0, so SWIZZLE_128B 8-row atoms stay aligned and need no base offset).  The CTA keeps up to four
+// 128-row accumulators in TMEM (t_m * N <= 512 columns), so every weight tile fetched serves all of them.
+// Per MMA this moves ~3x fewer bytes than v1 (hr_convs.0: 158 KB per 60 MMAs instead of 34 KB per 4).
+//
+// Pipeline: warp 0 = TMA producer (2 halo buffers + a ring of weight slots), warp 1 = MMA issuer / TMEM owner,
+// warps 2-5 = epilogue (same fused epilogue as v1, common.cuh).
+//
+// Replaces nn.Conv3d forward + dgrad for the stride-1 layers: torch_blocks.py:17 (RDB / trunk / UpConv convs),
+// Generator_3D_Resnet_ESRGAN.py:95-111 (hr_convs).
+#include <cuda.h>
+#include <mutex>
+#include <string.h>
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace ws {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxWSlots = 6;
+
+struct Tc2Params {
+  int N, DX, DY, DZ;
+  int by, bz, tx, slabrows;
+  int tiles_x, tiles_y;
+  int kx, ky, kz, px, py, pz;
+  int ck, kchunks, last_k16, cn, n_umma, n_tile;
+  int t_m, out_rows, halo_rows;
+  int a_buf_bytes, w_bytes, w_slots;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const Tc2Params p, const View dst, const Epi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t w_base = smem_base + 2u * p.a_buf_bytes;
+  const uint32_t bar_off = 2u * p.a_buf_bytes + (uint32_t)p.w_slots * p.w_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (4 + kMaxWSlots + s); };
+  const uint32_t accum_bar = bar_base + 8u * (4 + 2 * kMaxWSlots);
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * kMaxWSlots);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (5 + 2 * kMaxWSlots));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tyi = t % p.tiles_y; t /= p.tiles_y;
+  const int txi = t % p.tiles_x; t /= p.tiles_x;
+  const int n = t;
+  const int x0 = txi * p.tx, y0 = tyi * p.by;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.w_slots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int nyz = p.ky * p.kz;
+
+  // Producer and MMA warps run their loops warp-uniformly (all 32 lanes) and elect one lane only around the
+  // UTMALDG / UTCHMMA instructions: operands then live in uniform registers.  (Round-1 ncu finding: issuing from
+  // inside an `if (lane == 0)` region made ptxas wrap every tcgen05.mma in an R2UR/ELECT waterfall loop and the
+  // single issuing thread, not the tensor pipe, bounded the kernel.)
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    const uint32_t a_bytes = (uint32_t)p.halo_rows * 128u;
+    for (int yz = 0; yz < nyz; ++yz) {
+      const int tj = yz / p.kz, tl = yz % p.kz;
+      for (int ch = 0; ch < p.kchunks; ++ch) {
+        ptx::mbar_wait(a_empty(ab), aph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(a_full(ab), a_bytes);
+          ptx::tma_load_5d(smem_base + ab * p.a_buf_bytes, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
+                           x0 - p.px, n);
+        }
+        __syncwarp();
+        if (++ab == 2) { ab = 0; aph ^= 1u; }
+        for (int ti = 0; ti < p.kx; ++ti) {
+          const int tap = (ti * p.ky + tj) * p.kz + tl;
+          ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(w_full(wsl), (uint32_t)p.w_bytes);
+            ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, n0, tap);
+          }
+          __syncwarp();
+          if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)p.n_umma, 0u, 0u);
+    const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);  // everything but the start address
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    const int iters = nyz * p.kchunks;
+    for (int it = 0; it < iters; ++it) {
+      const int ch = it % p.kchunks;
+      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : 4;
+      ptx::mbar_wait(a_full(ab), aph);
+      const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
+      for (int ti = 0; ti < p.kx; ++ti) {
+        ptx::mbar_wait(w_full(wsl), wph);
+        ptx::tc_fence_after();
+        const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_bytes) >> 4) & 0x3fffu);
+        const uint32_t acc0 = (it > 0 || ti > 0) ? 1u : 0u;
+        for (int m = 0; m < p.t_m; ++m) {
+          const uint32_t am = a_addr + (uint32_t)(m * 128 + ti * p.slabrows) * 128u;
+          const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
+          if (ptx::elect_one()) {
+            // K advance inside the 128-byte swizzle row: +32 B = +2 in the (addr >> 4) field
+            ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
+            if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            if (nk > 2) ptx::mma_f16_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            if (nk > 3) ptx::mma_f16_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+        __syncwarp();
+        if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
+      __syncwarp();
+      if (++ab == 2) { ab = 0; aph ^= 1u; }
+    }
+    if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int sub = warp & 3;
+    ptx::mbar_wait(accum_bar, 0);
+    ptx::tc_fence_after();
+    const bool cl = dst.cs == 1;
+    const int es = dst.dtype == WS_F32 ? 4 : 2;
+    const bool vec_ok = cl && ((reinterpret_cast<uintptr_t>(dst.ptr) & 15) == 0) && ((dst.vs * es) % 16 == 0) &&
+                        ((dst.ns * es) % 16 == 0);
+    const bool cl2 = ep.out2.ptr && ep.out2.cs == 1;
+    const int es2 = ep.out2.dtype == WS_F32 ? 4 : 2;
+    const bool vec_ok2 = cl2 && ((reinterpret_cast<uintptr_t>(ep.out2.ptr) & 15) == 0) &&
+                         ((ep.out2.vs * es2) % 16 == 0) && ((ep.out2.ns * es2) % 16 == 0);
+    for (int m = 0; m < p.t_m; ++m) {
+      const int r = m * 128 + sub * 32 + lane;  // row inside the CTA's output region
+      const int rx = r / p.slabrows;
+      const int rem = r - rx * p.slabrows;
+      const int ry = rem / p.bz, rz = rem - ry * p.bz;
+      const int gx = x0 + rx, gy = y0 + ry;
+      const bool row_ok = r < p.out_rows && gx < p.DX && gy < p.DY;
+      const long long v = ((long long)gx * p.DY + gy) * p.DZ + rz;
+      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+        if (n0 + c0 >= p.cn) break;
+        uint32_t rr[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
+        ptx::tmem_ld_wait();
+        float y[16], pre[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = n0 + c0 + j;
+          y[j] = 0.f;
+          pre[j] = 0.f;
+          if (row_ok && c < p.cn) y[j] = ep.apply(__uint_as_float(rr[j]), n, c, v, pre[j]);
+        }
+        if (ep.stat_sum) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float s1 = warp_sum(pre[j]);
+            float s2 = warp_sum(pre[j] * pre[j]);
+            const int c = n0 + c0 + j;
+            if (lane == 0 && c < p.cn) {
+              atomicAdd(&ep.stat_sum[c], s1);
+              atomicAdd(&ep.stat_sqsum[c], s2);
+            }
+          }
+        }
+        if (!row_ok) continue;
+        const int cbase = n0 + c0;
+        const bool full = cbase + 16 <= p.cn;
+        if (full && vec_ok && ((cbase * es) % 16 == 0)) {
+          const long long o = dst.off(n, cbase, v);
+          if (dst.dtype == WS_BF16) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)dst.ptr + o);
+            q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            float4* q = reinterpret_cast<float4*>((float*)dst.ptr + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cbase + j < p.cn) dst.st(n, cbase + j, v, y[j]);
+        }
+        if (ep.out2.ptr) {
+          if (full && vec_ok2 && ((cbase * es2) % 16 == 0)) {
+            const long long o = ep.out2.off(n, cbase, v);
+            if (ep.out2.dtype == WS_BF16) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)ep.out2.ptr + o);
+              q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              float4* q = reinterpret_cast<float4*>((float*)ep.out2.ptr + o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cbase + j < p.cn) ep.out2.st(n, cbase + j, v, y[j]);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+constexpr int kSmemBudget = 225 * 1024;
+
+// Pick (by, tx): minimise estimated SM-time = waves * max(MMA cycles, L2->SMEM cycles) per K iteration.
+bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p) {
+  const int tmax = 512 / n_umma < 4 ? 512 / n_umma : 4;
+  if (tmax < 1 || DZ > 128) return false;
+  double best = 1e30;
+  bool found = false;
+  for (int by = 1; by <= DY && by * DZ <= 128 * tmax; ++by) {
+    const int slab = by * DZ;
+    if (slab % 8) continue;
+    for (int tx = 1; tx <= DX && tx * slab <= 128 * tmax; ++tx) {
+      if (tx + kx - 1 > 256) break;
+      const int t_m = (tx * slab + 127) / 128;
+      const int halo = (tx + kx - 1) * slab;
+      int a_rows = t_m * 128 + (kx - 1) * slab;
+      if (a_rows < halo) a_rows = halo;
+      const int a_bytes = (a_rows * 128 + 1023) / 1024 * 1024;
+      const int w_bytes = n_umma * 128;
+      if (2 * a_bytes + 2 * w_bytes + 2048 > kSmemBudget) continue;
+      const double mma = (double)t_m * kx * 4 * (n_umma / 2.0);
+      const double load = (halo * 128.0 + (double)kx * w_bytes) / 34.0;
+      const double iter = (mma > load ? mma : load) + 400.0;
+      const long long ctas = (long long)N * ((DX + tx - 1) / tx) * ((DY + by - 1) / by);
+      const long long waves = (ctas + 147) / 148;
+      const double cost = (double)waves * iter;
+      if (cost < best) {
+        best = cost;
+        found = true;
+        p.by = by; p.tx = tx; p.t_m = t_m; p.slabrows = slab; p.halo_rows = halo; p.a_buf_bytes = a_bytes;
+        p.w_bytes = w_bytes;
+      }
+    }
+  }
+  return found;
+}
+
+}  // namespace
+
+bool tc2_enabled() {
+  static const bool off = [] {
+    const char* v = getenv("WS_DISABLE_TC_V2");
+    return v && v[0] && v[0] != '0';
+  }();
+  return !off;
+}
+
+// mode 0: forward; mode 1: stride-1 dgrad. Returns -1 when this geometry is not covered (caller uses v1).
+int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* packed_w, const View& dst,
+                    const Epi& ep, cudaStream_t st) {
+  if (g.sx != 1 || g.sy != 1 || g.sz != 1) return -1;
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  int SX, SY, SZ;
+  if (mode == 0) {
+    p.DX = g.xo; p.DY = g.yo; p.DZ = g.zo; SX = g.x; SY = g.y; SZ = g.z;
+    p.px = g.px; p.py = g.py; p.pz = g.pz; p.ck = g.cin; p.cn = g.cout;
+  } else {
+    p.DX = g.x; p.DY = g.y; p.DZ = g.z; SX = g.xo; SY = g.yo; SZ = g.zo;
+    p.px = g.kx - 1 - g.px; p.py = g.ky - 1 - g.py; p.pz = g.kz - 1 - g.pz; p.ck = g.cout; p.cn = g.cin;
+  }
+  p.N = g.n; p.kx = g.kx; p.ky = g.ky; p.kz = g.kz; p.bz = p.DZ;
+  const int cn_pad = (p.cn + 15) / 16 * 16;
+  const int ck_pad = (p.ck + 7) / 8 * 8;
+  const int n_tiles = (cn_pad + 255) / 256;
+  p.n_tile = ((cn_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  p.n_umma = p.n_tile;
+  if (!choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, p)) return -1;
+  p.out_rows = p.tx * p.slabrows;
+  p.tiles_x = (p.DX + p.tx - 1) / p.tx;
+  p.tiles_y = (p.DY + p.by - 1) / p.by;
+  p.kchunks = (p.ck + 63) / 64;
+  p.last_k16 = (p.ck - 64 * (p.kchunks - 1) + 15) / 16;
+  p.w_slots = (kSmemBudget - 2048 - 2 * p.a_buf_bytes) / p.w_bytes;
+  if (p.w_slots > kMaxWSlots) p.w_slots = kMaxWSlots;
+  if (p.w_slots < 2) return -1;
+  uint32_t cols = 32;
+  while ((int)cols < p.t_m * p.n_umma) cols <<= 1;
+  p.tmem_cols = cols;
+
+  MapKey ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.ptr = reinterpret_cast<uintptr_t>(src.ptr);
+  ka.rank = 5; ka.dtype = WS_BF16;
+  ka.dims[0] = (uint64_t)p.ck; ka.dims[1] = (uint64_t)SZ; ka.dims[2] = (uint64_t)SY; ka.dims[3] = (uint64_t)SX;
+  ka.dims[4] = (uint64_t)g.n;
+  ka.strides[0] = (uint64_t)src.vs * 2;
+  ka.strides[1] = (uint64_t)src.vs * 2 * SZ;
+  ka.strides[2] = (uint64_t)src.vs * 2 * SZ * SY;
+  ka.strides[3] = (uint64_t)src.ns * 2;
+  ka.box[0] = 64; ka.box[1] = (uint32_t)p.bz; ka.box[2] = (uint32_t)p.by; ka.box[3] = (uint32_t)(p.tx + p.kx - 1);
+  ka.box[4] = 1;
+  for (int i = 0; i < 5; ++i) ka.estr[i] = 1;
+  CUtensorMap tmA, tmB;
+  if (int e = get_tensor_map(ka, &tmA)) return e;
+  MapKey kb;
+  memset(&kb, 0, sizeof(kb));
+  kb.ptr = reinterpret_cast<uintptr_t>(packed_w);
+  kb.rank = 3; kb.dtype = WS_BF16;
+  kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)g.taps();
+  kb.strides[0] = (uint64_t)ck_pad * 2;
+  kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
+  kb.box[0] = 64; kb.box[1] = (uint32_t)p.n_umma; kb.box[2] = 1;
+  kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
+  if (int e = get_tensor_map(kb, &tmB)) return e;
+
+  size_t smem = 2 * (size_t)p.a_buf_bytes + (size_t)p.w_slots * p.w_bytes + 8 * (6 + 2 * kMaxWSlots) + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  WS_REQUIRE(smem <= 227 * 1024, "conv_tc2: smem request %zu too large", smem);
+  dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)n_tiles);
+  conv3d_tc2_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p, dst, ep);
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+}  // namespace ws

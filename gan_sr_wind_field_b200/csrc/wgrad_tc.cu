@@ -102,8 +102,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   const uint32_t blk_bytes = (uint32_t)p.rows * 128u;  // one 64-channel block of one voxel tile
   const int tiles_per_n = p.tiles_x * p.tiles_y * p.tiles_z;
 
+  // Both loops run warp-uniformly and elect one lane only around UTMALDG / UTCHMMA (see conv_tc2.cu).
   if (warp == 0) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       // ===== TMA producer =====
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -121,34 +122,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int tx = t;
         const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
-        // fixed operand -> A ring ("A ring" = ring of the unshifted operand regardless of M/N role)
         ptx::mbar_wait(a_empty(as), aph ^ 1u);
-        ptx::mbar_expect_tx(a_full(as), blk_bytes * fix_blocks);
-        for (int b = 0; b < fix_blocks; ++b)
-          ptx::tma_load_5d(a_base + as * p.a_slot_bytes + b * blk_bytes, tm_fix, a_full(as), fix_c0 + b * 64, z0,
-                           y0, x0, n);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(a_full(as), blk_bytes * fix_blocks);
+          for (int b = 0; b < fix_blocks; ++b)
+            ptx::tma_load_5d(a_base + as * p.a_slot_bytes + b * blk_bytes, tm_fix, a_full(as), fix_c0 + b * 64, z0,
+                             y0, x0, n);
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1u; }
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
           const int cx = x0 * p.sx - p.px + ti, cy = y0 * p.sy - p.py + tj, cz = z0 * p.sz - p.pz + tl;
           ptx::mbar_wait(b_empty(bs), bph ^ 1u);
-          ptx::mbar_expect_tx(b_full(bs), blk_bytes * sh_blocks);
-          for (int b = 0; b < sh_blocks; ++b)
-            ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * blk_bytes, tm_sh, b_full(bs), sh_c0 + b * 64, cz,
-                             cy, cx, n);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(b_full(bs), blk_bytes * sh_blocks);
+            for (int b = 0; b < sh_blocks; ++b)
+              ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * blk_bytes, tm_sh, b_full(bs), sh_c0 + b * 64, cz,
+                               cy, cx, n);
+          }
+          __syncwarp();
           if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       // ===== MMA issuer =====
       const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
+      const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, blk_bytes, 1024);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       const int k16 = p.rows / 16;
-      bool first = true;
+      uint32_t acc_tile = 0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         ptx::mbar_wait(a_full(as), aph);
         const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
@@ -158,21 +164,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           const uint32_t sh_addr = b_base + bs * p.b_slot_bytes;
           const uint32_t m_addr = p.shift_on_m ? sh_addr : fix_addr;
           const uint32_t n_addr = p.shift_on_m ? fix_addr : sh_addr;
-          for (int k = 0; k < k16; ++k) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(m_addr + k * 2048, blk_bytes, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(n_addr + k * 2048, blk_bytes, 1024);
-            ptx::mma_f16_ss(tmem_base + (uint32_t)(tp * p.n_umma), adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+          const uint64_t adesc = desc_hi | (uint64_t)((m_addr >> 4) & 0x3fffu);
+          const uint64_t bdesc = desc_hi | (uint64_t)((n_addr >> 4) & 0x3fffu);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tp * p.n_umma);
+          if (ptx::elect_one()) {
+            // one MMA per 16 voxel rows: +2048 B = +128 in the (addr >> 4) field
+            for (int k = 0; k < k16; ++k)
+              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                              (acc_tile | (uint32_t)k) ? 1u : 0u);
+            ptx::mma_commit(b_empty(bs));
           }
-          ptx::mma_commit(b_empty(bs));
+          __syncwarp();
           if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
         }
-        ptx::mma_commit(a_empty(as));
+        if (ptx::elect_one()) ptx::mma_commit(a_empty(as));
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1u; }
-        first = false;
+        acc_tile = 1;
       }
-      ptx::mma_commit(accum_bar);
+      if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+      __syncwarp();
     }
-    __syncwarp();
   } else if (has_work) {
     // ===== epilogue: TMEM -> red.global.add into the fp32 workspace =====
     const int sub = warp & 3;

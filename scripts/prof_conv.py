@@ -1,0 +1,32 @@
+"""Micro-driver for profiling: the hr_convs.0 forward (5x5x5, 144->144 @128x128x10, B=8, bf16) a few times.
+Usage: python scripts/prof_conv.py [reps] [layer: g7|g5|rdb]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from gan_sr_wind_field_b200 import ops
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+layer = sys.argv[2] if len(sys.argv) > 2 else "g7"
+cfgs = {"g7": (8, 144, 144, (128, 128, 10), 5, 2), "g5": (8, 128, 128, (128, 128, 10), 3, 1),
+        "rdb": (8, 224, 32, (16, 16, 10), 3, 1), "g8": (8, 144, 3, (128, 128, 10), 5, 2)}
+n, cin, cout, vol, k, p = cfgs[layer]
+ops.set_precision("bf16")
+g = torch.Generator(device="cuda").manual_seed(0)
+x = ops.empty_cl(n, cin, *vol, torch.bfloat16, "cuda")
+x.copy_(torch.randn(n, cin, *vol, generator=g, device="cuda"))
+w = torch.randn(cout, cin, k, k, k, generator=g, device="cuda") / (cin * k ** 3) ** 0.5
+shape = ops.make_shape(x.shape, cout, (k, k, k), 1, p)
+y = ops.empty_cl(n, cout, *vol, torch.bfloat16, "cuda")
+cache = ops.PackedWeights()
+ops.conv_fwd(x, w, cache, shape, y, slope=0.2)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    ops.conv_fwd(x, w, cache, shape, y, slope=0.2)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+fl = 2.0 * n * vol[0] * vol[1] * vol[2] * cin * cout * k ** 3
+print(f"{layer}: {ms:.3f} ms/launch, {fl / ms / 1e9:.1f} TFLOP/s (dense-MAC convention)")

@@ -17,6 +17,7 @@
 // Generator_3D_Resnet_ESRGAN.py:95-111 (hr_convs).
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -28,6 +29,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kMaxWSlots = 6;
+constexpr int kMaxABufs = 6;
 
 struct Tc2Params {
   int N, DX, DY, DZ;
@@ -37,6 +39,9 @@ struct Tc2Params {
   int ck, kchunks, last_k16, cn, n_umma, n_tile;
   int t_m, out_rows, halo_rows;
   int a_buf_bytes, w_bytes, w_slots;
+  int a_bufs;        // halo buffers in the ring (2..kMaxABufs)
+  int a_sub_slabs;   // x-slabs per TMA instruction of the halo load
+  int a_ops;         // TMA instructions per halo load
   uint32_t tmem_cols;
 };
 
@@ -46,16 +51,17 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t w_base = smem_base + 2u * p.a_buf_bytes;
-  const uint32_t bar_off = 2u * p.a_buf_bytes + (uint32_t)p.w_slots * p.w_bytes;
+  const uint32_t w_base = smem_base + (uint32_t)p.a_bufs * p.a_buf_bytes;
+  const uint32_t bar_off = (uint32_t)p.a_bufs * p.a_buf_bytes + (uint32_t)p.w_slots * p.w_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto w_full = [&](int s) { return bar_base + 8u * (4 + s); };
-  auto w_empty = [&](int s) { return bar_base + 8u * (4 + kMaxWSlots + s); };
-  const uint32_t accum_bar = bar_base + 8u * (4 + 2 * kMaxWSlots);
-  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * kMaxWSlots);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (5 + 2 * kMaxWSlots));
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxABufs + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * kMaxABufs + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * kMaxABufs + kMaxWSlots + s); };
+  constexpr int kNumBars = 2 * kMaxABufs + 2 * kMaxWSlots;
+  const uint32_t accum_bar = bar_base + 8u * kNumBars;
+  const uint32_t tmem_slot = bar_base + 8u * (kNumBars + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (kNumBars + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t = blockIdx.x;
@@ -68,7 +74,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.a_bufs; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.w_slots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
     ptx::mbar_init(accum_bar, 1);
     ptx::fence_mbar_init();
@@ -92,18 +98,20 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== TMA producer =====
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
-    const uint32_t a_bytes = (uint32_t)p.halo_rows * 128u;
+    const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * 128u;
     for (int yz = 0; yz < nyz; ++yz) {
       const int tj = yz / p.kz, tl = yz % p.kz;
       for (int ch = 0; ch < p.kchunks; ++ch) {
         ptx::mbar_wait(a_empty(ab), aph ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(a_full(ab), a_bytes);
-          ptx::tma_load_5d(smem_base + ab * p.a_buf_bytes, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
-                           x0 - p.px, n);
+          // the halo box is fetched as a_ops independent TMA instructions (more requests in flight)
+          ptx::mbar_expect_tx(a_full(ab), a_op_bytes * (uint32_t)p.a_ops);
+          for (int o = 0; o < p.a_ops; ++o)
+            ptx::tma_load_5d(smem_base + ab * p.a_buf_bytes + o * a_op_bytes, &tmA, a_full(ab), ch * 64, tl - p.pz,
+                             y0 - p.py + tj, x0 - p.px + o * p.a_sub_slabs, n);
         }
         __syncwarp();
-        if (++ab == 2) { ab = 0; aph ^= 1u; }
+        if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
         for (int ti = 0; ti < p.kx; ++ti) {
           const int tap = (ti * p.ky + tj) * p.kz + tl;
           ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
@@ -152,7 +160,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
       __syncwarp();
-      if (++ab == 2) { ab = 0; aph ^= 1u; }
+      if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
     }
     if (ptx::elect_one()) ptx::mma_commit(accum_bar);
     __syncwarp();
@@ -279,16 +287,25 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
       const int t_m = (tx * slab + 127) / 128;
       const int halo = (tx + kx - 1) * slab;
       int a_rows = t_m * 128 + (kx - 1) * slab;
-      if (a_rows < halo) a_rows = halo;
+      // the halo is fetched in up to 4 TMA instructions of `sub` slabs each: the last one may overrun the halo
+      for (int want = 1; want <= 4; ++want) {
+        const int sub = (tx + kx - 1 + want - 1) / want;
+        const int ops_rows = ((tx + kx - 1 + sub - 1) / sub) * sub * slab;
+        if (a_rows < ops_rows) a_rows = ops_rows;
+      }
       const int a_bytes = (a_rows * 128 + 1023) / 1024 * 1024;
       const int w_bytes = n_umma * 128;
       if (2 * a_bytes + 2 * w_bytes + 2048 > kSmemBudget) continue;
-      const double mma = (double)t_m * kx * 4 * (n_umma / 2.0);
+      // measured on B200 (scripts/micro/mma_rate.cu): a cta_group::1 M=128 MMA costs max(72, N/2) cycles — the
+      // 4 KB A-operand read from SMEM floors it at ~72 regardless of N
+      const double per_mma = n_umma / 2.0 > 72.0 ? n_umma / 2.0 : 72.0;
+      const double mma = (double)t_m * kx * 4 * per_mma;
       const double load = (halo * 128.0 + (double)kx * w_bytes) / 34.0;
-      const double iter = (mma > load ? mma : load) + 400.0;
+      const double iter = (mma > load ? mma : load) + 150.0 * kx + 300.0;
       const long long ctas = (long long)N * ((DX + tx - 1) / tx) * ((DY + by - 1) / by);
       const long long waves = (ctas + 147) / 148;
-      const double cost = (double)waves * iter;
+      // fixed per-CTA cost (prologue, pipeline ramp, epilogue of t_m tiles) in units of iterations' cycles
+      const double cost = (double)waves * (iter + (6000.0 + 2500.0 * t_m) / 30.0);
       if (cost < best) {
         best = cost;
         found = true;
@@ -336,9 +353,26 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   p.tiles_y = (p.DY + p.by - 1) / p.by;
   p.kchunks = (p.ck + 63) / 64;
   p.last_k16 = (p.ck - 64 * (p.kchunks - 1) + 15) / 16;
-  p.w_slots = (kSmemBudget - 2048 - 2 * p.a_buf_bytes) / p.w_bytes;
-  if (p.w_slots > kMaxWSlots) p.w_slots = kMaxWSlots;
-  if (p.w_slots < 2) return -1;
+  static const int env_split = getenv("WS_TC2_ASPLIT") ? atoi(getenv("WS_TC2_ASPLIT")) : 4;
+  static const int env_bufs = getenv("WS_TC2_ABUFS") ? atoi(getenv("WS_TC2_ABUFS")) : kMaxABufs;
+  {
+    const int slabs = p.tx + p.kx - 1;
+    int want_ops = env_split < 1 ? 1 : (env_split > 4 ? 4 : env_split);
+    p.a_sub_slabs = (slabs + want_ops - 1) / want_ops;
+    p.a_ops = (slabs + p.a_sub_slabs - 1) / p.a_sub_slabs;
+  }
+  // weight ring: at least kx + 1 slots when they fit, then as many halo buffers as the rest allows
+  p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : p.kx + 1;
+  while (p.w_slots > 2 && 2 * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > kSmemBudget) --p.w_slots;
+  p.a_bufs = (kSmemBudget - 2048 - p.w_slots * p.w_bytes) / p.a_buf_bytes;
+  if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
+  if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
+  if (p.a_bufs < 2 || p.w_slots < 2) return -1;
+  {
+    int spare = (kSmemBudget - 2048 - p.a_bufs * p.a_buf_bytes) / p.w_bytes;
+    if (spare > kMaxWSlots) spare = kMaxWSlots;
+    if (spare > p.w_slots) p.w_slots = spare;
+  }
   uint32_t cols = 32;
   while ((int)cols < p.t_m * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
@@ -353,7 +387,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   ka.strides[1] = (uint64_t)src.vs * 2 * SZ;
   ka.strides[2] = (uint64_t)src.vs * 2 * SZ * SY;
   ka.strides[3] = (uint64_t)src.ns * 2;
-  ka.box[0] = 64; ka.box[1] = (uint32_t)p.bz; ka.box[2] = (uint32_t)p.by; ka.box[3] = (uint32_t)(p.tx + p.kx - 1);
+  ka.box[0] = 64; ka.box[1] = (uint32_t)p.bz; ka.box[2] = (uint32_t)p.by; ka.box[3] = (uint32_t)p.a_sub_slabs;
   ka.box[4] = 1;
   for (int i = 0; i < 5; ++i) ka.estr[i] = 1;
   CUtensorMap tmA, tmB;
@@ -369,7 +403,8 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
   if (int e = get_tensor_map(kb, &tmB)) return e;
 
-  size_t smem = 2 * (size_t)p.a_buf_bytes + (size_t)p.w_slots * p.w_bytes + 8 * (6 + 2 * kMaxWSlots) + 1024;
+  size_t smem = (size_t)p.a_bufs * p.a_buf_bytes + (size_t)p.w_slots * p.w_bytes +
+                8 * (2 * kMaxABufs + 2 * kMaxWSlots + 2) + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

@@ -1,0 +1,51 @@
+"""Kernel-time breakdown of one training step via torch.profiler (CUPTI; cheap compared with ncu).
+Groups by (kernel, grid) and prints the top entries; writes gpurun_out/step_kernels.json."""
+import collections, json, os, re, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import ProfilerActivity, profile
+import bench
+from gan_sr_wind_field_b200 import ops
+from gan_sr_wind_field_b200.config.config import Config
+from gan_sr_wind_field_b200.GAN_models.wind_field_GAN_3D import wind_field_GAN_3D
+from gan_sr_wind_field_b200.synthetic import make_batch
+
+dev = torch.device("cuda:0")
+ops.set_precision("bf16")
+cfg = Config(bench.INI)
+cfg.is_train, cfg.gpu_id, cfg.device = True, 0, dev
+torch.manual_seed(2001)
+gan = wind_field_GAN_3D(cfg)
+LR, HR, Z, x, y = make_batch(8, 128, 10, 8, seed=2001, device=dev)
+t = cfg.training
+gan.feed_xy_niter(x, y, torch.tensor(t.niter, device=dev), t.d_g_train_ratio, t.d_g_train_period)
+for i in range(3):
+    gan.optimize_parameters(LR, HR, Z, 1 + i)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    gan.optimize_parameters(LR, HR, Z, 5)
+    torch.cuda.synchronize()
+path = os.path.join(ROOT, "gpurun_out", "step_trace.json")
+os.makedirs(os.path.dirname(path), exist_ok=True)
+prof.export_chrome_trace(path)
+tr = json.load(open(path))
+agg = collections.defaultdict(lambda: [0, 0.0])
+tot = 0.0
+tmin, tmax = 1e30, 0
+for e in tr["traceEvents"]:
+    if e.get("cat") == "kernel":
+        name = re.sub(r"\(.*", "", e["name"]).replace("ws::(anonymous namespace)::", "").replace("void ", "")
+        name = re.sub(r"<.*", "", name)[:40]
+        grid = tuple(e.get("args", {}).get("grid", []))
+        agg[(name, grid)][0] += 1
+        agg[(name, grid)][1] += e["dur"]
+        tot += e["dur"]
+        tmin = min(tmin, e["ts"]); tmax = max(tmax, e["ts"] + e["dur"])
+print(f"kernels: {sum(v[0] for v in agg.values())}, sum of kernel time {tot/1e3:.1f} ms, GPU span {(tmax-tmin)/1e3:.1f} ms")
+rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+for (name, grid), (n, us) in rows[:45]:
+    print(f"{name:42s} {str(grid):18s} n={n:4d} {us/1e3:8.3f} ms {100*us/tot:5.1f}%")
+json.dump([dict(kernel=k[0], grid=list(k[1]), launches=v[0], ms=v[1] / 1e3) for k, v in rows],
+          open(os.path.join(ROOT, "gpurun_out", "step_kernels.json"), "w"), indent=1)
+os.remove(path)

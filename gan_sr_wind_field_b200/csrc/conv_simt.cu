@@ -456,6 +456,148 @@ __global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, 
   }
 }
 
+// ---- narrow-input layers (Cin <= 4: feature_conv, terrain_convs.0, D's first conv) -------------------------
+// The implicit-GEMM tiling above wastes 13/16 of every K chunk when Cin = 3.  Direct form instead: one thread per
+// output voxel, 16 output channels per thread, the (taps x Cin x 16) weight slice in shared memory (warp-wide
+// broadcast reads), inputs straight from the (NCXYZ fp32) boundary tensor — neighbouring threads share L1 lines.
+constexpr int kSmallCo = 16;
+__global__ void __launch_bounds__(256)
+conv_small_cin_fwd(ConvGeom g, View src, const float* __restrict__ w /*[tap][cin][cout]*/, View dst, Epi ep) {
+  extern __shared__ float wsm[];  // [taps*cin][16]
+  const int T = g.taps();
+  const int co0 = blockIdx.y * kSmallCo;
+  for (int i = threadIdx.x; i < T * g.cin * kSmallCo; i += blockDim.x) {
+    int j = i % kSmallCo, k = i / kSmallCo;
+    wsm[i] = (co0 + j < g.cout) ? w[(long long)k * g.cout + co0 + j] : 0.f;
+  }
+  __syncthreads();
+  const long long VO = g.vout();
+  const long long total = (long long)g.n * VO;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = m < total;
+  const long long mm = ok ? m : 0;
+  const int n = (int)(mm / VO);
+  const long long v = mm % VO;
+  const int zo = (int)(v % g.zo);
+  const int yo = (int)((v / g.zo) % g.yo);
+  const int xo = (int)(v / ((long long)g.zo * g.yo));
+  float acc[kSmallCo];
+#pragma unroll
+  for (int j = 0; j < kSmallCo; ++j) acc[j] = 0.f;
+  for (int ti = 0; ti < g.kx; ++ti) {
+    const int xi = xo * g.sx - g.px + ti;
+    if (xi < 0 || xi >= g.x) continue;
+    for (int tj = 0; tj < g.ky; ++tj) {
+      const int yi = yo * g.sy - g.py + tj;
+      if (yi < 0 || yi >= g.y) continue;
+      for (int tl = 0; tl < g.kz; ++tl) {
+        const int zi = zo * g.sz - g.pz + tl;
+        if (zi < 0 || zi >= g.z) continue;
+        const int tap = (ti * g.ky + tj) * g.kz + tl;
+        const long long vi = ((long long)xi * g.y + yi) * g.z + zi;
+        for (int c = 0; c < g.cin; ++c) {
+          const float xv = src.ld(n, c, vi);
+          const float4* wr = reinterpret_cast<const float4*>(&wsm[(tap * g.cin + c) * kSmallCo]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 f = wr[q];
+            acc[4 * q] = fmaf(xv, f.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(xv, f.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv, f.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv, f.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (!ok) return;
+  const bool vec = dst.cs == 1 && ((reinterpret_cast<uintptr_t>(dst.ptr) & 15) == 0) &&
+                   ((dst.vs * dst.esize()) % 16 == 0) && ((dst.ns * dst.esize()) % 16 == 0) &&
+                   ((co0 * dst.esize()) % 16 == 0) && co0 + kSmallCo <= g.cout;
+  float y[kSmallCo];
+#pragma unroll
+  for (int j = 0; j < kSmallCo; ++j) {
+    float pre;
+    y[j] = (co0 + j < g.cout) ? ep.apply(acc[j], n, co0 + j, v, pre) : 0.f;
+  }
+  if (vec && dst.dtype == WS_BF16) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)dst.ptr + dst.off(n, co0, v));
+    q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  } else if (vec) {
+    float4* q = reinterpret_cast<float4*>((float*)dst.ptr + dst.off(n, co0, v));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kSmallCo; ++j)
+      if (co0 + j < g.cout) dst.st(n, co0 + j, v, y[j]);
+  }
+  if (ep.out2.ptr) {
+#pragma unroll
+    for (int j = 0; j < kSmallCo; ++j)
+      if (co0 + j < g.cout) ep.out2.st(n, co0 + j, v, y[j]);
+  }
+}
+
+// wgrad for Cin <= 4: every thread owns up to 8 of the taps*cin*cout outputs and walks its block's voxel chunk;
+// within a warp the x gathers hit 1-2 addresses (co is the fastest thread index) and the dy reads are contiguous.
+__global__ void __launch_bounds__(512)
+conv_small_cin_wgrad(ConvGeom g, View in, View dy, float* __restrict__ wsp /*[tap][cin][cout]*/,
+                     long long v_per_block) {
+  const int T = g.taps();
+  const int O = T * g.cin * g.cout;
+  const long long VO = g.vout();
+  const long long K = (long long)g.n * VO;
+  const long long kbeg = (long long)blockIdx.x * v_per_block;
+  const long long kend = kbeg + v_per_block < K ? kbeg + v_per_block : K;
+  constexpr int MAXO = 8;
+  float acc[MAXO];
+  int o_ti[MAXO], o_tj[MAXO], o_tl[MAXO], o_ci[MAXO], o_co[MAXO];
+  int nown = 0;
+#pragma unroll
+  for (int i = 0; i < MAXO; ++i) {
+    acc[i] = 0.f;
+    int o = threadIdx.x + i * blockDim.x;
+    if (o < O) {
+      o_co[i] = o % g.cout;
+      o_ci[i] = (o / g.cout) % g.cin;
+      const int tap = o / (g.cout * g.cin);
+      o_ti[i] = tap / (g.ky * g.kz); o_tj[i] = (tap / g.kz) % g.ky; o_tl[i] = tap % g.kz;
+      nown = i + 1;
+    } else {
+      o_co[i] = o_ci[i] = o_ti[i] = o_tj[i] = o_tl[i] = 0;
+    }
+  }
+#pragma unroll 4
+  for (long long kg = kbeg; kg < kend; ++kg) {
+    const int n = (int)(kg / VO);
+    const long long v = kg % VO;
+    const int zo = (int)(v % g.zo);
+    const int yo = (int)((v / g.zo) % g.yo);
+    const int xo = (int)(v / ((long long)g.zo * g.yo));
+#pragma unroll
+    for (int i = 0; i < MAXO; ++i) {
+      if (i >= nown) break;
+      const int xi = xo * g.sx - g.px + o_ti[i], yi = yo * g.sy - g.py + o_tj[i], zi = zo * g.sz - g.pz + o_tl[i];
+      if (xi < 0 || xi >= g.x || yi < 0 || yi >= g.y || zi < 0 || zi >= g.z) continue;
+      const float xv = in.ld(n, o_ci[i], ((long long)xi * g.y + yi) * g.z + zi);
+      acc[i] = fmaf(xv, dy.ld(n, o_co[i], v), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXO; ++i) {
+    int o = threadIdx.x + i * blockDim.x;
+    if (o < O) atomicAdd(&wsp[o], acc[i]);
+  }
+}
+
 bool vec_ok(const View& v, int channels) {
   if (v.cs != 1) return false;
   int q = 4;  // 4 elements per vector access
@@ -473,6 +615,15 @@ int launch_igemm(const ConvGeom& g, const View& src, const float* w, const View&
   int va = vec_ok(src, CK) ? 1 : 0;
   int vb = (CN % 4 == 0 && ((uintptr_t)w % 16) == 0) ? 1 : 0;
   if (M <= 0 || CN <= 0) return 0;
+  if (MODE == 0 && g.cin <= 4 && !ep.stat_sum) {
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((g.cout + kSmallCo - 1) / kSmallCo));
+    size_t smem = (size_t)g.taps() * g.cin * kSmallCo * sizeof(float);
+    if (smem <= 48 * 1024) {
+      conv_small_cin_fwd<<<grid, 256, smem, st>>>(g, src, w, dst, ep);
+      WS_POST_LAUNCH(1);
+      return 0;
+    }
+  }
 #define WS_LAUNCH(BM_, BN_, TM_, TN_)                                                        \
   do {                                                                                       \
     dim3 grid((unsigned)((M + BM_ - 1) / BM_), (unsigned)((CN + BN_ - 1) / BN_));            \
@@ -534,6 +685,17 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   float* wsp = (float*)workspace;
   WS_CHECK_CUDA(cudaMemsetAsync(wsp, 0, need, st));
   const long long K = (long long)g.n * g.vout();
+  if (g.cin <= 4 && g.taps() * g.cin * g.cout <= 8 * 512) {
+    const int O = g.taps() * g.cin * g.cout;
+    int threads = O < 512 ? (O + 31) / 32 * 32 : 512;
+    long long blocks = 148LL * 64;
+    long long vpb = (K + blocks - 1) / blocks;
+    if (vpb < 32) vpb = 32;
+    blocks = (K + vpb - 1) / vpb;
+    conv_small_cin_wgrad<<<(unsigned)blocks, threads, 0, st>>>(g, in, dy, wsp, vpb);
+    WS_POST_LAUNCH(1);
+    return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
+  }
   int va = vec_ok(in, g.cin) ? 1 : 0;
   int vb = vec_ok(dy, g.cout) ? 1 : 0;
   auto pick = [](int c) { return c > 16 ? 64 : (c > 4 ? 16 : 4); };

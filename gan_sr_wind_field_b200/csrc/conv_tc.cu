@@ -25,6 +25,7 @@
 #include <string>
 #include <string.h>
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -169,94 +170,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
 
-    const bool cl = dst.cs == 1;
-    const int es = dst.dtype == WS_F32 ? 4 : 2;
-    const bool vec_ok = cl && ((reinterpret_cast<uintptr_t>(dst.ptr) & 15) == 0) &&
-                        ((dst.vs * es) % 16 == 0) && ((dst.ns * es) % 16 == 0);
-    const bool cl2 = ep.out2.ptr && ep.out2.cs == 1;
-    const int es2 = ep.out2.dtype == WS_F32 ? 4 : 2;
-    const bool vec_ok2 = cl2 && ((reinterpret_cast<uintptr_t>(ep.out2.ptr) & 15) == 0) &&
-                         ((ep.out2.vs * es2) % 16 == 0) && ((ep.out2.ns * es2) % 16 == 0);
-
+    const EpiVec ev = make_epi_vec(dst, ep);
     for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
       if (n0 + c0 >= p.cn) break;  // warp-uniform
       uint32_t r[16];
       ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
-      float y[16];
-      float pre[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = n0 + c0 + j;
-        y[j] = 0.f;
-        pre[j] = 0.f;
-        if (row_ok && c < p.cn) y[j] = ep.apply(__uint_as_float(r[j]), n, c, v, pre[j]);
-      }
-      if (ep.stat_sum) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float s1 = warp_sum(pre[j]);
-          float s2 = warp_sum(pre[j] * pre[j]);
-          const int c = n0 + c0 + j;
-          if (lane == 0 && c < p.cn) {
-            atomicAdd(&ep.stat_sum[c], s1);
-            atomicAdd(&ep.stat_sqsum[c], s2);
-          }
-        }
-      }
-      if (row_ok) {
-        const int cbase = n0 + c0;
-        const bool full = cbase + 16 <= p.cn;
-        // primary output
-        if (full && vec_ok && ((cbase * es) % 16 == 0)) {
-          const long long o = dst.off(n, cbase, v);
-          if (dst.dtype == WS_BF16) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)dst.ptr + o);
-            q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            float4* q = reinterpret_cast<float4*>((float*)dst.ptr + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (cbase + j < p.cn) dst.st(n, cbase + j, v, y[j]);
-        }
-        // optional second output
-        if (ep.out2.ptr) {
-          if (full && vec_ok2 && ((cbase * es2) % 16 == 0)) {
-            const long long o = ep.out2.off(n, cbase, v);
-            if (ep.out2.dtype == WS_BF16) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)ep.out2.ptr + o);
-              q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-              float4* q = reinterpret_cast<float4*>((float*)ep.out2.ptr + o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cbase + j < p.cn) ep.out2.st(n, cbase + j, v, y[j]);
-          }
-        }
-      }
+      epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r, lane);
     }
     ptx::tc_fence_before();
   }

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -169,14 +170,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int sub = warp & 3;
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
-    const bool cl = dst.cs == 1;
-    const int es = dst.dtype == WS_F32 ? 4 : 2;
-    const bool vec_ok = cl && ((reinterpret_cast<uintptr_t>(dst.ptr) & 15) == 0) && ((dst.vs * es) % 16 == 0) &&
-                        ((dst.ns * es) % 16 == 0);
-    const bool cl2 = ep.out2.ptr && ep.out2.cs == 1;
-    const int es2 = ep.out2.dtype == WS_F32 ? 4 : 2;
-    const bool vec_ok2 = cl2 && ((reinterpret_cast<uintptr_t>(ep.out2.ptr) & 15) == 0) &&
-                         ((ep.out2.vs * es2) % 16 == 0) && ((ep.out2.ns * es2) % 16 == 0);
+    const EpiVec ev = make_epi_vec(dst, ep);
     for (int m = 0; m < p.t_m; ++m) {
       const int r = m * 128 + sub * 32 + lane;  // row inside the CTA's output region
       const int rx = r / p.slabrows;
@@ -190,75 +184,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t rr[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
         ptx::tmem_ld_wait();
-        float y[16], pre[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = n0 + c0 + j;
-          y[j] = 0.f;
-          pre[j] = 0.f;
-          if (row_ok && c < p.cn) y[j] = ep.apply(__uint_as_float(rr[j]), n, c, v, pre[j]);
-        }
-        if (ep.stat_sum) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float s1 = warp_sum(pre[j]);
-            float s2 = warp_sum(pre[j] * pre[j]);
-            const int c = n0 + c0 + j;
-            if (lane == 0 && c < p.cn) {
-              atomicAdd(&ep.stat_sum[c], s1);
-              atomicAdd(&ep.stat_sqsum[c], s2);
-            }
-          }
-        }
-        if (!row_ok) continue;
-        const int cbase = n0 + c0;
-        const bool full = cbase + 16 <= p.cn;
-        if (full && vec_ok && ((cbase * es) % 16 == 0)) {
-          const long long o = dst.off(n, cbase, v);
-          if (dst.dtype == WS_BF16) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)dst.ptr + o);
-            q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            float4* q = reinterpret_cast<float4*>((float*)dst.ptr + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (cbase + j < p.cn) dst.st(n, cbase + j, v, y[j]);
-        }
-        if (ep.out2.ptr) {
-          if (full && vec_ok2 && ((cbase * es2) % 16 == 0)) {
-            const long long o = ep.out2.off(n, cbase, v);
-            if (ep.out2.dtype == WS_BF16) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* q = reinterpret_cast<uint4*>((__nv_bfloat16*)ep.out2.ptr + o);
-              q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-              float4* q = reinterpret_cast<float4*>((float*)ep.out2.ptr + o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cbase + j < p.cn) ep.out2.st(n, cbase + j, v, y[j]);
-          }
-        }
+        epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
       }
     }
     ptx::tc_fence_before();
@@ -279,10 +205,18 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
   if (tmax < 1 || DZ > 128) return false;
   double best = 1e30;
   bool found = false;
+  // experiment hook: WS_TC2_FORCE="by,tx" pins the tile shape
+  static int force_by = 0, force_tx = 0;
+  static const bool forced = [] {
+    const char* v = getenv("WS_TC2_FORCE");
+    return v && sscanf(v, "%d,%d", &force_by, &force_tx) == 2;
+  }();
   for (int by = 1; by <= DY && by * DZ <= 128 * tmax; ++by) {
     const int slab = by * DZ;
     if (slab % 8) continue;
+    if (forced && by != force_by) continue;
     for (int tx = 1; tx <= DX && tx * slab <= 128 * tmax; ++tx) {
+      if (forced && tx != force_tx) continue;
       if (tx + kx - 1 > 256) break;
       const int t_m = (tx * slab + 127) / 128;
       const int halo = (tx + kx - 1) * slab;
@@ -301,9 +235,18 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
       const double per_mma = n_umma / 2.0 > 72.0 ? n_umma / 2.0 : 72.0;
       const double mma = (double)t_m * kx * 4 * per_mma;
       const double load = (halo * 128.0 + (double)kx * w_bytes) / 34.0;
-      const double iter = (mma > load ? mma : load) + 150.0 * kx + 300.0;
       const long long ctas = (long long)N * ((DX + tx - 1) / tx) * ((DY + by - 1) / by);
-      const long long waves = (ctas + 147) / 148;
+      // co-residency: small tiles let 2 CTAs share an SM (SMEM and TMEM permitting), which hides one CTA's
+      // barrier / TMA latency behind the other's MMAs (measured: trunk conv 73 -> 55 us)
+      const int smem_min = 2 * a_bytes + (kx + 1 < 3 ? 3 : kx + 1) * w_bytes + 2048;
+      int cols = 32;
+      while (cols < t_m * n_umma) cols <<= 1;
+      int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 ? 2 : 1;
+      const long long per_sm = (ctas + 147) / 148;
+      const int r = per_sm < cps ? (int)per_sm : cps;  // CTAs actually sharing an SM
+      const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
+      const double overhead = (150.0 * kx + 300.0) / r;
+      const double iter = (mma > load ? mma : load) * r + overhead;
       // fixed per-CTA cost (prologue, pipeline ramp, epilogue of t_m tiles) in units of iterations' cycles
       const double cost = (double)waves * (iter + (6000.0 + 2500.0 * t_m) / 30.0);
       if (cost < best) {
@@ -311,6 +254,7 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
         found = true;
         p.by = by; p.tx = tx; p.t_m = t_m; p.slabrows = slab; p.halo_rows = halo; p.a_buf_bytes = a_bytes;
         p.w_bytes = w_bytes;
+        p.a_bufs = r;  // (ab)used as "CTAs per SM this config was costed with"; finalised by the caller
       }
     }
   }
@@ -361,15 +305,17 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     p.a_sub_slabs = (slabs + want_ops - 1) / want_ops;
     p.a_ops = (slabs + p.a_sub_slabs - 1) / p.a_sub_slabs;
   }
+  // SMEM budget: the whole SM for one resident CTA, half of it when the config was costed with two
+  const int budget = p.a_bufs >= 2 ? (227 * 1024) / 2 - 1024 : kSmemBudget;
   // weight ring: at least kx + 1 slots when they fit, then as many halo buffers as the rest allows
-  p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : p.kx + 1;
-  while (p.w_slots > 2 && 2 * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > kSmemBudget) --p.w_slots;
-  p.a_bufs = (kSmemBudget - 2048 - p.w_slots * p.w_bytes) / p.a_buf_bytes;
+  p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : (p.kx + 1 < 3 ? 3 : p.kx + 1);
+  while (p.w_slots > 2 && 2 * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > budget) --p.w_slots;
+  p.a_bufs = (budget - 2048 - p.w_slots * p.w_bytes) / p.a_buf_bytes;
   if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
   if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
   if (p.a_bufs < 2 || p.w_slots < 2) return -1;
   {
-    int spare = (kSmemBudget - 2048 - p.a_bufs * p.a_buf_bytes) / p.w_bytes;
+    int spare = (budget - 2048 - p.a_bufs * p.a_buf_bytes) / p.w_bytes;
     if (spare > kMaxWSlots) spare = kMaxWSlots;
     if (spare > p.w_slots) p.w_slots = spare;
   }

@@ -35,8 +35,11 @@ tot = 0.0
 tmin, tmax = 1e30, 0
 for e in tr["traceEvents"]:
     if e.get("cat") == "kernel":
-        name = re.sub(r"\(.*", "", e["name"]).replace("ws::(anonymous namespace)::", "").replace("void ", "")
-        name = re.sub(r"<.*", "", name)[:40]
+        name = e["name"].replace("void ", "")
+        name = re.sub(r"ws::[^:]*::", "", name)          # ws::<unnamed>:: / ws::(anonymous namespace)::
+        name = re.sub(r"\(.*", "", name)
+        m_ = re.match(r"([A-Za-z_0-9:]+)(<[^>]*>)?", name)
+        name = (m_.group(1).split("::")[-1] + (m_.group(2) or ""))[:44] if m_ else name[:44]
         grid = tuple(e.get("args", {}).get("grid", []))
         agg[(name, grid)][0] += 1
         agg[(name, grid)][1] += e["dur"]

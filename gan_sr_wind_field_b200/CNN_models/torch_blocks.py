@@ -317,6 +317,15 @@ class RDB(nn.Module):
     def _dense_convs(self):
         return [m.conv[0] for name, m in self._modules.items() if name.startswith("conv")]
 
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for key, value in self.__dict__.items():
+            if key != "_rdb_state":  # device scratch (packed weights), not module state
+                setattr(new, key, copy.deepcopy(value, memo))
+        return new
+
     def run(self, x, outer=None, outer_scale=None):
         """residual_scaling * LFF(dense(x)) + x, optionally composed with the enclosing RRDB's
         ``outer_scale * (.) + outer`` (torch_blocks.py:328-330) in the same epilogue."""
@@ -327,8 +336,10 @@ class RDB(nn.Module):
         else:
             alpha, beta1, beta2 = self.residual_scaling * outer_scale, outer_scale, 1.0
             outer = _to_f32(outer)
+        if not hasattr(self, "_rdb_state"):
+            self._rdb_state = ops.RDBState()
         cfg = dict(nconv=len(convs), slope=self.lrelu_negative_slope, alpha=alpha, beta1=beta1, beta2=beta2,
-                   caches=[c._packed for c in convs] + [self.LFF._packed])
+                   state=self._rdb_state)
         params = [c.weight for c in convs] + [self.LFF.weight, self.LFF.bias]
         return ops.RDBFn.apply(x, outer, cfg, *params)
 

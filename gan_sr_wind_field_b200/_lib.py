@@ -38,6 +38,12 @@ class WsEpilogue(C.Structure):
                 ("out2", WsTensor), ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p)]
 
 
+class WsRdbDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n", "x", "y", "z", "f", "gc", "nconv", "k", "k_lff")] + \
+               [(k, C.c_float) for k in ("slope", "alpha", "beta1", "beta2")] + \
+               [("math", C.c_int32), ("repack", C.c_int32)]
+
+
 class WindSRError(RuntimeError):
     pass
 
@@ -63,6 +69,10 @@ SYMBOLS = [
     ("ws_conv3d_dgrad", _I, [_SP, _TP, _P, _TP, _EP, _I, _P]),
     ("ws_conv3d_wgrad_workspace_bytes", _Z, [_SP, _I]),
     ("ws_conv3d_wgrad", _I, [_SP, _TP, _TP, _P, _P, _I, _I, _P, _Z, _P]),
+    ("ws_rdb_packed_bytes", _Z, [C.POINTER(WsRdbDesc), _I, _I]),
+    ("ws_rdb_forward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P, _P]),
+    ("ws_rdb_backward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P),
+                             C.POINTER(_P), _P, _P, _Z, _P]),
     ("ws_upsample_nearest_xy_fwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_upsample_nearest_xy_bwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_copy", _I, [_TP, _TP, _I, _I, _L, _P]),

@@ -320,3 +320,142 @@ int ws_windloss_bwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* z
 }
 
 }  // extern "C"
+
+// ---- residual dense block executor ---------------------------------------------------------------------------
+namespace {
+struct RdbGeom {
+  ws_conv_shape dense[WS_RDB_MAX_CONVS];
+  ws_conv_shape lff;
+  int ctot;
+};
+int rdb_geom(const ws_rdb_desc* d, RdbGeom& r) {
+  WS_REQUIRE(d && d->nconv >= 0 && d->nconv <= WS_RDB_MAX_CONVS, "rdb: bad descriptor");
+  WS_REQUIRE(d->k % 2 == 1 && d->k_lff % 2 == 1, "rdb: kernel sizes must be odd");
+  for (int i = 0; i < d->nconv; ++i) {
+    ws_conv_shape s = {d->n, d->x, d->y, d->z, d->f + i * d->gc, d->gc, d->k, d->k, d->k, 1, 1, 1,
+                       (d->k - 1) / 2, (d->k - 1) / 2, (d->k - 1) / 2};
+    r.dense[i] = s;
+  }
+  r.ctot = d->f + d->nconv * d->gc;
+  ws_conv_shape l = {d->n, d->x, d->y, d->z, r.ctot, d->f, d->k_lff, d->k_lff, d->k_lff, 1, 1, 1,
+                     (d->k_lff - 1) / 2, (d->k_lff - 1) / 2, (d->k_lff - 1) / 2};
+  r.lff = l;
+  return 0;
+}
+ws_tensor slice(const ws_tensor& t, int c0) {
+  ws_tensor v = t;
+  v.ptr = (char*)t.ptr + (size_t)c0 * t.cstride * (t.dtype == WS_F32 ? 4 : 2);
+  return v;
+}
+ws_epilogue plain_epilogue() {
+  ws_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.lrelu_slope = 1.f; e.alpha = 1.f; e.mask_slope = 1.f;
+  return e;
+}
+}  // namespace
+
+extern "C" size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int i, int dgrad) {
+  RdbGeom r;
+  if (!d || rdb_geom(d, r) || i < 0 || i > d->nconv) return 0;
+  const ws_conv_shape* s = i < d->nconv ? &r.dense[i] : &r.lff;
+  size_t a = ws_packed_weight_bytes(s, dgrad ? WS_PACK_SIMT_DGRAD : WS_PACK_SIMT_FWD);
+  size_t b = ws_packed_weight_bytes(s, dgrad ? WS_PACK_TC_DGRAD : WS_PACK_TC_FWD);
+  return a > b ? a : b;
+}
+
+extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* outer,
+                              const ws_tensor* buf, const ws_tensor* out, const float* const* w,
+                              void* const* packed, const float* lff_bias, void* stream) {
+  RdbGeom r;
+  if (int e = rdb_geom(d, r)) return e;
+  WS_REQUIRE(x && x->ptr && buf && buf->ptr && out && out->ptr && w && packed, "ws_rdb_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long v = (long long)d->x * d->y * d->z;
+  // buf[:, :f] = x (cast to the activation dtype)
+  ws_tensor b0 = *buf;
+  if (int e = copy_launch(View(x), View(&b0), d->n, d->f, v, st)) return e;
+  for (int i = 0; i < d->nconv; ++i) {
+    const ws_conv_shape* s = &r.dense[i];
+    ConvGeom g(*s);
+    ws_tensor in = *buf, o = slice(*buf, s->cin);
+    View vin(&in), vout(&o);
+    const bool tc = fwd_path(g, vin, d->math) == WS_PATH_TCGEN05;
+    if (d->repack)
+      if (int e = pack_weights_launch(w[i], g, tc ? WS_PACK_TC_FWD : WS_PACK_SIMT_FWD, packed[i], st)) return e;
+    ws_epilogue ep = plain_epilogue();
+    ep.lrelu_slope = d->slope;
+    if (int e = ws_conv3d_fwd(s, &in, packed[i], &o, &ep, d->math, stream)) return e;
+  }
+  {
+    ConvGeom g(r.lff);
+    View vin(buf);
+    const bool tc = fwd_path(g, vin, d->math) == WS_PATH_TCGEN05;
+    if (d->repack)
+      if (int e = pack_weights_launch(w[d->nconv], g, tc ? WS_PACK_TC_FWD : WS_PACK_SIMT_FWD, packed[d->nconv], st))
+        return e;
+    ws_epilogue ep = plain_epilogue();
+    ep.bias = lff_bias;
+    ep.alpha = d->alpha;
+    ep.res1 = *x; ep.beta1 = d->beta1;
+    if (outer && outer->ptr) { ep.res2 = *outer; ep.beta2 = d->beta2; }
+    if (int e = ws_conv3d_fwd(&r.lff, buf, packed[d->nconv], out, &ep, d->math, stream)) return e;
+  }
+  return 0;
+}
+
+extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* buf,
+                               const ws_tensor* dbuf, const ws_tensor* g_lff, const ws_tensor* gbuf,
+                               const ws_tensor* dx, const float* const* w, void* const* packed,
+                               float* const* dw, float* db_lff, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  RdbGeom r;
+  if (int e = rdb_geom(d, r)) return e;
+  WS_REQUIRE(dy && dy->ptr && buf && buf->ptr && dbuf && dbuf->ptr && g_lff && g_lff->ptr && w && packed,
+             "ws_rdb_backward: null pointer");
+  WS_REQUIRE(d->nconv == 0 || (gbuf && gbuf->ptr), "ws_rdb_backward: null g scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long v = (long long)d->x * d->y * d->z;
+  // gradient entering the LFF accumulator: alpha * dy, in the activation dtype
+  if (int e = axpby_launch(View(dy), d->alpha, View((const ws_tensor*)nullptr), 0.f, View(g_lff), d->n, d->f, v, st))
+    return e;
+  const bool want_w = dw != nullptr;
+  if (want_w && (dw[d->nconv] || db_lff)) {
+    if (int e = ws_conv3d_wgrad(&r.lff, buf, g_lff, dw[d->nconv], db_lff, 0, d->math, workspace, workspace_bytes,
+                                stream))
+      return e;
+  }
+  {
+    ConvGeom g(r.lff);
+    const bool tc = dgrad_path(g, View(g_lff), d->math) == WS_PATH_TCGEN05;
+    if (d->repack)
+      if (int e = pack_weights_launch(w[d->nconv], g, tc ? WS_PACK_TC_DGRAD : WS_PACK_SIMT_DGRAD,
+                                      packed[d->nconv], st))
+        return e;
+    ws_epilogue ep = plain_epilogue();
+    if (int e = ws_conv3d_dgrad(&r.lff, g_lff, packed[d->nconv], dbuf, &ep, d->math, stream)) return e;
+  }
+  for (int i = d->nconv - 1; i >= 0; --i) {
+    const ws_conv_shape* s = &r.dense[i];
+    ConvGeom g(*s);
+    ws_tensor dslice = slice(*dbuf, s->cin), yslice = slice(*buf, s->cin);
+    // g = dbuf[:, cin:cin+gc] * lrelu'(buf[:, cin:cin+gc])
+    if (int e = lrelu_bwd_launch(View(&dslice), View(&yslice), d->slope, nullptr, nullptr, View(gbuf), d->n, d->gc,
+                                 v, st))
+      return e;
+    if (want_w && dw[i]) {
+      if (int e = ws_conv3d_wgrad(s, buf, gbuf, dw[i], nullptr, 0, d->math, workspace, workspace_bytes, stream))
+        return e;
+    }
+    const bool tc = dgrad_path(g, View(gbuf), d->math) == WS_PATH_TCGEN05;
+    if (d->repack)
+      if (int e = pack_weights_launch(w[i], g, tc ? WS_PACK_TC_DGRAD : WS_PACK_SIMT_DGRAD, packed[i], st)) return e;
+    ws_epilogue ep = plain_epilogue();
+    ep.res1 = *dbuf; ep.beta1 = 1.f;  // accumulate into dbuf[:, :cin]
+    if (int e = ws_conv3d_dgrad(s, gbuf, packed[i], dbuf, &ep, d->math, stream)) return e;
+  }
+  if (dx && dx->ptr) {
+    if (int e = axpby_launch(View(dbuf), 1.f, View(dy), d->beta1, View(dx), d->n, d->f, v, st)) return e;
+  }
+  return 0;
+}

@@ -417,81 +417,114 @@ def conv_block(x, weight, bias=None, res=None, *, stride=1, padding=0, slope=1.0
 # ------------------------------------------------------------------------------------------------------
 # autograd: residual dense block (torch_blocks.py:217-290) as ONE node
 # ------------------------------------------------------------------------------------------------------
+class RDBState:
+    """Per-RDB device scratch that outlives a step: the packed copies of its weights (forward and dgrad
+    operand layouts) and the parameter versions they were packed from."""
+
+    def __init__(self):
+        self.packed = {0: None, 1: None}
+        self.stamp = {0: None, 1: None}
+
+    def buffers(self, desc, params, dgrad: int):
+        lib = load()
+        nconv = desc.nconv
+        if self.packed[dgrad] is None or self.packed[dgrad][0].device != params[0].device:
+            self.packed[dgrad] = [torch.empty(lib.ws_rdb_packed_bytes(C.byref(desc), i, dgrad), dtype=torch.uint8,
+                                              device=params[0].device) for i in range(nconv + 1)]
+            self.stamp[dgrad] = None
+        stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + (desc.math,)
+        repack = stamp != self.stamp[dgrad]
+        self.stamp[dgrad] = stamp
+        return self.packed[dgrad], int(repack)
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
 class RDBFn(torch.autograd.Function):
     """x (fp32 trunk state, N,F,X,Y,Z) -> alpha * (LFF(dense(x)) + b) + beta1 * x + beta2 * outer
 
-    The four dense convs write their LeakyReLU'd outputs straight into channel slices of one (F+4*gc)-channel
-    concat buffer (no torch.cat, torch_blocks.py:214); the LFF epilogue applies bias, the 0.2 residual scale
-    and the skip add(s) (torch_blocks.py:285-290, and :328-330 when this is the last RDB of an RRDB).
+    ONE C-ABI call per direction (ws_rdb_forward / ws_rdb_backward): the dense convs write their LeakyReLU'd
+    outputs straight into channel slices of one (F+4*gc)-channel concat buffer (no torch.cat,
+    torch_blocks.py:214); the LFF epilogue applies bias, the 0.2 residual scale and the skip add(s)
+    (torch_blocks.py:285-290, and :328-330 when this is the last RDB of an RRDB).  Backward walks the block in
+    reverse: LFF wgrad/dgrad, then per dense conv LeakyReLU-backward of its slice, wgrad, dgrad accumulated into
+    the fp32 gradient of the concat buffer.
     """
 
     @staticmethod
     def forward(ctx, x, outer, cfg, *params):
         # params: w0..w{k-1}, w_lff, b_lff
+        _require_cuda(x)
+        lib = load()
         nconv = cfg["nconv"]
         ws, w_lff, b_lff = params[:nconv], params[nconv], params[nconv + 1]
-        caches = cfg["caches"]
-        slope = cfg["slope"]
         n, f, X, Y, Z = x.shape
         gc = ws[0].shape[0] if nconv else 0
         ctot = f + nconv * gc
         cdt = act_dtype()
-        buf = empty_cl(n, ctot, X, Y, Z, cdt, x.device)
-        copy_(x, buf[:, :f])
         k = ws[0].shape[2] if nconv else 1
-        pad = (k - 1) // 2
-        for i in range(nconv):
-            cin = f + i * gc
-            shape = make_shape((n, cin, X, Y, Z), gc, (k, k, k), 1, pad)
-            conv_fwd(buf[:, :cin], ws[i], caches[i], shape, buf[:, cin:cin + gc], slope=slope)
         kl = w_lff.shape[2]
-        shape_l = make_shape((n, ctot, X, Y, Z), f, (kl, kl, kl), 1, (kl - 1) // 2)
+        desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], cfg["alpha"], cfg["beta1"],
+                              cfg["beta2"] if outer is not None else 0.0, math_mode(), 0)
+        state: RDBState = cfg["state"]
+        packed, desc.repack = state.buffers(desc, params, 0)
+        buf = empty_cl(n, ctot, X, Y, Z, cdt, x.device)
         out = empty_cl(n, f, X, Y, Z, torch.float32, x.device)
-        conv_fwd(buf, w_lff, caches[nconv], shape_l, out, bias=b_lff.detach() if b_lff is not None else None,
-                 alpha=cfg["alpha"], res1=x, beta1=cfg["beta1"], res2=outer,
-                 beta2=cfg["beta2"] if outer is not None else 0.0)
+        xv, bv, ov = view(x), view(buf), view(out)
+        outer_v = view(outer) if outer is not None else null_view()
+        wd = [p.detach() for p in params[:nconv + 1]]
+        check(lib.ws_rdb_forward(C.byref(desc), C.byref(xv), C.byref(outer_v), C.byref(bv), C.byref(ov),
+                                 _ptr_array(wd), _ptr_array(packed), ptr(b_lff), stream_ptr()), "ws_rdb_forward")
         ctx.cfg = cfg
-        ctx.dims = (n, f, X, Y, Z, gc, ctot, k, kl)
+        ctx.desc_args = (n, X, Y, Z, f, gc, nconv, k, kl)
         ctx.has_outer = outer is not None
         ctx.save_for_backward(buf, *params)
         return out
 
     @staticmethod
     def backward(ctx, dy):
+        lib = load()
         buf, *params = ctx.saved_tensors
         cfg = ctx.cfg
-        nconv = cfg["nconv"]
-        ws, w_lff, b_lff = params[:nconv], params[nconv], params[nconv + 1]
-        caches, slope = cfg["caches"], cfg["slope"]
-        n, f, X, Y, Z, gc, ctot, k, kl = ctx.dims
+        n, X, Y, Z, f, gc, nconv, k, kl = ctx.desc_args
+        ctot = f + nconv * gc
         cdt = act_dtype()
         dev = dy.device
         need = ctx.needs_input_grad
         need_params = any(need[3:])
-        # gradient through the LFF: d(acc) = alpha * dy
-        g_l = empty_cl(n, f, X, Y, Z, cdt, dev)
-        axpby(dy, cfg["alpha"], None, 0.0, g_l)
-        shape_l = make_shape((n, ctot, X, Y, Z), f, (kl, kl, kl), 1, (kl - 1) // 2)
-        grads = [None] * (nconv + 2)
-        if need_params:
-            dw, db = conv_wgrad(buf, g_l, shape_l, want_bias=b_lff is not None)
-            grads[nconv], grads[nconv + 1] = dw, db
+        desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], cfg["alpha"], cfg["beta1"],
+                              cfg["beta2"] if ctx.has_outer else 0.0, math_mode(), 0)
+        state: RDBState = cfg["state"]
+        packed, desc.repack = state.buffers(desc, params, 1)
+        if dy.dtype != torch.float32 or not _linear_voxels(dy):
+            dy = dy.float().contiguous(memory_format=torch.channels_last_3d)
         dbuf = empty_cl(n, ctot, X, Y, Z, torch.float32, dev)
-        conv_dgrad(g_l, w_lff, caches[nconv], shape_l, dbuf)
-        pad = (k - 1) // 2
-        for i in range(nconv - 1, -1, -1):
-            cin = f + i * gc
-            shape = make_shape((n, cin, X, Y, Z), gc, (k, k, k), 1, pad)
-            g = empty_cl(n, gc, X, Y, Z, cdt, dev)
-            lrelu_bwd(dbuf[:, cin:cin + gc], buf[:, cin:cin + gc], slope, g)
-            if need_params:
-                grads[i], _ = conv_wgrad(buf[:, :cin], g, shape)
-            d_in = dbuf[:, :cin]
-            conv_dgrad(g, ws[i], caches[i], shape, d_in, res1=d_in, beta1=1.0)
-        dx = None
-        if need[0]:
-            dx = empty_cl(n, f, X, Y, Z, torch.float32, dev)
-            axpby(dbuf[:, :f], 1.0, dy, cfg["beta1"], dx)
+        g_lff = empty_cl(n, f, X, Y, Z, cdt, dev)
+        g = empty_cl(n, max(gc, 1), X, Y, Z, cdt, dev)
+        dx = empty_cl(n, f, X, Y, Z, torch.float32, dev) if need[0] else None
+        grads = [None] * (nconv + 2)
+        dw_arr = None
+        db = None
+        if need_params:
+            for i in range(nconv + 1):
+                grads[i] = torch.empty_like(params[i], dtype=torch.float32)
+            if params[nconv + 1] is not None:
+                db = torch.empty_like(params[nconv + 1], dtype=torch.float32)
+                grads[nconv + 1] = db
+            dw_arr = _ptr_array(grads[:nconv + 1])
+        nbytes = max(int(params[i].numel()) for i in range(nconv + 1)) * 4
+        wsp = _workspace(nbytes, dev)
+        dyv, bv, dbv, glv, gv = view(dy), view(buf), view(dbuf), view(g_lff), view(g)
+        dxv = view(dx) if dx is not None else null_view()
+        wd = [p.detach() for p in params[:nconv + 1]]
+        check(lib.ws_rdb_backward(C.byref(desc), C.byref(dyv), C.byref(bv), C.byref(dbv), C.byref(glv), C.byref(gv),
+                                  C.byref(dxv), _ptr_array(wd), _ptr_array(packed), dw_arr, ptr(db),
+                                  wsp.data_ptr(), wsp.numel(), stream_ptr()), "ws_rdb_backward")
         douter = None
         if ctx.has_outer and need[1]:
             douter = dy if cfg["beta2"] == 1.0 else dy * cfg["beta2"]

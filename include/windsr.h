@@ -136,6 +136,35 @@ size_t ws_conv3d_wgrad_workspace_bytes(const ws_conv_shape* s, int math);
 int ws_conv3d_wgrad(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, float* dw, float* db,
                     int accumulate, int math, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- residual dense block executor (torch_blocks.py:217-290, 328-330) ------------------------------- */
+/* One call runs a whole RDB: (re)pack its weights, 4 dense conv + LeakyReLU launches writing channel slices of the
+ * concat buffer, then the LFF conv whose epilogue applies  out = alpha*(LFF(buf)+bias) + beta1*x + beta2*outer.
+ * The launch-bound trunk (240 of 249 generator convs) spends its time in launch overhead otherwise. */
+#define WS_RDB_MAX_CONVS 8
+typedef struct ws_rdb_desc {
+  int32_t n, x, y, z;       /* LR volume                                   */
+  int32_t f, gc, nconv;     /* in/out channels, growth channels, dense convs */
+  int32_t k, k_lff;         /* dense kernel size (3), LFF kernel size (1)    */
+  float slope, alpha, beta1, beta2;
+  int32_t math;
+  int32_t repack;           /* 1: weights changed since the last call -> pack again */
+} ws_rdb_desc;
+/* bytes each per-conv packed-weight buffer must have (max over the packings this path may choose) */
+size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int conv_index /* 0..nconv-1 dense, nconv = LFF */, int dgrad);
+/* x: fp32 trunk state (n,f,..); outer: optional fp32 (RRDB input); buf: (n, f+nconv*gc, ..) activation-dtype
+ * concat buffer (filled here, saved for backward); out: fp32 (n,f,..).
+ * w[i]: torch-layout fp32 weights, packed[i]: device buffers of ws_rdb_packed_bytes(i, 0). */
+int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* outer, const ws_tensor* buf,
+                   const ws_tensor* out, const float* const* w, void* const* packed, const float* lff_bias,
+                   void* stream);
+/* dy: fp32 gradient of `out`.  Scratch: dbuf fp32 (n, f+nconv*gc, ..), g_lff activation-dtype (n,f,..),
+ * g activation-dtype (n,gc,..).  dx (optional) = dL/dx incl. the beta1 skip.  dw[i] (optional, torch layout)
+ * and db_lff receive the parameter gradients (overwritten).  packed[i]: buffers of ws_rdb_packed_bytes(i, 1). */
+int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* buf, const ws_tensor* dbuf,
+                    const ws_tensor* g_lff, const ws_tensor* g, const ws_tensor* dx, const float* const* w,
+                    void* const* packed, float* const* dw, float* db_lff, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---- nearest upsample (x2 in x and y, z untouched): nn.Upsample(scale_factor=(2,2,1)) torch_blocks.py:347 */
 /* in: (n, c, x, y, z) view, out: (n, c, 2x, 2y, z) view; bit-exact gather out[x,y,z] = in[x/2, y/2, z] */
 int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,

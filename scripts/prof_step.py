@@ -23,6 +23,14 @@ gan.feed_xy_niter(x, y, torch.tensor(t.niter, device=dev), t.d_g_train_ratio, t.
 for i in range(3):
     gan.optimize_parameters(LR, HR, Z, 1 + i)
 torch.cuda.synchronize()
+import time
+for i in range(3):
+    t0 = time.perf_counter()
+    gan.optimize_parameters(LR, HR, Z, 4)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"step: CPU enqueue {1e3*(t1-t0):.1f} ms (includes the one host read before backward), total {1e3*(t2-t0):.1f} ms")
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     gan.optimize_parameters(LR, HR, Z, 5)
     torch.cuda.synchronize()

@@ -126,8 +126,11 @@ class wind_field_GAN_3D(BaseGAN):
 
     # ---------------------------------------------------------------------------------------------------
     def _noise(self, sigma, shape, it):
-        return trainingtricks.instance_noise(torch.tensor(sigma, device=self.device), shape, it, self.niter,
-                                             device=self.device)
+        """instance noise U[0,1) * sqrt(sigma * (1 - (it-1)/niter)) (trainingtricks.py:49-58); the scalar is formed
+        on the host (no H2D copy / stream sync per call); past niter+1 it is NaN like the reference's sqrt(<0)."""
+        var = float(sigma) * (1.0 - (float(it) - 1.0) / float(self._niter_host))
+        scale = math.sqrt(var) if var >= 0.0 else float("nan")
+        return torch.rand(shape, device=self.device) * scale
 
     def D_forward(self, HR, fake_HR, it, train_D: bool):
         """D on the real and generated batch (wind_field_GAN_3D.py:221-304): train mode + sigma 1 noise in D
@@ -260,7 +263,7 @@ class wind_field_GAN_3D(BaseGAN):
     def compute_losses_and_optimize(self, LR, HR, Z, it, training_iteration: bool = False):
         self.batch_size = HR.size(0)
         it_host = int(it)
-        it_dev = torch.tensor(float(it_host), device=self.device)
+        it_dev = it_host  # only the host value is needed: schedule, labels and noise scale are host-side scalars
         self.make_new_labels(it_host)
         if self.use_D_feature_extractor_cost and it_host % self.cfg.training.feature_D_update_period == 0:
             self.feature_extractor = copy.deepcopy(self.D.features)

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "tc_task.cuh"
 
 namespace ws {
 
@@ -39,8 +40,10 @@ int simt_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void
 size_t simt_wgrad_workspace_bytes(const ConvGeom&);
 int bias_grad(const View&, float*, int, int, long long, int, cudaStream_t);
 bool tc_view_ok(const View&, int);
-int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t);
-int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t);
+int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t,
+                   const TcOverride* ov = nullptr);
+int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t,
+                    const TcOverride* ov = nullptr);
 bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
@@ -111,9 +114,8 @@ static int fwd_path(const ConvGeom& g, const View& in, int math) {
 }
 static int dgrad_path(const ConvGeom& g, const View& dy, int math) {
   if (math != WS_MATH_BF16) return WS_PATH_SIMT;
-  if (tc_disabled("dgrad")) return WS_PATH_SIMT;
+  if (tc_disabled("dgrad") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
   if (device_cc_major() != 10) return WS_PATH_SIMT;
-  if (g.sx != 1 || g.sy != 1 || g.sz != 1) return WS_PATH_SIMT;
   if (!tc_view_ok(dy, g.cout)) return WS_PATH_SIMT;
   if (g.z > 128) return WS_PATH_SIMT;
   return WS_PATH_TCGEN05;
@@ -125,6 +127,50 @@ static int wgrad_path(const ConvGeom& g, const View& in, const View& dy, int mat
   if (!tc_view_ok(in, g.cin) || !tc_view_ok(dy, g.cout)) return WS_PATH_SIMT;
   if (g.cin > 256 && g.cout > 256) return WS_PATH_SIMT;
   return WS_PATH_TCGEN05;
+}
+
+// Data-gradient of a STRIDED conv on the tensor cores: the input grid splits into sx*sy*sz parity classes; within
+// a class the gradient is a stride-1 correlation of dy with the sub-set of taps of matching parity, written to the
+// (d*s + parity) voxels of dx.  (Replaces the dgrad of the (4,4,3)/(2,2,1|2) discriminator convs,
+// torch_blocks.py:467-506, which the CUDA-core family computed by testing every tap for divisibility.)
+static int tc_strided_dgrad(const ConvGeom& g, const View& dy, const void* packed_w, const View& dx, const Epi& ep,
+                            cudaStream_t st) {
+  const int rows = (g.cin + 15) / 16 * 16, cols = (g.cout + 7) / 8 * 8;
+  (void)rows; (void)cols;
+  int tap_base = 0;
+  for (int pa = 0; pa < g.sx; ++pa)
+    for (int pb = 0; pb < g.sy; ++pb)
+      for (int pc = 0; pc < g.sz; ++pc) {
+        const int par[3] = {pa, pb, pc}, k[3] = {g.kx, g.ky, g.kz}, s[3] = {g.sx, g.sy, g.sz};
+        const int pad[3] = {g.px, g.py, g.pz}, ext[3] = {g.x, g.y, g.z};
+        int nt[3], pp[3], dd[3];
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+          const int i0 = (par[a] + pad[a]) % s[a];
+          nt[a] = i0 < k[a] ? (k[a] - i0 + s[a] - 1) / s[a] : 0;
+          const int s0 = (par[a] + pad[a] - i0) / s[a];
+          pp[a] = nt[a] - 1 - s0;
+          dd[a] = (ext[a] - par[a] + s[a] - 1) / s[a];
+          if (nt[a] == 0 || dd[a] <= 0) empty = true;
+        }
+        const int class_taps = nt[0] * nt[1] * nt[2];
+        if (dd[0] <= 0 || dd[1] <= 0 || dd[2] <= 0) { tap_base += class_taps; continue; }
+        WS_REQUIRE(!empty, "strided dgrad: a parity class without taps is not supported on the tcgen05 path");
+        TcOverride ov;
+        ov.DX = dd[0]; ov.DY = dd[1]; ov.DZ = dd[2];
+        ov.SX = g.xo; ov.SY = g.yo; ov.SZ = g.zo;
+        ov.kx = nt[0]; ov.ky = nt[1]; ov.kz = nt[2];
+        ov.px = pp[0]; ov.py = pp[1]; ov.pz = pp[2];
+        ov.ck = g.cout; ov.cn = g.cin;
+        ov.tap_base = tap_base; ov.taps_total = g.taps();
+        ov.omx = g.sx; ov.oax = pa; ov.omy = g.sy; ov.oay = pb; ov.omz = g.sz; ov.oaz = pc;
+        ov.ODY = g.y; ov.ODZ = g.z;
+        int r = tc2_enabled() ? tc2_conv_launch(g, 1, dy, packed_w, dx, ep, st, &ov) : -1;
+        if (r < 0) r = tc_conv_launch(g, 1, dy, packed_w, dx, ep, st, &ov);
+        if (r) return r;
+        tap_base += class_taps;
+      }
+  return 0;
 }
 
 }  // namespace ws
@@ -200,6 +246,7 @@ int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* pac
   View vdy(dy), vdx(dx);
   Epi e(ep, g.cin);
   if (dgrad_path(g, vdy, math) == WS_PATH_TCGEN05) {
+    if (is_strided(g)) return tc_strided_dgrad(g, vdy, packed_w, vdx, e, (cudaStream_t)stream);
     if (tc2_enabled()) {
       int r = tc2_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
       if (r >= 0) return r;

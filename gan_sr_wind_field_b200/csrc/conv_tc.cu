@@ -28,6 +28,7 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "tc_task.cuh"
 
 namespace ws {
 
@@ -53,6 +54,8 @@ struct TcParams {
   int stages;
   int stage_bytes;
   int a_rows;      // bz*by*bx
+  int tap_base;    // first tap of the packed weights this launch uses
+  int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
 };
 
@@ -123,7 +126,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_dst = smem_base + stage * p.stage_bytes;
           ptx::mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
           ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), ch * 64, cz, cy, cx, n);
-          ptx::tma_load_3d(a_dst + kABytes, &tmB, full_bar(stage), ch * 64, n0, tap);
+          ptx::tma_load_3d(a_dst + kABytes, &tmB, full_bar(stage), ch * 64, n0, p.tap_base + tap);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -165,7 +168,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int rx = row / (p.bz * p.by);
     const int gx = x0 + rx, gy = y0 + ry, gz = z0 + rz;
     const bool row_ok = row < p.a_rows && gx < p.DX && gy < p.DY && gz < p.DZ;
-    const long long v = ((long long)gx * p.DY + gy) * p.DZ + gz;
+    const long long v = ((long long)(gx * p.omx + p.oax) * p.ODY + (gy * p.omy + p.oay)) * p.ODZ + (gz * p.omz + p.oaz);
 
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
@@ -288,11 +291,15 @@ bool tc_view_ok(const View& v, int channels) {
 
 // mode 0: forward (src = in, dst = out); mode 1: stride-1 dgrad (src = dy, dst = dx).
 int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* packed_w, const View& dst,
-                   const Epi& ep, cudaStream_t st) {
+                   const Epi& ep, cudaStream_t st, const TcOverride* ov) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int SX, SY, SZ;
-  if (mode == 0) {
+  int taps_total = g.taps();
+  if (ov) {
+    p.DX = ov->DX; p.DY = ov->DY; p.DZ = ov->DZ; SX = ov->SX; SY = ov->SY; SZ = ov->SZ;
+    p.sx = p.sy = p.sz = 1; p.px = ov->px; p.py = ov->py; p.pz = ov->pz; p.ck = ov->ck; p.cn = ov->cn;
+  } else if (mode == 0) {
     p.DX = g.xo; p.DY = g.yo; p.DZ = g.zo; SX = g.x; SY = g.y; SZ = g.z;
     p.sx = g.sx; p.sy = g.sy; p.sz = g.sz; p.px = g.px; p.py = g.py; p.pz = g.pz;
     p.ck = g.cin; p.cn = g.cout;
@@ -304,6 +311,12 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
     p.ck = g.cout; p.cn = g.cin;
   }
   p.N = g.n; p.kx = g.kx; p.ky = g.ky; p.kz = g.kz;
+  p.omx = p.omy = p.omz = 1; p.ODY = p.DY; p.ODZ = p.DZ;
+  if (ov) {
+    p.kx = ov->kx; p.ky = ov->ky; p.kz = ov->kz; p.tap_base = ov->tap_base; taps_total = ov->taps_total;
+    p.omx = ov->omx; p.oax = ov->oax; p.omy = ov->omy; p.oay = ov->oay; p.omz = ov->omz; p.oaz = ov->oaz;
+    p.ODY = ov->ODY; p.ODZ = ov->ODZ;
+  }
   choose_tile(p.DX, p.DY, p.DZ, p.sx, p.sy, p.sz, p.bx, p.by, p.bz);
   p.tiles_x = (p.DX + p.bx - 1) / p.bx;
   p.tiles_y = (p.DY + p.by - 1) / p.by;
@@ -320,7 +333,7 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
   p.stage_bytes = kABytes + p.n_umma * 128;
   p.stages = (int)((220 * 1024 - 1024 - 256) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  int iters = g.taps() * p.kchunks;
+  int iters = p.kx * p.ky * p.kz * p.kchunks;
   if (p.stages > iters) p.stages = iters < 2 ? 2 : iters;
   uint32_t cols = 32;
   while ((int)cols < p.n_umma) cols <<= 1;
@@ -352,7 +365,7 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
   memset(&kb, 0, sizeof(kb));
   kb.ptr = reinterpret_cast<uintptr_t>(packed_w);
   kb.rank = 3; kb.dtype = WS_BF16;
-  kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)g.taps();
+  kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)taps_total;
   kb.strides[0] = (uint64_t)ck_pad * 2;
   kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
   kb.box[0] = 64; kb.box[1] = (uint32_t)p.n_umma; kb.box[2] = 1;

@@ -23,6 +23,7 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "tc_task.cuh"
 
 namespace ws {
 
@@ -43,6 +44,8 @@ struct Tc2Params {
   int a_bufs;        // halo buffers in the ring (2..kMaxABufs)
   int a_sub_slabs;   // x-slabs per TMA instruction of the halo load
   int a_ops;         // TMA instructions per halo load
+  int tap_base;      // first tap of the packed weights this launch uses
+  int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
 };
 
@@ -114,7 +117,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
         for (int ti = 0; ti < p.kx; ++ti) {
-          const int tap = (ti * p.ky + tj) * p.kz + tl;
+          const int tap = p.tap_base + (ti * p.ky + tj) * p.kz + tl;
           ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(w_full(wsl), (uint32_t)p.w_bytes);
@@ -178,7 +181,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ry = rem / p.bz, rz = rem - ry * p.bz;
       const int gx = x0 + rx, gy = y0 + ry;
       const bool row_ok = r < p.out_rows && gx < p.DX && gy < p.DY;
-      const long long v = ((long long)gx * p.DY + gy) * p.DZ + rz;
+      const long long v = ((long long)(gx * p.omx + p.oax) * p.ODY + (gy * p.omy + p.oay)) * p.ODZ + (rz * p.omz + p.oaz);
       for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
         if (n0 + c0 >= p.cn) break;
         uint32_t rr[16];
@@ -273,12 +276,16 @@ bool tc2_enabled() {
 
 // mode 0: forward; mode 1: stride-1 dgrad. Returns -1 when this geometry is not covered (caller uses v1).
 int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* packed_w, const View& dst,
-                    const Epi& ep, cudaStream_t st) {
-  if (g.sx != 1 || g.sy != 1 || g.sz != 1) return -1;
+                    const Epi& ep, cudaStream_t st, const TcOverride* ov) {
+  if (!ov && (g.sx != 1 || g.sy != 1 || g.sz != 1)) return -1;
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   int SX, SY, SZ;
-  if (mode == 0) {
+  int taps_total = g.taps();
+  if (ov) {
+    p.DX = ov->DX; p.DY = ov->DY; p.DZ = ov->DZ; SX = ov->SX; SY = ov->SY; SZ = ov->SZ;
+    p.px = ov->px; p.py = ov->py; p.pz = ov->pz; p.ck = ov->ck; p.cn = ov->cn;
+  } else if (mode == 0) {
     p.DX = g.xo; p.DY = g.yo; p.DZ = g.zo; SX = g.x; SY = g.y; SZ = g.z;
     p.px = g.px; p.py = g.py; p.pz = g.pz; p.ck = g.cin; p.cn = g.cout;
   } else {
@@ -286,6 +293,12 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     p.px = g.kx - 1 - g.px; p.py = g.ky - 1 - g.py; p.pz = g.kz - 1 - g.pz; p.ck = g.cout; p.cn = g.cin;
   }
   p.N = g.n; p.kx = g.kx; p.ky = g.ky; p.kz = g.kz; p.bz = p.DZ;
+  p.omx = p.omy = p.omz = 1; p.ODY = p.DY; p.ODZ = p.DZ;
+  if (ov) {
+    p.kx = ov->kx; p.ky = ov->ky; p.kz = ov->kz; p.tap_base = ov->tap_base; taps_total = ov->taps_total;
+    p.omx = ov->omx; p.oax = ov->oax; p.omy = ov->omy; p.oay = ov->oay; p.omz = ov->omz; p.oaz = ov->oaz;
+    p.ODY = ov->ODY; p.ODZ = ov->ODZ;
+  }
   const int cn_pad = (p.cn + 15) / 16 * 16;
   const int ck_pad = (p.ck + 7) / 8 * 8;
   const int n_tiles = (cn_pad + 255) / 256;
@@ -342,7 +355,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   memset(&kb, 0, sizeof(kb));
   kb.ptr = reinterpret_cast<uintptr_t>(packed_w);
   kb.rank = 3; kb.dtype = WS_BF16;
-  kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)g.taps();
+  kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)taps_total;
   kb.strides[0] = (uint64_t)ck_pad * 2;
   kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
   kb.box[0] = 64; kb.box[1] = (uint32_t)p.n_umma; kb.box[2] = 1;

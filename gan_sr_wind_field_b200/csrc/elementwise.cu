@@ -63,6 +63,27 @@ __global__ void pack_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__
   }
 }
 
+// One parity class of a STRIDED data-gradient (conv_tc*.cu + api.cu: tc_strided_dgrad): taps (tu,tv,tl) of the
+// class map to original taps i = i0 + s*(nt-1-t) per axis.  p[t][ci_pad16][co_pad8] = w[co][ci][ix][iy][iz].
+__global__ void pack_tc_class(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout, int cin, int kx,
+                              int ky, int kz, int ntx, int nty, int ntz, int i0x, int i0y, int i0z, int sx, int sy,
+                              int sz, int rows_pad, int cols_pad) {
+  const int taps = ntx * nty * ntz;
+  long long total = (long long)taps * rows_pad * cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int col = (int)(i % cols_pad);
+    long long r = i / cols_pad;
+    int row = (int)(r % rows_pad);
+    int t = (int)(r / rows_pad);
+    int tl = t % ntz, tv = (t / ntz) % nty, tu = t / (ntz * nty);
+    int ix = i0x + sx * (ntx - 1 - tu), iy = i0y + sy * (nty - 1 - tv), iz = i0z + sz * (ntz - 1 - tl);
+    float v = 0.f;
+    if (row < cin && col < cout) v = w[(((long long)col * cin + row) * kx + ix) * ky * kz + iy * kz + iz];
+    p[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ---- copies ------------------------------------------------------------------------------------------
 // generic strided copy; thread index runs over (n, v, c) with c fastest when dst is channels-last,
 // and over (n, c, v) with v fastest when dst is NCXYZ, so the WRITE side is always coalesced.
@@ -367,6 +388,25 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
     long long total = (long long)g.cout * g.cin * taps;
     pack_simt<<<grid_for(total), kBlock, 0, st>>>(w, (float*)packed, g.cout, g.cin, taps,
                                                  kind == WS_PACK_SIMT_DGRAD);
+  } else if (kind == WS_PACK_TC_DGRAD && (g.sx != 1 || g.sy != 1 || g.sz != 1)) {
+    // strided conv: one block of taps per parity class of the input grid, classes in (pa, pb, pc) order
+    const int rows = (g.cin + 15) / 16 * 16, cols = (g.cout + 7) / 8 * 8;
+    __nv_bfloat16* out = (__nv_bfloat16*)packed;
+    for (int pa = 0; pa < g.sx; ++pa)
+      for (int pb = 0; pb < g.sy; ++pb)
+        for (int pc = 0; pc < g.sz; ++pc) {
+          const int i0x = (pa + g.px) % g.sx, i0y = (pb + g.py) % g.sy, i0z = (pc + g.pz) % g.sz;
+          const int ntx = i0x < g.kx ? (g.kx - i0x + g.sx - 1) / g.sx : 0;
+          const int nty = i0y < g.ky ? (g.ky - i0y + g.sy - 1) / g.sy : 0;
+          const int ntz = i0z < g.kz ? (g.kz - i0z + g.sz - 1) / g.sz : 0;
+          const long long total = (long long)ntx * nty * ntz * rows * cols;
+          if (total == 0) continue;
+          pack_tc_class<<<grid_for(total), kBlock, 0, st>>>(w, out, g.cout, g.cin, g.kx, g.ky, g.kz, ntx, nty, ntz,
+                                                           i0x, i0y, i0z, g.sx, g.sy, g.sz, rows, cols);
+          WS_POST_LAUNCH(1);
+          out += total;
+        }
+    return 0;
   } else {
     int dgrad = kind == WS_PACK_TC_DGRAD;
     int rows = dgrad ? (g.cin + 15) / 16 * 16 : (g.cout + 15) / 16 * 16;

@@ -7,13 +7,13 @@ def noisy_labels(label_type, batch_size, noise_stddev=0.05, false_label_val=0.0,
                  val_lower_lim=0.0, val_upper_lim=1.0, device=torch.device("cpu")):
     """Gaussian-perturbed real/fake label vector of length ``batch_size``, clamped to [lower, upper]."""
     std = float(noise_stddev)
+    base = float(true_label_val if label_type else false_label_val)
+    lo, hi = float(val_lower_lim), float(val_upper_lim)
     if std > 0.0:
-        label = torch.normal(mean=0.0, std=torch.full((int(batch_size),), std)).to(device)
-    else:
-        # torch.normal with std 0 returns the mean; skip the host RNG round trip
-        label = torch.zeros(int(batch_size), device=device)
-    label = label + (true_label_val if label_type else false_label_val)
-    return torch.clamp(label, min=float(val_lower_lim), max=float(val_upper_lim))
+        label = torch.randn(int(batch_size), device=device) * std + base
+        return torch.clamp(label, min=lo, max=hi)
+    # no noise: a constant vector, filled on the device (no host RNG round trip, no H2D copy)
+    return torch.full((int(batch_size),), min(max(base, lo), hi), device=device)
 
 
 def instance_noise(sigma_base, shape, it, niter, device=torch.device("cpu")):

@@ -193,16 +193,20 @@ class wind_field_GAN_3D(BaseGAN):
         dxy = dxy * t.xy_divergence_loss_weight
         base = adv + pix + feat
         physics = xy + zg + div + dxy
-        # one host read decides both guards of the reference (:434-443 and :457)
-        ok_physics, ok_base = torch.stack([torch.isfinite(physics).all(), torch.isfinite(base).all()]).tolist()
-        loss_G = base + physics if ok_physics else base
+        # The reference's guards (:434-443 and :457): drop the physics terms when any of them is NaN/Inf, and skip
+        # the optimiser step when the total is NaN/Inf.  The first is decided ON THE DEVICE (select, with
+        # WindLossFn.backward discarding the 0*inf cotangents of the dropped branch); the second needs the host,
+        # but is read only after backward has been enqueued, so the single host sync of the step overlaps nothing.
+        ok_physics = torch.isfinite(physics).all()
+        loss_G = base + torch.where(ok_physics, physics, torch.zeros_like(physics))
+        ok_total = torch.isfinite(base).all()
         if training_iteration:
             if self.sync_G is not None:
                 self.sync_G.begin()
             loss_G.backward()
             if self.sync_G is not None:
                 self.sync_G.finish()
-            if ok_base:  # loss_G is finite (the reference's second guard, :457)
+            if bool(ok_total):  # loss_G is finite
                 self.optimizer_G.step()
         d = self.train_G_loss_dict if training_iteration else self.validation_G_loss_dict
         d.update(total=loss_G, adversarial=adv, pix=pix, xy_gradient=xy, z_gradient=zg, divergence=div,

@@ -546,17 +546,18 @@ conv_small_cin_fwd(ConvGeom g, View src, const float* __restrict__ w /*[tap][cin
   }
 }
 
-// wgrad for Cin <= 4: every thread owns up to 8 of the taps*cin*cout outputs and walks its block's voxel chunk;
-// within a warp the x gathers hit 1-2 addresses (co is the fastest thread index) and the dy reads are contiguous.
+// wgrad for Cin <= 4: every thread owns up to 8 of the taps*cin*cout outputs; a block walks a run of (x, y)
+// columns and, per column, the z levels — tap validity and the x/y part of the gather offset are resolved once
+// per column, so the inner loop is {z-range check, 2 loads, 1 FMA}.  Within a warp (co fastest) the x gathers hit
+// 1-2 addresses and the dy reads are contiguous.  Block partials are combined with one atomic per output.
 __global__ void __launch_bounds__(512)
 conv_small_cin_wgrad(ConvGeom g, View in, View dy, float* __restrict__ wsp /*[tap][cin][cout]*/,
-                     long long v_per_block) {
+                     long long cols_per_block) {
   const int T = g.taps();
   const int O = T * g.cin * g.cout;
-  const long long VO = g.vout();
-  const long long K = (long long)g.n * VO;
-  const long long kbeg = (long long)blockIdx.x * v_per_block;
-  const long long kend = kbeg + v_per_block < K ? kbeg + v_per_block : K;
+  const long long ncols = (long long)g.n * g.xo * g.yo;
+  const long long cbeg = (long long)blockIdx.x * cols_per_block;
+  const long long cend = cbeg + cols_per_block < ncols ? cbeg + cols_per_block : ncols;
   constexpr int MAXO = 8;
   float acc[MAXO];
   int o_ti[MAXO], o_tj[MAXO], o_tl[MAXO], o_ci[MAXO], o_co[MAXO];
@@ -565,30 +566,35 @@ conv_small_cin_wgrad(ConvGeom g, View in, View dy, float* __restrict__ wsp /*[ta
   for (int i = 0; i < MAXO; ++i) {
     acc[i] = 0.f;
     int o = threadIdx.x + i * blockDim.x;
+    o_co[i] = o_ci[i] = o_ti[i] = o_tj[i] = o_tl[i] = 0;
     if (o < O) {
       o_co[i] = o % g.cout;
       o_ci[i] = (o / g.cout) % g.cin;
       const int tap = o / (g.cout * g.cin);
       o_ti[i] = tap / (g.ky * g.kz); o_tj[i] = (tap / g.kz) % g.ky; o_tl[i] = tap % g.kz;
       nown = i + 1;
-    } else {
-      o_co[i] = o_ci[i] = o_ti[i] = o_tj[i] = o_tl[i] = 0;
     }
   }
-#pragma unroll 4
-  for (long long kg = kbeg; kg < kend; ++kg) {
-    const int n = (int)(kg / VO);
-    const long long v = kg % VO;
-    const int zo = (int)(v % g.zo);
-    const int yo = (int)((v / g.zo) % g.yo);
-    const int xo = (int)(v / ((long long)g.zo * g.yo));
+  for (long long col = cbeg; col < cend; ++col) {
+    const int yo = (int)(col % g.yo);
+    const int xo = (int)((col / g.yo) % g.xo);
+    const int n = (int)(col / ((long long)g.yo * g.xo));
+    const long long vo0 = ((long long)xo * g.yo + yo) * g.zo;
 #pragma unroll
     for (int i = 0; i < MAXO; ++i) {
       if (i >= nown) break;
-      const int xi = xo * g.sx - g.px + o_ti[i], yi = yo * g.sy - g.py + o_tj[i], zi = zo * g.sz - g.pz + o_tl[i];
-      if (xi < 0 || xi >= g.x || yi < 0 || yi >= g.y || zi < 0 || zi >= g.z) continue;
-      const float xv = in.ld(n, o_ci[i], ((long long)xi * g.y + yi) * g.z + zi);
-      acc[i] = fmaf(xv, dy.ld(n, o_co[i], v), acc[i]);
+      const int xi = xo * g.sx - g.px + o_ti[i], yi = yo * g.sy - g.py + o_tj[i];
+      if (xi < 0 || xi >= g.x || yi < 0 || yi >= g.y) continue;
+      const long long xin = in.off(n, o_ci[i], ((long long)xi * g.y + yi) * g.z);
+      const long long dyo = dy.off(n, o_co[i], vo0);
+      const int zoff = o_tl[i] - g.pz;
+      float a = 0.f;
+      for (int zo = 0; zo < g.zo; ++zo) {
+        const int zi = zo * g.sz + zoff;
+        if (zi < 0 || zi >= g.z) continue;
+        a = fmaf(in.ld(xin + (long long)zi * in.vs), dy.ld(dyo + (long long)zo * dy.vs), a);
+      }
+      acc[i] += a;
     }
   }
 #pragma unroll
@@ -688,11 +694,12 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   if (g.cin <= 4 && g.taps() * g.cin * g.cout <= 8 * 512) {
     const int O = g.taps() * g.cin * g.cout;
     int threads = O < 512 ? (O + 31) / 32 * 32 : 512;
-    long long blocks = 148LL * 64;
-    long long vpb = (K + blocks - 1) / blocks;
-    if (vpb < 32) vpb = 32;
-    blocks = (K + vpb - 1) / vpb;
-    conv_small_cin_wgrad<<<(unsigned)blocks, threads, 0, st>>>(g, in, dy, wsp, vpb);
+    const long long ncols = (long long)g.n * g.xo * g.yo;
+    long long blocks = 148LL * 8;
+    long long cpb = (ncols + blocks - 1) / blocks;
+    if (cpb < 4) cpb = 4;
+    blocks = (ncols + cpb - 1) / cpb;
+    conv_small_cin_wgrad<<<(unsigned)blocks, threads, 0, st>>>(g, in, dy, wsp, cpb);
     WS_POST_LAUNCH(1);
     return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
   }

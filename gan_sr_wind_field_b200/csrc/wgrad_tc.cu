@@ -41,7 +41,7 @@ struct WgParams {
   long long tiles_per_split;
   int kx, ky, kz, sx, sy, sz, px, py, pz;
   int taps, taps_per_cta, tap_groups;
-  int m_blocks;          // 64-channel blocks of the M operand actually loaded (1 or 2)
+  int m_total;           // channels of the M operand covered by this launch (grid.z blocks of 128)
   int n_blocks;          // 64-channel blocks of the N operand
   int m0, n0;            // channel offsets of this launch inside the full cout / cin ranges
   int m_valid, n_valid;  // valid rows / columns of the accumulator
@@ -73,6 +73,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (5 + 2 * kMaxBSlots));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = p.m0 + (int)blockIdx.z * 128;                       // this CTA's 128-row M block
+  const int m_valid = min(128, p.m_total - (int)blockIdx.z * 128);
+  const int m_blocks = (m_valid + 63) / 64;
   const int tap_group = blockIdx.x;
   const int split = blockIdx.y;
   const int tap_lo = tap_group * p.taps_per_cta;
@@ -111,10 +114,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       // the unshifted operand (dy) is the one that is NOT x
       const CUtensorMap* tm_fix = p.shift_on_m ? &tmN : &tmM;
       const CUtensorMap* tm_sh = p.shift_on_m ? &tmM : &tmN;
-      const int fix_blocks = p.shift_on_m ? p.n_blocks : p.m_blocks;
-      const int sh_blocks = p.shift_on_m ? p.m_blocks : p.n_blocks;
-      const int fix_c0 = p.shift_on_m ? p.n0 : p.m0;
-      const int sh_c0 = p.shift_on_m ? p.m0 : p.n0;
+      const int fix_blocks = p.shift_on_m ? p.n_blocks : m_blocks;
+      const int sh_blocks = p.shift_on_m ? m_blocks : p.n_blocks;
+      const int fix_c0 = p.shift_on_m ? p.n0 : m0;
+      const int sh_c0 = p.shift_on_m ? m0 : p.n0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         int t = (int)(tile % tiles_per_n);
         const int n = (int)(tile / tiles_per_n);
@@ -198,8 +201,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         uint32_t r[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tp * p.n_umma + c0), r);
         ptx::tmem_ld_wait();
-        if (m < p.m_valid) {
-          float* dst = wsp + (long long)tap * p.tap_stride + (long long)(p.m0 + m) * p.m_stride +
+        if (m < m_valid) {
+          float* dst = wsp + (long long)tap * p.tap_stride + (long long)(m0 + m) * p.m_stride +
                        (long long)(p.n0 + c0) * p.n_stride;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -248,8 +251,8 @@ size_t tc_wgrad_workspace_bytes(const ConvGeom& g) {
 
 // One launch: M rows = channels [m0, m0+m_count) of the M operand, N cols = channels [n0, n0+n_count) of the
 // N operand.  swap == 0: M = cout (dy), N = cin (x).  swap == 1: M = cin (x), N = cout (dy).
-static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* wsp, int swap, int m0,
-                      int m_count, int n0, int n_count, cudaStream_t st) {
+static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* wsp, int swap, int m_total,
+                      int n0, int n_count, cudaStream_t st) {
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.n;
@@ -262,23 +265,13 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   p.kx = g.kx; p.ky = g.ky; p.kz = g.kz; p.sx = g.sx; p.sy = g.sy; p.sz = g.sz;
   p.px = g.px; p.py = g.py; p.pz = g.pz;
   p.taps = g.taps();
-  p.m0 = m0; p.n0 = n0; p.m_valid = m_count; p.n_valid = n_count;
+  p.m0 = 0; p.m_total = m_total; p.n0 = n0; p.n_valid = n_count;
   p.n_umma = (n_count + 15) / 16 * 16;
-  WS_REQUIRE(m_count <= 128 && p.n_umma <= 256, "wgrad tile too large (%d x %d)", m_count, p.n_umma);
-  p.m_blocks = (m_count + 63) / 64;
+  WS_REQUIRE(p.n_umma <= 256, "wgrad N tile too large (%d)", p.n_umma);
+  const int mz = (m_total + 127) / 128;
   p.n_blocks = (p.n_umma + 63) / 64;
   p.shift_on_m = swap;
-  p.taps_per_cta = 512 / p.n_umma;
-  if (p.taps_per_cta > p.taps) p.taps_per_cta = p.taps;
-  p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
-  // balance taps over groups
-  p.taps_per_cta = (p.taps + p.tap_groups - 1) / p.tap_groups;
-  uint32_t cols = 32;
-  while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
-  p.tmem_cols = cols;
   const int blk = p.rows * 128;
-  const int fix_blocks = swap ? p.n_blocks : p.m_blocks;
-  const int sh_blocks = swap ? p.m_blocks : p.n_blocks;
   // the M operand tile must always present 2 blocks worth of address space (UMMA M = 128 reads 2 blocks)
   const int fix_alloc = swap ? p.n_blocks : 2;
   const int sh_alloc = swap ? 2 : p.n_blocks;
@@ -288,16 +281,44 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   p.b_slots = budget / p.b_slot_bytes;
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
   WS_REQUIRE(p.b_slots >= 2, "wgrad: shared memory budget too small for 2 operand slots");
-  (void)fix_blocks; (void)sh_blocks;
 
-  // split-K so the grid covers the chip a few times
-  long long base_ctas = p.tap_groups;
-  long long splits = (148LL * 2 + base_ctas - 1) / base_ctas;
-  if (splits > p.total_tiles) splits = p.total_tiles;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
-  p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
-  splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  // Work split: tap groups x voxel-tile splits x M blocks.  Modelled cost per CTA =
+  //   tiles * taps_per_cta * max(MMA, L2->SMEM) + taps_per_cta * (128 x N red.global.add epilogue) + fixed,
+  // MMA at the measured max(72, N/2) cycles per K=16 step.  Few taps per CTA keep the atomic epilogue short.
+  const double per_mma = p.n_umma / 2.0 > 72.0 ? p.n_umma / 2.0 : 72.0;
+  const double unit_mma = (p.rows / 16) * per_mma;
+  const double unit_load = (double)sh_alloc * blk / 33.0;
+  const double unit = unit_mma > unit_load ? unit_mma : unit_load;
+  const double atom = 128.0 * p.n_umma * 1.1;
+  const int max_tpc = 512 / p.n_umma;
+  double best = 1e30;
+  int best_tpc = 1;
+  long long best_tps = p.total_tiles;
+  for (int tpc = 1; tpc <= max_tpc && tpc <= p.taps; ++tpc) {
+    const int tg = (p.taps + tpc - 1) / tpc;
+    for (int target = 148; target <= 444; target += 148) {
+      long long splits = (target + (long long)tg * mz - 1) / ((long long)tg * mz);
+      if (splits > p.total_tiles) splits = p.total_tiles;
+      if (splits < 1) splits = 1;
+      const long long tps = (p.total_tiles + splits - 1) / splits;
+      const long long ctas = (long long)tg * mz * ((p.total_tiles + tps - 1) / tps);
+      const long long waves = (ctas + 147) / 148;
+      const double t = (double)waves * (tps * (tpc * unit + (double)fix_alloc * blk / 33.0) + tpc * atom + 8000.0);
+      if (t < best) { best = t; best_tpc = tpc; best_tps = tps; }
+    }
+  }
+  p.taps_per_cta = best_tpc;
+  p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
+  p.tiles_per_split = best_tps;
+  long long splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  if (splits > 65535) {
+    splits = 65535;
+    p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
+    splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
+  p.tmem_cols = cols;
 
   // workspace layout is always [tap][cout][cin]
   p.tap_stride = (long long)g.cout * g.cin;
@@ -336,7 +357,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
-  dim3 grid((unsigned)p.tap_groups, (unsigned)splits);
+  dim3 grid((unsigned)p.tap_groups, (unsigned)splits, (unsigned)mz);
   if (!swap) wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_dy, tm_x, p, wsp);
   else wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_dy, p, wsp);
   WS_POST_LAUNCH(1);
@@ -366,12 +387,9 @@ int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, i
   const bool swap = g.cout < 64 && g.cin >= g.cout;
   const int mtot = swap ? g.cin : g.cout;
   const int ntot = swap ? g.cout : g.cin;
-  for (int m0 = 0; m0 < mtot; m0 += 128) {
-    int mc = mtot - m0 < 128 ? mtot - m0 : 128;
-    for (int n0 = 0; n0 < ntot; n0 += 256) {
-      int nc = ntot - n0 < 256 ? ntot - n0 : 256;
-      if (int e = launch_one(g, x, dy, wsp, swap ? 1 : 0, m0, mc, n0, nc, st)) return e;
-    }
+  for (int n0 = 0; n0 < ntot; n0 += 256) {
+    int nc = ntot - n0 < 256 ? ntot - n0 : 256;
+    if (int e = launch_one(g, x, dy, wsp, swap ? 1 : 0, mtot, n0, nc, st)) return e;
   }
   long long total = (long long)g.taps() * g.cin * g.cout;
   int blocks = (int)((total + 255) / 256);

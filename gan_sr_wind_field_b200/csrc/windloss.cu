@@ -292,11 +292,15 @@ __global__ void windloss_bwd_G_kernel(View hr, View sr, View zalt, const float* 
 #pragma unroll
     for (int c = 0; c < 9; ++c) e[c] = ds[c] - dh[c];
     float div = e[0] + e[4] + e[8], dxy = e[0] + e[4];
+    // a zero coefficient means "this term is not in the loss" (e.g. dropped by the NaN guard): its field may be
+    // Inf/NaN and must not be multiplied in (0 * inf = NaN)
+    auto mul0 = [](float c, float v) { return c == 0.f ? 0.f : c * v; };
 #pragma unroll
-    for (int c = 0; c < 9; ++c) g[c] = (c < 6 ? c_xy : c_z) * e[c];
-    g[0] += c_div * div + c_dxy * dxy;
-    g[4] += c_div * div + c_dxy * dxy;
-    g[8] += c_div * div;
+    for (int c = 0; c < 9; ++c) g[c] = mul0(c < 6 ? c_xy : c_z, e[c]);
+    const float gd = mul0(c_div, div), gxy = mul0(c_dxy, dxy);
+    g[0] += gd + gxy;
+    g[4] += gd + gxy;
+    g[8] += gd;
     // normaliser path: the element(s) that attain SR_max receive dL/dSR_max (sign for the |.| maxes)
     long long base = (long long)p.n * 9 * V + p.v;
     if (a_xy != 0.f || a_z != 0.f) {
@@ -365,9 +369,11 @@ __global__ void windloss_bwd_apply_kernel(View hr, View sr, View zalt, const flo
       float acc = 0.f;
 #pragma unroll
       for (int r = -1; r <= 1; ++r) {
-        if (wx[r + 1] != 0.f) acc += wx[r + 1] * Gn[(long long)c * V + p.v + r * sx];
-        if (wy[r + 1] != 0.f) acc += wy[r + 1] * Gn[(long long)(3 + c) * V + p.v + r * sy];
-        if (wz[r + 1] != 0.f) acc += wz[r + 1] * Gn[(long long)(6 + c) * V + p.v + r];
+        // G == 0 means "no loss term touches this derivative": skip it even if the stencil weight is Inf
+        // (degenerate grid spacing), 0 * inf must not poison the gradient
+        if (wx[r + 1] != 0.f) { float gv = Gn[(long long)c * V + p.v + r * sx]; if (gv != 0.f) acc += wx[r + 1] * gv; }
+        if (wy[r + 1] != 0.f) { float gv = Gn[(long long)(3 + c) * V + p.v + r * sy]; if (gv != 0.f) acc += wy[r + 1] * gv; }
+        if (wz[r + 1] != 0.f) { float gv = Gn[(long long)(6 + c) * V + p.v + r]; if (gv != 0.f) acc += wz[r + 1] * gv; }
       }
       float e = sr.ld(p.n, c, p.v) - hr.ld(p.n, c, p.v);
       float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);

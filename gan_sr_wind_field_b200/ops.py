@@ -756,6 +756,9 @@ class WindLossFn(torch.autograd.Function):
         hr3, sr, Z, cx, cy, argmax = ctx.saved_tensors
         n, c, X, Y, Zn = sr.shape
         coef = torch.zeros((_lib.WLB_SLOTS,), dtype=torch.float32, device=sr.device)
+        # cotangents of loss terms the caller dropped with a device-side select arrive as 0 * inf = NaN: they
+        # stand for "this term is not in the loss" (wind_field_GAN_3D.py:434-443), i.e. zero
+        dres = torch.where(torch.isfinite(dres), dres, torch.zeros_like(dres))
         coef[0:6] = dres[0:6]
         coef[6:10] = dres[7:14:2]  # SR max slots 7, 9, 11, 13
         dsr = torch.empty(sr.shape, dtype=torch.float32, device=sr.device)

@@ -255,3 +255,40 @@ def test_bf16_gradients_at_shipped_init_scale():
         g2 = torch.autograd.grad(torch.nn.functional.l1_loss(o2, HR), [p2[n] for n in names])
     env = {n: rel_l2(a, b) for n, a, b in zip(names, g2, g_ref)}
     assert all(errs[n] <= max(TOL["bf16"], 1.5 * env[n] + 5e-3) for n in names), (errs, env)
+
+
+def test_nan_guard_drops_physics_terms_like_the_reference():
+    """Degenerate altitude levels (two equal z levels -> division by zero in calculate_div_z) make the physics
+    terms NaN/Inf; the reference then optimises adversarial + pixel (+ feature) only
+    (wind_field_GAN_3D.py:434-454).  The device-side guard must give a finite total equal to the oracle's and
+    finite parameter gradients, and still take the optimiser step."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.config.config import Config
+    from gan_sr_wind_field_b200.GAN_models.wind_field_GAN_3D import wind_field_GAN_3D
+    from oracle import wind_oracle as wo
+    z = load_npz("gan_step.npz")
+    cfg = Config(os.path.join(GOLDEN, "configs", "tiny_gan.ini"))
+    cfg.is_train, cfg.gpu_id, cfg.device = True, 0, torch.device("cuda:0")
+    gan = wind_field_GAN_3D(cfg)
+    G0, D0 = sd_from(z, "G0/"), sd_from(z, "D0/")
+    gan.G.load_state_dict(G0)
+    gan.D.load_state_dict(D0)
+    LR, HR, Z, x, y = (torch.from_numpy(z[k]) for k in ("LR", "HR", "Z", "x", "y"))
+    Z = Z.clone()
+    Z[..., 4] = Z[..., 3]  # zero spacing between two levels
+    gan.feed_xy_niter(x.cuda(), y.cuda(), torch.tensor(100, device="cuda"), 1, 2)
+    w0 = gan.G.hr_convs[2].weight.detach().clone()
+    with ops.precision("fp32"):
+        gan.optimize_parameters(LR.cuda(), HR.cuda(), Z.cuda(), 1)
+    losses = {k: float(v) for k, v in gan.get_G_train_loss_dict_ref().items()}
+    assert not np.isfinite(losses["z_gradient"]) or not np.isfinite(losses["divergence"])
+    # oracle with the reference's guard
+    SR = wo.generator_forward(G0, LR, Z)
+    real = torch.full((2,), 0.9 + 0.1 * 1 / 100)
+    adv = wo.adversarial_G(wo.discriminator_forward(D0, HR, False).squeeze(),
+                           wo.discriminator_forward(D0, SR, False).squeeze(), real, torch.zeros(2))
+    total, _ = wo.generator_loss(HR, SR, Z, x, y, dict(pixel=0.136, xy=3.064, z=0.2, div=0.366, dxy=0.721, adv=0.05),
+                                 adv=adv)
+    assert np.isfinite(losses["total"]) and abs(losses["total"] - float(total)) <= 1e-4 * abs(float(total))
+    assert all(torch.isfinite(p.grad).all() for p in gan.G.parameters() if p.grad is not None)
+    assert not torch.equal(gan.G.hr_convs[2].weight.detach(), w0)  # the step was taken

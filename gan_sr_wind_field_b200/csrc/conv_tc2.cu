@@ -49,6 +49,11 @@ struct Tc2Params {
   uint32_t tmem_cols;
 };
 
+// kPair: launched as clusters of two CTAs (cta_group::2).  Each CTA keeps its own halo tile, accumulators and
+// epilogue, but only HALF of every weight tile; the leader issues one M=256 MMA per step that multiplies both CTAs'
+// A tiles with the pair's combined B tile.  Per SM this halves the weight traffic from L2 and the B-operand reads
+// from shared memory (measured: a cta_group::1 N=144 MMA already saturates the 128 B/clk SMEM port).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const Tc2Params p, const View dst, const Epi ep) {
@@ -68,11 +73,15 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (kNumBars + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   int t = blockIdx.x;
+  // a padding CTA (odd tile count in pair mode) works on an out-of-range tile: zero-filled loads, no stores
+  const bool tile_ok = t < p.N * p.tiles_x * p.tiles_y;
   const int tyi = t % p.tiles_y; t /= p.tiles_y;
   const int txi = t % p.tiles_x; t /= p.tiles_x;
-  const int n = t;
-  const int x0 = txi * p.tx, y0 = tyi * p.by;
+  const int n = tile_ok ? t : p.N - 1;
+  const int x0 = tile_ok ? txi * p.tx : p.DX + p.kx, y0 = tyi * p.by;
   const int n0 = blockIdx.y * p.n_tile;
 
   if (warp == 0 && lane == 0) {
@@ -84,15 +93,21 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-    ptx::tmem_relinquish();
+    if (kPair) { ptx::tmem_alloc2(tmem_slot, p.tmem_cols); ptx::tmem_relinquish2(); }
+    else { ptx::tmem_alloc(tmem_slot, p.tmem_cols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // the peer's TMA and the leader's commits target barriers of the other CTA
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int nyz = p.ky * p.kz;
+  // pair mode: per-CTA weight slice = rows [rank * n_umma/2, +n_umma/2) of the tile; the leader's full barriers
+  // count the bytes of both CTAs
+  const uint32_t w_cta_bytes = (uint32_t)p.w_bytes;  // bytes this CTA loads per weight tile (half a tile in pair mode)
+  const int w_row0 = n0 + (kPair ? (int)rank * (p.n_umma / 2) : 0);
+  const uint32_t tx_mult = kPair ? 2u : 1u;
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes) and elect one lane only around the
   // UTMALDG / UTCHMMA instructions: operands then live in uniform registers.  (Round-1 ncu finding: issuing from
@@ -109,10 +124,16 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::mbar_wait(a_empty(ab), aph ^ 1u);
         if (ptx::elect_one()) {
           // the halo box is fetched as a_ops independent TMA instructions (more requests in flight)
-          ptx::mbar_expect_tx(a_full(ab), a_op_bytes * (uint32_t)p.a_ops);
-          for (int o = 0; o < p.a_ops; ++o)
-            ptx::tma_load_5d(smem_base + ab * p.a_buf_bytes + o * a_op_bytes, &tmA, a_full(ab), ch * 64, tl - p.pz,
-                             y0 - p.py + tj, x0 - p.px + o * p.a_sub_slabs, n);
+          if (leader) ptx::mbar_expect_tx(a_full(ab), a_op_bytes * (uint32_t)p.a_ops * tx_mult);
+          for (int o = 0; o < p.a_ops; ++o) {
+            const uint32_t d = smem_base + ab * p.a_buf_bytes + o * a_op_bytes;
+            if (kPair)
+              ptx::tma_load_5d_2sm(d, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
+                                   x0 - p.px + o * p.a_sub_slabs, n);
+            else
+              ptx::tma_load_5d(d, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
+                               x0 - p.px + o * p.a_sub_slabs, n);
+          }
         }
         __syncwarp();
         if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
@@ -120,17 +141,18 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int tap = p.tap_base + (ti * p.ky + tj) * p.kz + tl;
           ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(w_full(wsl), (uint32_t)p.w_bytes);
-            ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, n0, tap);
+            if (leader) ptx::mbar_expect_tx(w_full(wsl), w_cta_bytes * tx_mult);
+            if (kPair) ptx::tma_load_3d_2sm(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, w_row0, tap);
+            else ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, w_row0, tap);
           }
           __syncwarp();
           if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)p.n_umma, 0u, 0u);
+  } else if (warp == 1 && leader) {
+    // ===== MMA issuer (pair mode: the leader CTA only) =====
+    const uint32_t idesc = ptx::make_idesc(1u, kPair ? 256u : 128u, (uint32_t)p.n_umma, 0u, 0u);
     const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);  // everything but the start address
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
@@ -151,24 +173,31 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
           if (ptx::elect_one()) {
             // K advance inside the 128-byte swizzle row: +32 B = +2 in the (addr >> 4) field
-            ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
-            if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-            if (nk > 2) ptx::mma_f16_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            if (nk > 3) ptx::mma_f16_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            if (kPair) {
+              ptx::mma_f16_ss2(d_tmem, adesc, bdesc, idesc, acc0);
+              if (nk > 1) ptx::mma_f16_ss2(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              if (nk > 2) ptx::mma_f16_ss2(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              if (nk > 3) ptx::mma_f16_ss2(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            } else {
+              ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
+              if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              if (nk > 2) ptx::mma_f16_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              if (nk > 3) ptx::mma_f16_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            }
           }
           __syncwarp();
         }
-        if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+        if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(w_empty(wsl)); else ptx::mma_commit(w_empty(wsl)); }
         __syncwarp();
         if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
       }
-      if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
+      if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(a_empty(ab)); else ptx::mma_commit(a_empty(ab)); }
       __syncwarp();
       if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
     }
-    if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+    if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(accum_bar); else ptx::mma_commit(accum_bar); }
     __syncwarp();
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue =====
     const int sub = warp & 3;
     ptx::mbar_wait(accum_bar, 0);
@@ -180,7 +209,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int rem = r - rx * p.slabrows;
       const int ry = rem / p.bz, rz = rem - ry * p.bz;
       const int gx = x0 + rx, gy = y0 + ry;
-      const bool row_ok = r < p.out_rows && gx < p.DX && gy < p.DY;
+      const bool row_ok = tile_ok && r < p.out_rows && gx < p.DX && gy < p.DY;
       const long long v = ((long long)(gx * p.omx + p.oax) * p.ODY + (gy * p.omy + p.oay)) * p.ODZ + (rz * p.omz + p.oaz);
       for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
         if (n0 + c0 >= p.cn) break;
@@ -193,17 +222,19 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::tc_fence_before();
   }
 
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kPair) ptx::tmem_dealloc2(tmem_base, p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
 constexpr int kSmemBudget = 225 * 1024;
 
 // Pick (by, tx): minimise estimated SM-time = waves * max(MMA cycles, L2->SMEM cycles) per K iteration.
-bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p) {
+bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
   const int tmax = 512 / n_umma < 4 ? 512 / n_umma : 4;
   if (tmax < 1 || DZ > 128) return false;
   double best = 1e30;
@@ -231,7 +262,7 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
         if (a_rows < ops_rows) a_rows = ops_rows;
       }
       const int a_bytes = (a_rows * 128 + 1023) / 1024 * 1024;
-      const int w_bytes = n_umma * 128;
+      const int w_bytes = n_umma * 128 / (pair ? 2 : 1);  // per-CTA share of a weight tile
       if (2 * a_bytes + 2 * w_bytes + 2048 > kSmemBudget) continue;
       // measured on B200 (scripts/micro/mma_rate.cu): a cta_group::1 M=128 MMA costs max(72, N/2) cycles — the
       // 4 KB A-operand read from SMEM floors it at ~72 regardless of N
@@ -244,7 +275,7 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, Tc2Params& p)
       const int smem_min = 2 * a_bytes + (kx + 1 < 3 ? 3 : kx + 1) * w_bytes + 2048;
       int cols = 32;
       while (cols < t_m * n_umma) cols <<= 1;
-      int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 ? 2 : 1;
+      int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 && !pair ? 2 : 1;
       const long long per_sm = (ctas + 147) / 148;
       const int r = per_sm < cps ? (int)per_sm : cps;  // CTAs actually sharing an SM
       const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
@@ -304,7 +335,12 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   const int n_tiles = (cn_pad + 255) / 256;
   p.n_tile = ((cn_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
   p.n_umma = p.n_tile;
-  if (!choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, p)) return -1;
+  // CTA-pair mode (cta_group::2): worth it when the weight tile is wide and the grid is large
+  static const int env_pair = getenv("WS_TC2_PAIR") ? atoi(getenv("WS_TC2_PAIR")) : -1;
+  const long long vox = (long long)p.N * p.DX * p.DY * p.DZ;
+  bool pair = env_pair >= 0 ? env_pair != 0 : (p.n_umma >= 128 && vox >= 148LL * 2 * 384);
+  if (n_tiles != 1) pair = false;
+  if (!choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, pair, p)) return -1;
   p.out_rows = p.tx * p.slabrows;
   p.tiles_x = (p.DX + p.tx - 1) / p.tx;
   p.tiles_y = (p.DY + p.by - 1) / p.by;
@@ -358,7 +394,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)taps_total;
   kb.strides[0] = (uint64_t)ck_pad * 2;
   kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
-  kb.box[0] = 64; kb.box[1] = (uint32_t)p.n_umma; kb.box[2] = 1;
+  kb.box[0] = 64; kb.box[1] = (uint32_t)(pair ? p.n_umma / 2 : p.n_umma); kb.box[2] = 1;
   kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
   if (int e = get_tensor_map(kb, &tmB)) return e;
 
@@ -367,12 +403,30 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "conv_tc2: smem request %zu too large", smem);
-  dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)n_tiles);
-  conv3d_tc2_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p, dst, ep);
+  const unsigned tiles = (unsigned)(p.N * p.tiles_x * p.tiles_y);
+  if (!pair) {
+    dim3 grid(tiles, (unsigned)n_tiles);
+    conv3d_tc2_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, p, dst, ep);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2, 1, 1);  // pairs of adjacent tiles; an odd tail gets a padding CTA
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc2_kernel<true>, tmA, tmB, p, dst, ep));
+  }
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -131,7 +131,11 @@ class Generator_3D(nn.Module, lc.GlobalLoggingClass):
         feat = ops.CatFn.apply(a, t, buf)
         scale = self.hr_convs[1].sample(n, F + T, x.device)
         feat = self.hr_convs[0](feat, chan_scale=scale)
-        return self.hr_convs[2].run(feat, out_dtype=torch.float32, out_contig=True)
+        last = self.hr_convs[2]
+        if (ops.get_precision() == "bf16" and last.stride == (1, 1, 1) and last.kernel_size[0] * last.out_channels <= 16
+                and last.in_channels >= 16 and feat.dtype == torch.bfloat16):
+            return ops.XFoldConvFn.apply(feat, last.weight, last.bias, last.padding)
+        return last.run(feat, out_dtype=torch.float32, out_contig=True)
 
 
 def _copy_into(src, dst):

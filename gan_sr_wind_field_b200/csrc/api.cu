@@ -63,6 +63,8 @@ int bn_bwd_reduce_launch(const View&, const View&, const View&, const float*, co
 int bn_bwd_apply_launch(const View&, const View&, const View&, const float*, const float*, const float*,
                         const float*, const float*, float, long long, const View&, int, int, long long,
                         cudaStream_t);
+int xfold_sum_launch(const View&, const float*, const View&, int, int, int, int, int, int, int, cudaStream_t);
+int xunfold_launch(const View&, const View&, int, int, int, int, int, int, int, int, cudaStream_t);
 int axis_coeffs_launch(const float*, int, float*, cudaStream_t);
 int wind_gradient_launch(const View&, const View&, const float*, const float*, const View&, int, int, int, int,
                          cudaStream_t);
@@ -288,6 +290,17 @@ int ws_upsample_nearest_xy_bwd(const ws_tensor* dout, const ws_tensor* din, int 
                                void* stream) {
   WS_REQUIRE(dout && dout->ptr && din && din->ptr, "ws_upsample_nearest_xy_bwd: null pointer");
   return upsample_bwd_launch(View(dout), View(din), n, c, x, y, z, (cudaStream_t)stream);
+}
+
+int ws_xfold_sum(const ws_tensor* y, const float* bias, const ws_tensor* out, int n, int co, int kx, int pad,
+                 int x, int yy, int z, void* stream) {
+  WS_REQUIRE(y && y->ptr && out && out->ptr && co > 0 && kx > 0, "ws_xfold_sum: bad arguments");
+  return xfold_sum_launch(View(y), bias, View(out), n, co, kx, pad, x, yy, z, (cudaStream_t)stream);
+}
+int ws_xunfold(const ws_tensor* dout, const ws_tensor* u, int n, int co, int kx, int pad, int cpad, int x, int yy,
+               int z, void* stream) {
+  WS_REQUIRE(dout && dout->ptr && u && u->ptr && cpad >= kx * co, "ws_xunfold: bad arguments");
+  return xunfold_launch(View(dout), View(u), n, co, kx, pad, cpad, x, yy, z, (cudaStream_t)stream);
 }
 
 int ws_copy(const ws_tensor* src, const ws_tensor* dst, int n, int c, int64_t v, void* stream) {

@@ -266,6 +266,48 @@ __global__ void upsample_bwd_generic(View dout, View din, int n, int c, int x, i
   }
 }
 
+// ---- x-fold (narrow-output conv, see windsr.h) -----------------------------------------------------------
+__global__ void xfold_sum_kernel(View y, const float* __restrict__ bias, View out, int n, int co, int kx, int pad,
+                                 int X, int Y, int Z) {
+  const long long V = (long long)X * Y * Z;
+  const long long total = (long long)n * co * V;
+  const long long sx = (long long)Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % V;
+    const int c = (int)((i / V) % co);
+    const int nn = (int)(i / (V * co));
+    const int xx = (int)(v / sx);
+    float acc = bias ? bias[c] : 0.f;
+    for (int dx = 0; dx < kx; ++dx) {
+      const int xs = xx + dx - pad;
+      if (xs >= 0 && xs < X) acc += y.ld(nn, dx * co + c, v + (long long)(dx - pad) * sx);
+    }
+    out.st(nn, c, v, acc);
+  }
+}
+
+__global__ void xunfold_kernel(View dout, View u, int n, int co, int kx, int pad, int cpad, int X, int Y, int Z) {
+  const long long V = (long long)X * Y * Z;
+  const long long total = (long long)n * V * cpad;
+  const long long sx = (long long)Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cpad);
+    const long long r = i / cpad;
+    const long long v = r % V;
+    const int nn = (int)(r / V);
+    float val = 0.f;
+    if (ch < kx * co) {
+      const int dx = ch / co, c = ch % co;
+      const int xx = (int)(v / sx);
+      const int xs = xx - dx + pad;
+      if (xs >= 0 && xs < X) val = dout.ld(nn, c, v + (long long)(pad - dx) * sx);
+    }
+    u.st(nn, ch, v, val);
+  }
+}
+
 // ---- BatchNorm --------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const float* sum, const float* sqsum, long long count, int c,
                                    const float* gamma, const float* beta, float eps, float momentum,
@@ -485,6 +527,24 @@ int upsample_bwd_launch(const View& dout, const View& din, int n, int c, int x, 
   long long total = (long long)n * c * x * y * z;
   if (total <= 0) return 0;
   upsample_bwd_generic<<<grid_for(total), kBlock, 0, st>>>(dout, din, n, c, x, y, z, c_fastest_of(din));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+int xfold_sum_launch(const View& y, const float* bias, const View& out, int n, int co, int kx, int pad, int X,
+                     int Y, int Z, cudaStream_t st) {
+  long long total = (long long)n * co * X * Y * Z;
+  if (total <= 0) return 0;
+  xfold_sum_kernel<<<grid_for(total), kBlock, 0, st>>>(y, bias, out, n, co, kx, pad, X, Y, Z);
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+int xunfold_launch(const View& dout, const View& u, int n, int co, int kx, int pad, int cpad, int X, int Y, int Z,
+                   cudaStream_t st) {
+  long long total = (long long)n * cpad * X * Y * Z;
+  if (total <= 0) return 0;
+  xunfold_kernel<<<grid_for(total), kBlock, 0, st>>>(dout, u, n, co, kx, pad, cpad, X, Y, Z);
   WS_POST_LAUNCH(1);
   return 0;
 }

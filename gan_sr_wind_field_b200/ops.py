@@ -397,6 +397,61 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, db, dres, None
 
 
+class XFoldConvFn(torch.autograd.Function):
+    """Stride-1 conv with a very narrow output (kx * cout <= 16: hr_convs.2, 144 -> 3, Generator…py:105-110) with
+    the kx taps along x folded into the output-channel dimension (windsr.h "x-fold helpers"): one (1,ky,kz) conv
+    with kx*cout (-> 16) channels on the tensor cores + a shifted sum; 5x fewer MMAs than the direct form, whose
+    N = 16 MMAs cost as much as N = 144 ones.  Output: contiguous NCXYZ fp32 (the generator's result)."""
+
+    @staticmethod
+    def _folded_weight(weight):
+        co, ci, kx, ky, kz = weight.shape
+        w5 = weight.detach().permute(2, 0, 1, 3, 4).reshape(kx * co, ci, 1, ky, kz)
+        if kx * co < 16:
+            w5 = torch.cat((w5, w5.new_zeros((16 - kx * co, ci, 1, ky, kz))), 0)
+        return w5.contiguous()
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, padding):
+        lib = load()
+        co, ci, kx, ky, kz = weight.shape
+        px, py, pz = padding
+        n, _, X, Y, Z = x.shape
+        w5 = XFoldConvFn._folded_weight(weight)
+        shape = make_shape(x.shape, 16, (1, ky, kz), 1, (0, py, pz))
+        ybuf = empty_cl(n, 16, X, Y, Z, torch.float32, x.device)
+        conv_fwd(x, w5, None, shape, ybuf)
+        out = torch.empty((n, co, X, Y, Z), dtype=torch.float32, device=x.device)
+        yv, ov = view(ybuf), view(out)
+        check(lib.ws_xfold_sum(C.byref(yv), ptr(bias.detach() if bias is not None else None), C.byref(ov), n, co, kx,
+                               px, X, Y, Z, stream_ptr()), "ws_xfold_sum")
+        ctx.save_for_backward(x, w5)
+        ctx.meta = (tuple(weight.shape), shape, px, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load()
+        x, w5 = ctx.saved_tensors
+        (co, ci, kx, ky, kz), shape, px, has_bias = ctx.meta
+        n, _, X, Y, Z = x.shape
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dout = dout.contiguous() if not _linear_voxels(dout) else dout
+        u = empty_cl(n, 16, X, Y, Z, act_dtype(), x.device)
+        dv, uv = view(dout), view(u)
+        check(lib.ws_xunfold(C.byref(dv), C.byref(uv), n, co, kx, px, 16, X, Y, Z, stream_ptr()), "ws_xunfold")
+        dx = dw = db = None
+        if need_w:
+            dw5, _ = conv_wgrad(x, u, shape)
+            dw = dw5[:kx * co].reshape(kx, co, ci, ky, kz).permute(1, 2, 0, 3, 4).contiguous()
+        if need_b and has_bias:
+            db = dout.sum((0, 2, 3, 4))
+        if need_x:
+            dx = empty_cl(*x.shape, act_dtype(), x.device)
+            conv_dgrad(u, w5, None, shape, dx)
+        return dx, dw, db, None
+
+
 def _linear_voxels(t: torch.Tensor) -> bool:
     try:
         view(t)

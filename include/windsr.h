@@ -173,6 +173,17 @@ int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n,
 int ws_upsample_nearest_xy_bwd(const ws_tensor* dout, const ws_tensor* din, int n, int c, int x, int y, int z,
                                void* stream);
 
+/* ---- x-fold helpers for very narrow outputs (hr_convs.2: 144 -> 3, Generator…py:105-110) ----------------
+ * A tcgen05 MMA costs the same for N = 16 as for N = 144, so a Cout = 3 conv wastes the tensor pipe.  Folding the
+ * kx taps along x into the output-channel dimension — Y[x', (dx,co)] = sum_{dy,dz,ci} W[co,ci,dx,dy,dz] *
+ * in[x', y+dy, z+dz, ci], out[x, co] = bias[co] + sum_dx Y[x + dx - pad, (dx,co)] — turns the 5x5x5 conv into a
+ * 1x5x5 conv with 15 (->16) output channels (5x fewer MMAs) plus this shifted sum; the same unfolding of the
+ * output gradient, U[x', (dx,co)] = dout[x' - dx + pad, co], serves dgrad and wgrad. */
+int ws_xfold_sum(const ws_tensor* y, const float* bias, const ws_tensor* out, int n, int co, int kx, int pad,
+                 int x, int yy, int z, void* stream);
+int ws_xunfold(const ws_tensor* dout, const ws_tensor* u, int n, int co, int kx, int pad, int cpad, int x, int yy,
+               int z, void* stream);
+
 /* ---- elementwise helpers -------------------------------------------------------------------------- */
 /* dst(n,c,v) = src(n,c,v) with dtype/layout conversion (the torch.cat / clone / layout changes of
  * torch_blocks.py:214,286 and Generator…py:228 expressed as strided copies) */

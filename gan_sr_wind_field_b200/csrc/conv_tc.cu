@@ -174,12 +174,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::tc_fence_after();
 
     const EpiVec ev = make_epi_vec(dst, ep);
+    const bool simple = epi_is_simple(ep);
     for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
       if (n0 + c0 >= p.cn) break;  // warp-uniform
       uint32_t r[16];
       ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
-      epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r, lane);
+      if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r);
+      else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r, lane);
     }
     ptx::tc_fence_before();
   }

@@ -203,6 +203,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
     const EpiVec ev = make_epi_vec(dst, ep);
+    const bool simple = epi_is_simple(ep);
     for (int m = 0; m < p.t_m; ++m) {
       const int r = m * 128 + sub * 32 + lane;  // row inside the CTA's output region
       const int rx = r / p.slabrows;
@@ -216,7 +217,8 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t rr[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
         ptx::tmem_ld_wait();
-        epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
+        if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr);
+        else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
       }
     }
     ptx::tc_fence_before();

@@ -84,6 +84,51 @@ __device__ __forceinline__ void store16(const View& t, bool vec, int n, int c0, 
   }
 }
 
+// Fast path (warp-uniform choice): no per-channel scale / dropout scale / mask / statistics — the epilogues of the
+// RDB dense convs, their dgrads (fp32 accumulate), LFF (+bias, two residuals) and the HR convs.  The generic
+// version below spends most of its issue slots on predicated-off per-element branches (ncu: the dense-conv dgrad
+// was ~80 % epilogue); this one is ~6 instructions per element.
+__device__ __forceinline__ bool epi_is_simple(const Epi& ep) { return !ep.mask.ptr && !ep.stat_sum; }
+
+__device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& ev, const View& dst, int n,
+                                                  long long v, int cbase, int cn, bool row_ok,
+                                                  const uint32_t (&rr)[16]) {
+  if (!row_ok) return;
+  float y[16];
+  const float slope = ep.lrelu_slope, alpha = ep.alpha;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(rr[j]);
+  if (ep.oscale) {  // eval-mode BatchNorm scale (uniform branch; the loads are warp-wide broadcasts)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] *= (cbase + j < cn ? ep.oscale[cbase + j] : 0.f);
+  }
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] += (cbase + j < cn ? ep.bias[cbase + j] : 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) y[j] = alpha * (y[j] > 0.f ? y[j] : slope * y[j]);
+  if (ep.chan_scale) {  // Dropout3d channel scale; alpha commutes with it
+    const float* cs = ep.chan_scale + (long long)n * ep.cout + cbase;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] *= (cbase + j < cn ? cs[j] : 0.f);
+  }
+  if (ep.res1.ptr) {
+    float r[16];
+    load16(ep.res1, ev.res1, n, cbase, v, cn, r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta1, r[j], y[j]);
+  }
+  if (ep.res2.ptr) {
+    float r[16];
+    load16(ep.res2, ev.res2, n, cbase, v, cn, r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta2, r[j], y[j]);
+  }
+  store16(dst, ev.dst, n, cbase, v, cn, y);
+  if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
+}
+
 // One 16-column chunk of fp32 accumulators `rr` (tcgen05.ld 32x32b.x16) for accumulator row = voxel (n, v).
 // Must be called by all 32 lanes (the BN-statistics reduction is warp-wide); stores are predicated on row_ok.
 __device__ __forceinline__ void epilogue16(const Epi& ep, const EpiVec& ev, const View& dst, int n, long long v,

@@ -383,7 +383,30 @@ class ConvFn(torch.autograd.Function):
             copy_(g, gp[:, :shape.cout])
             g = gp
             shape = make_shape(x.shape, pad_cout, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
-        if need_w or (need_b and ctx.has_bias):
+        rem = shape.cout % 128
+        if (need_w and not pad_cout and cdt == torch.bfloat16 and shape.cout > 128 and 0 < rem <= 32
+                and rem * shape.kx <= 128 and (rem * shape.kx) % 8 == 0 and shape.kx > 1
+                and (shape.sx, shape.sy, shape.sz) == (1, 1, 1) and x.dtype == torch.bfloat16
+                and g.dtype == torch.bfloat16):
+            # Cout = 128*q + rem (hr_convs.0: 144 = 128 + 16): a second 128-row M tile for `rem` rows would cost as
+            # much as the first.  Instead fold the kx taps of the remainder channels into the channel dimension
+            # (U[x', (dx,co)] = g[x' - dx + px, co], windsr.h "x-fold helpers"): one (1,ky,kz) wgrad with kx*rem
+            # rows — kx times fewer MMAs for the remainder.
+            main = shape.cout - rem
+            s_main = make_shape(x.shape, main, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
+            dw_main, _ = conv_wgrad(x, g[:, :main], s_main)
+            cu = rem * shape.kx
+            u = empty_cl(g.shape[0], cu, *g.shape[2:], cdt, g.device)
+            gv, uv = view(g[:, main:]), view(u)
+            check(load().ws_xunfold(C.byref(gv), C.byref(uv), g.shape[0], rem, shape.kx, shape.px, cu, g.shape[2],
+                                    g.shape[3], g.shape[4], stream_ptr()), "ws_xunfold")
+            s_rem = make_shape(x.shape, cu, (1, shape.ky, shape.kz), 1, (0, shape.py, shape.pz))
+            dw_u, _ = conv_wgrad(x, u, s_rem)
+            dw_rem = dw_u.reshape(shape.kx, rem, shape.cin, shape.ky, shape.kz).permute(1, 2, 0, 3, 4)
+            dw = torch.cat((dw_main, dw_rem), 0)
+            if need_b and ctx.has_bias:
+                db = g.float().sum((0, 2, 3, 4))
+        elif need_w or (need_b and ctx.has_bias):
             dw, db = conv_wgrad(x, g, shape, want_bias=ctx.has_bias and need_b, want_weight=need_w)
             if pad_cout:
                 dw = dw[:weight.shape[0]].contiguous() if dw is not None else None

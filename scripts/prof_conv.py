@@ -9,7 +9,9 @@ from gan_sr_wind_field_b200 import ops
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 layer = sys.argv[2] if len(sys.argv) > 2 else "g7"
 cfgs = {"g7": (8, 144, 144, (128, 128, 10), 5, 2), "g5": (8, 128, 128, (128, 128, 10), 3, 1),
-        "rdb": (8, 224, 32, (16, 16, 10), 3, 1), "g8": (8, 144, 3, (128, 128, 10), 5, 2)}
+        "rdb": (8, 224, 32, (16, 16, 10), 3, 1), "g8": (8, 144, 3, (128, 128, 10), 5, 2),
+        "dg": (8, 32, 224, (16, 16, 10), 3, 1), "lff": (8, 256, 128, (16, 16, 10), 1, 0),
+        "rdb0": (8, 128, 32, (16, 16, 10), 3, 1)}
 n, cin, cout, vol, k, p = cfgs[layer]
 ops.set_precision("bf16")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -17,14 +19,16 @@ x = ops.empty_cl(n, cin, *vol, torch.bfloat16, "cuda")
 x.copy_(torch.randn(n, cin, *vol, generator=g, device="cuda"))
 w = torch.randn(cout, cin, k, k, k, generator=g, device="cuda") / (cin * k ** 3) ** 0.5
 shape = ops.make_shape(x.shape, cout, (k, k, k), 1, p)
-y = ops.empty_cl(n, cout, *vol, torch.bfloat16, "cuda")
+acc = layer == "dg"   # dense-conv dgrad look-alike: fp32 output accumulated in place
+y = ops.zeros_cl(n, cout, *vol, torch.float32 if acc else torch.bfloat16, "cuda")
 cache = ops.PackedWeights()
-ops.conv_fwd(x, w, cache, shape, y, slope=0.2)
+kw = dict(res1=y, beta1=1.0) if acc else dict(slope=0.2)
+ops.conv_fwd(x, w, cache, shape, y, **kw)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    ops.conv_fwd(x, w, cache, shape, y, slope=0.2)
+    ops.conv_fwd(x, w, cache, shape, y, **kw)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps

@@ -19,6 +19,7 @@ is executed:
 from __future__ import annotations
 
 import copy
+import os
 import math
 
 import torch
@@ -41,6 +42,12 @@ def _zero():
     return torch.zeros(1)
 
 
+def _set_mode(module, training: bool):
+    """module.train()/.eval() walks every sub-module (~1000 here): skip it when the mode already matches."""
+    if module.training != training:
+        module.train(training)
+
+
 class wind_field_GAN_3D(BaseGAN):
     def __init__(self, cfg):
         super().__init__(cfg)
@@ -59,6 +66,7 @@ class wind_field_GAN_3D(BaseGAN):
         self.max_diff_squared = torch.tensor(4.0, device=self.device)  # HR is in [-1, 1]
         self.epsilon_PSNR = torch.tensor(1e-8, device=self.device)
         self.feature_extractor = None
+        self._D_requires_grad = None  # cached state of the D.parameters() requires_grad toggle
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
 
@@ -93,9 +101,14 @@ class wind_field_GAN_3D(BaseGAN):
         initialization.init_weights(self.D, scale=d.weight_init_scale)
 
         t = cfg.training
-        self.optimizer_G = torch.optim.Adam(self.G.parameters(), lr=t.learning_rate_g,
+        # Same Adam as wind_field_GAN_3D.py:147-160; on a GPU the single-kernel ("fused") implementation is used:
+        # it takes a device-side ``found_inf`` flag, which is how the reference's "skip the step when the loss is
+        # not finite" guard (:457) runs without a host read.
+        fused = self.device.type == "cuda" and os.environ.get("WINDSR_FUSED_ADAM", "1") != "0"
+        self._fused_adam = fused
+        self.optimizer_G = torch.optim.Adam(self.G.parameters(), lr=t.learning_rate_g, fused=fused,
                                             weight_decay=t.adam_weight_decay_g, betas=(t.adam_beta1_g, 0.999))
-        self.optimizer_D = torch.optim.Adam(self.D.parameters(), lr=t.learning_rate_d,
+        self.optimizer_D = torch.optim.Adam(self.D.parameters(), lr=t.learning_rate_d, fused=fused,
                                             weight_decay=t.adam_weight_decay_d, betas=(t.adam_beta1_d, 0.999))
         self.optimizers += [self.optimizer_G, self.optimizer_D]
         if t.multistep_lr_steps:
@@ -137,11 +150,11 @@ class wind_field_GAN_3D(BaseGAN):
         steps; eval mode (BN running stats, no dropout) + sigma 2 noise, real branch detached, in G steps."""
         noisy = self.cfg.training.use_instance_noise
         if train_D:
-            self.D.train()
+            _set_mode(self.D, True)
             y_pred = self.D(HR + self._noise(1.0, HR.size(), it) if noisy else HR).squeeze()
             fake_in = fake_HR.detach()
             return y_pred, self.D(fake_in + self._noise(1.0, HR.size(), it) if noisy else fake_in).squeeze()
-        self.D.eval()
+        _set_mode(self.D, False)
         with torch.no_grad():
             y_pred = self.D(HR + self._noise(2.0, HR.size(), it) if noisy else HR).squeeze()
         return y_pred, self.D(fake_HR + self._noise(2.0, HR.size(), it) if noisy else fake_HR).squeeze()
@@ -195,18 +208,21 @@ class wind_field_GAN_3D(BaseGAN):
         physics = xy + zg + div + dxy
         # The reference's guards (:434-443 and :457): drop the physics terms when any of them is NaN/Inf, and skip
         # the optimiser step when the total is NaN/Inf.  The first is decided ON THE DEVICE (select, with
-        # WindLossFn.backward discarding the 0*inf cotangents of the dropped branch); the second needs the host,
-        # but is read only after backward has been enqueued, so the single host sync of the step overlaps nothing.
+        # WindLossFn.backward discarding the 0*inf cotangents of the dropped branch); the second is handed to the
+        # fused Adam kernel as its ``found_inf`` flag, so a training step has no host synchronisation at all.
         ok_physics = torch.isfinite(physics).all()
         loss_G = base + torch.where(ok_physics, physics, torch.zeros_like(physics))
-        ok_total = torch.isfinite(base).all()
         if training_iteration:
             if self.sync_G is not None:
                 self.sync_G.begin()
             loss_G.backward()
             if self.sync_G is not None:
                 self.sync_G.finish()
-            if bool(ok_total):  # loss_G is finite
+            not_finite = ~torch.isfinite(loss_G.detach()).reshape(())
+            if self._fused_adam:
+                self.optimizer_G.found_inf = not_finite.to(torch.float32)
+                self.optimizer_G.step()  # a no-op on the device when loss_G is not finite
+            elif not bool(not_finite):
                 self.optimizer_G.step()
         d = self.train_G_loss_dict if training_iteration else self.validation_G_loss_dict
         d.update(total=loss_G, adversarial=adv, pix=pix, xy_gradient=xy, z_gradient=zg, divergence=div,
@@ -218,15 +234,17 @@ class wind_field_GAN_3D(BaseGAN):
 
     def update_G(self, LR, HR, Z, it, training_iteration: bool):
         if training_iteration:
-            self.G.train()
+            _set_mode(self.G, True)
             fake_HR = self.G(LR, Z)
-            for p in self.D.parameters():
-                p.requires_grad = False
+            if self._D_requires_grad is not False:
+                for p in self.D.parameters():
+                    p.requires_grad = False
+                self._D_requires_grad = False
             self.G.zero_grad(set_to_none=True)
             y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
             self.calculate_optimize_and_log_G_loss(HR, fake_HR, Z, y_pred, fake_y_pred, True)
         else:
-            self.G.eval()
+            _set_mode(self.G, False)
             with torch.no_grad():
                 fake_HR = self.G(LR, Z)
                 y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
@@ -235,8 +253,10 @@ class wind_field_GAN_3D(BaseGAN):
 
     def update_D(self, HR, fake_HR, it, training_epoch: bool):
         if training_epoch:
-            for p in self.D.parameters():
-                p.requires_grad = True
+            if self._D_requires_grad is not True:
+                for p in self.D.parameters():
+                    p.requires_grad = True
+                self._D_requires_grad = True
             self.optimizer_D.zero_grad(set_to_none=True)
             y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=True)
         else:
@@ -278,7 +298,7 @@ class wind_field_GAN_3D(BaseGAN):
                 self.update_G(LR, HR, Z, it_dev, True)
             else:
                 with torch.no_grad():
-                    self.G.eval()
+                    _set_mode(self.G, False)
                     fake_HR = self.G(LR, Z)
                 self.update_D(HR, fake_HR, it_dev, True)
             return

@@ -119,7 +119,11 @@ def check(status: int, what: str):
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on the current device (fast path: no Stream object)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:  # pragma: no cover - older torch
+        return torch.cuda.current_stream().cuda_stream
 
 
 def _dtype_code(t: torch.Tensor) -> int:

@@ -258,7 +258,7 @@ int get_tensor_map_impl(const MapKey& key, CUtensorMap* out) {
 }
 
 // choose (bz, by, bx), bz*by*bx <= 128, maximising useful rows per 128-row MMA tile
-void choose_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+void choose_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
   double best = -1.0;
   bx = by = bz = 1;
   for (int z = 1; z <= DZ && z <= 128; ++z) {
@@ -278,6 +278,22 @@ void choose_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& b
       }
     }
   }
+}
+
+void choose_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+  struct Hit { int bx, by, bz; };
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, Hit> memo;
+  unsigned long long key = 1469598103934665603ull;
+  for (int v : {DX, DY, DZ, sx, sy, sz}) key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) { bx = it->second.bx; by = it->second.by; bz = it->second.bz; return; }
+  }
+  choose_tile_search(DX, DY, DZ, sx, sy, sz, bx, by, bz);
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = Hit{bx, by, bz};
 }
 
 }  // namespace

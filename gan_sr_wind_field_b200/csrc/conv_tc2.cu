@@ -17,6 +17,7 @@
 // Generator_3D_Resnet_ESRGAN.py:95-111 (hr_convs).
 #include <cuda.h>
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -236,7 +237,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int kSmemBudget = 225 * 1024;
 
 // Pick (by, tx): minimise estimated SM-time = waves * max(MMA cycles, L2->SMEM cycles) per K iteration.
-bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
+bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
   const int tmax = 512 / n_umma < 4 ? 512 / n_umma : 4;
   if (tmax < 1 || DZ > 128) return false;
   double best = 1e30;
@@ -295,6 +296,32 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc
     }
   }
   return found;
+}
+
+// The search above costs ~10 us of host time; the trunk launches ~500 convs per step, so memoise it per geometry.
+bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
+  struct Hit { bool ok; int by, tx, t_m, slabrows, halo_rows, a_buf_bytes, w_bytes, a_bufs; };
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, Hit> memo;
+  unsigned long long key = 1469598103934665603ull;
+  for (long long v : {(long long)N, (long long)DX, (long long)DY, (long long)DZ, (long long)kx, (long long)n_umma,
+                      (long long)pair})
+    key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) {
+      const Hit& h = it->second;
+      p.by = h.by; p.tx = h.tx; p.t_m = h.t_m; p.slabrows = h.slabrows; p.halo_rows = h.halo_rows;
+      p.a_buf_bytes = h.a_buf_bytes; p.w_bytes = h.w_bytes; p.a_bufs = h.a_bufs;
+      return h.ok;
+    }
+  }
+  const bool ok = choose_cfg_search(N, DX, DY, DZ, kx, n_umma, pair, p);
+  Hit h = {ok, p.by, p.tx, p.t_m, p.slabrows, p.halo_rows, p.a_buf_bytes, p.w_bytes, p.a_bufs};
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = h;
+  return ok;
 }
 
 }  // namespace

@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include <mutex>
+#include <unordered_map>
 
 namespace ws {
 
@@ -220,7 +221,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   }
 }
 
-void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+void choose_wgrad_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
   double best = -1.0;
   bx = by = 1; bz = 16;
   for (int z = 1; z <= 128; ++z) {
@@ -241,6 +242,22 @@ void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, 
       }
     }
   }
+}
+
+void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+  struct Hit { int bx, by, bz; };
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, Hit> memo;
+  unsigned long long key = 1469598103934665603ull;
+  for (int v : {DX, DY, DZ, sx, sy, sz}) key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) { bx = it->second.bx; by = it->second.by; bz = it->second.bz; return; }
+  }
+  choose_wgrad_tile_search(DX, DY, DZ, sx, sy, sz, bx, by, bz);
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = Hit{bx, by, bz};
 }
 
 }  // namespace

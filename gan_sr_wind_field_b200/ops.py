@@ -94,9 +94,27 @@ def out_dims(s: WsConvShape) -> Tuple[int, int, int]:
 # ------------------------------------------------------------------------------------------------------
 # packed-weight cache (fp32 torch-layout Parameter -> kernel operand layout), keyed by parameter version
 # ------------------------------------------------------------------------------------------------------
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_WEIGHTS_EPOCH = 0
+
+
+def invalidate_packed_weights(*_args, **_kwargs) -> None:
+    """Force every packed-weight cache to repack on next use.  Called after EVERY optimizer step through torch's
+    global step hook: single-kernel ("fused") optimizers update parameters without bumping ``Tensor._version``,
+    so the version stamp alone would leave stale operand copies behind.  Call it by hand after writing weights
+    through a path torch does not see (raw pointers, ``.data`` aliases)."""
+    global _WEIGHTS_EPOCH
+    _WEIGHTS_EPOCH += 1
+
+
+_register_step_hook(invalidate_packed_weights)
+
+
 class PackedWeights:
     """Caches the packed copies of one weight Parameter; repacks when the parameter changes
-    (optimizer step / load_state_dict bump ``_version``; ``.to()`` changes ``data_ptr``)."""
+    (load_state_dict / in-place ops bump ``_version``; ``.to()`` changes ``data_ptr``; any optimizer step bumps
+    the module-wide epoch, see ``invalidate_packed_weights``)."""
 
     def __init__(self):
         self._cache = {}
@@ -105,7 +123,7 @@ class PackedWeights:
         """``pad_cout`` > w.shape[0]: pack as if the layer had that many output channels (extra filters zero) —
         lets the 3-channel hr_convs.2 run its dgrad / wgrad on the tensor-core kernels (UMMA needs K, N >= 16)."""
         key = (kind, pad_cout)
-        stamp = (w._version, w.data_ptr(), shape.cin, shape.cout)
+        stamp = (w._version, w.data_ptr(), shape.cin, shape.cout, _WEIGHTS_EPOCH)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -510,7 +528,7 @@ class RDBState:
             self.packed[dgrad] = [torch.empty(lib.ws_rdb_packed_bytes(C.byref(desc), i, dgrad), dtype=torch.uint8,
                                               device=params[0].device) for i in range(nconv + 1)]
             self.stamp[dgrad] = None
-        stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + (desc.math,)
+        stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + (desc.math, _WEIGHTS_EPOCH)
         repack = stamp != self.stamp[dgrad]
         self.stamp[dgrad] = stamp
         return self.packed[dgrad], int(repack)

@@ -19,6 +19,14 @@ gan.feed_xy_niter(x, y, torch.tensor(t.niter, device=dev), t.d_g_train_ratio, t.
 for i in range(3):
     gan.optimize_parameters(LR, HR, Z, 1 + i)
 torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for i in range(5):
+    gan.optimize_parameters(LR, HR, Z, 5 + i)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"host enqueue {1e3 * (t1 - t0) / 5:.1f} ms/step, wall {1e3 * (t2 - t0) / 5:.1f} ms/step (no profiler)")
 st0 = torch.cuda.memory_stats()
 pr = cProfile.Profile()
 pr.enable()

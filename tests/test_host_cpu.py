@@ -236,3 +236,15 @@ def test_grad_sync_world_size_2_gloo(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env))
     codes = [p.wait(timeout=180) for p in procs]
     assert codes == [0, 0], codes
+
+
+def test_optimizer_step_invalidates_packed_weights():
+    """Every optimizer step (fused ones do not bump Tensor._version) must advance the packed-weight epoch."""
+    from gan_sr_wind_field_b200 import ops
+    p = torch.nn.Parameter(torch.randn(4, 4))
+    p.grad = torch.randn(4, 4)
+    e0 = ops._WEIGHTS_EPOCH
+    torch.optim.Adam([p], fused=True).step()
+    assert ops._WEIGHTS_EPOCH == e0 + 1
+    torch.optim.SGD([p], lr=0.1).step()
+    assert ops._WEIGHTS_EPOCH == e0 + 2

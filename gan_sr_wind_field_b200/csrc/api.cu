@@ -47,6 +47,9 @@ int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&,
 bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
+int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
+                 cudaStream_t);
+size_t tc_rdb_wgrad_workspace_bytes(int, int, int, int);
 int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
 int copy_launch(const View&, const View&, int, int, long long, cudaStream_t);
 int axpby_launch(const View&, float, const View&, float, const View&, int, int, long long, cudaStream_t);
@@ -415,6 +418,36 @@ ws_epilogue plain_epilogue() {
 }
 }  // namespace
 
+namespace {
+// Pseudo conv of the merged dense-conv weight gradient: M = buffer channels read by the widest dense conv,
+// N = all nconv*gc gradient channels (wgrad_tc.cu, tc_rdb_wgrad).
+ws_conv_shape rdb_merged_shape(const ws_rdb_desc* d) {
+  ws_conv_shape s = {d->n, d->x, d->y, d->z, d->f + (d->nconv - 1) * d->gc, d->nconv * d->gc, d->k, d->k, d->k, 1, 1,
+                     1, (d->k - 1) / 2, (d->k - 1) / 2, (d->k - 1) / 2};
+  return s;
+}
+bool rdb_merged_wgrad_ok(const ws_rdb_desc* d, const ws_tensor* buf, const ws_tensor* gbuf) {
+  if (d->nconv < 2 || d->nconv * d->gc > 256 || d->gc % 16 != 0 || getenv("WS_DISABLE_RDB_MERGED_WGRAD")) return false;
+  ws_conv_shape s = rdb_merged_shape(d);
+  return wgrad_path(ConvGeom(s), View(buf), View(gbuf), d->math) == WS_PATH_TCGEN05;
+}
+}  // namespace
+
+extern "C" size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d) {
+  RdbGeom r;
+  if (!d || rdb_geom(d, r)) return 0;
+  size_t need = 0;
+  for (int i = 0; i <= d->nconv; ++i) {
+    size_t b = ws_conv3d_wgrad_workspace_bytes(i < d->nconv ? &r.dense[i] : &r.lff, d->math);
+    if (b > need) need = b;
+  }
+  if (d->nconv >= 2 && d->math == WS_MATH_BF16) {
+    size_t b = tc_rdb_wgrad_workspace_bytes(d->k * d->k * d->k, d->f + (d->nconv - 1) * d->gc, d->nconv, d->gc);
+    if (b > need) need = b;
+  }
+  return need;
+}
+
 extern "C" size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int i, int dgrad) {
   RdbGeom r;
   if (!d || rdb_geom(d, r) || i < 0 || i > d->nconv) return 0;
@@ -480,6 +513,9 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   if (int e = axpby_launch(View(dy), d->alpha, View((const ws_tensor*)nullptr), 0.f, View(g_lff), d->n, d->f, v, st))
     return e;
   const bool want_w = dw != nullptr;
+  // gbuf holds the gradients of ALL dense conv outputs side by side (n, nconv*gc, ..): the dgrad chain consumes
+  // slice i as it goes, the weight gradients of the dense convs are then one merged GEMM at the end.
+  const bool merged = want_w && rdb_merged_wgrad_ok(d, buf, gbuf);
   if (want_w && (dw[d->nconv] || db_lff)) {
     if (int e = ws_conv3d_wgrad(&r.lff, buf, g_lff, dw[d->nconv], db_lff, 0, d->math, workspace, workspace_bytes,
                                 stream))
@@ -498,21 +534,30 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   for (int i = d->nconv - 1; i >= 0; --i) {
     const ws_conv_shape* s = &r.dense[i];
     ConvGeom g(*s);
-    ws_tensor dslice = slice(*dbuf, s->cin), yslice = slice(*buf, s->cin);
-    // g = dbuf[:, cin:cin+gc] * lrelu'(buf[:, cin:cin+gc])
-    if (int e = lrelu_bwd_launch(View(&dslice), View(&yslice), d->slope, nullptr, nullptr, View(gbuf), d->n, d->gc,
+    ws_tensor dslice = slice(*dbuf, s->cin), yslice = slice(*buf, s->cin), gslice = slice(*gbuf, i * d->gc);
+    const ws_tensor* gi = &gslice;
+    // g_i = dbuf[:, cin:cin+gc] * lrelu'(buf[:, cin:cin+gc])
+    if (int e = lrelu_bwd_launch(View(&dslice), View(&yslice), d->slope, nullptr, nullptr, View(gi), d->n, d->gc,
                                  v, st))
       return e;
-    if (want_w && dw[i]) {
-      if (int e = ws_conv3d_wgrad(s, buf, gbuf, dw[i], nullptr, 0, d->math, workspace, workspace_bytes, stream))
+    if (want_w && dw[i] && !merged) {
+      if (int e = ws_conv3d_wgrad(s, buf, gi, dw[i], nullptr, 0, d->math, workspace, workspace_bytes, stream))
         return e;
     }
-    const bool tc = dgrad_path(g, View(gbuf), d->math) == WS_PATH_TCGEN05;
+    const bool tc = dgrad_path(g, View(gi), d->math) == WS_PATH_TCGEN05;
     if (d->repack)
       if (int e = pack_weights_launch(w[i], g, tc ? WS_PACK_TC_DGRAD : WS_PACK_SIMT_DGRAD, packed[i], st)) return e;
     ws_epilogue ep = plain_epilogue();
     ep.res1 = *dbuf; ep.beta1 = 1.f;  // accumulate into dbuf[:, :cin]
-    if (int e = ws_conv3d_dgrad(s, gbuf, packed[i], dbuf, &ep, d->math, stream)) return e;
+    if (int e = ws_conv3d_dgrad(s, gi, packed[i], dbuf, &ep, d->math, stream)) return e;
+  }
+  if (merged) {
+    ws_conv_shape ms = rdb_merged_shape(d);
+    int cin[WS_RDB_MAX_CONVS];
+    for (int i = 0; i < d->nconv; ++i) cin[i] = r.dense[i].cin;
+    if (int e = tc_rdb_wgrad(ConvGeom(ms), View(buf), View(gbuf), dw, cin, d->nconv, d->gc, workspace,
+                             workspace_bytes, st))
+      return e;
   }
   if (dx && dx->ptr) {
     if (int e = axpby_launch(View(dbuf), 1.f, View(dy), d->beta1, View(dx), d->n, d->f, v, st)) return e;

@@ -120,6 +120,82 @@ __global__ void copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict
   }
 }
 
+// ---- 8-channel vector helpers for the channels-last elementwise fast paths -------------------------------------
+__device__ __forceinline__ void ld8(const View& t, long long o, float (&f)[8]) {
+  if (t.dtype == WS_F32) {
+    const float4 a = *reinterpret_cast<const float4*>((const float*)t.ptr + o);
+    const float4 b = *reinterpret_cast<const float4*>((const float*)t.ptr + o + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 r = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)t.ptr + o);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f[2 * j] = __uint_as_float(w[j] << 16);
+      f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ void st8(const View& t, long long o, const float (&f)[8]) {
+  if (t.dtype == WS_F32) {
+    *reinterpret_cast<float4*>((float*)t.ptr + o) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>((float*)t.ptr + o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>((__nv_bfloat16*)t.ptr + o) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// host: can `t` be addressed as 8-channel vectors (channels contiguous, every row start 16/32-byte aligned)?
+inline bool vec8_ok(const View& t, int c) {
+  if (!t.ptr) return true;
+  const int al = t.dtype == WS_F32 ? 4 : 8;  // elements per 16 bytes
+  return t.cs == 1 && c % 8 == 0 && t.vs % al == 0 && t.ns % al == 0 && ((uintptr_t)t.ptr % 16) == 0;
+}
+
+// y = a*x1 (+ b*x2), all channels-last, 8 channels per thread
+__global__ void axpby_cl8_kernel(View x1, float a, View x2, float b, View y, int c8, long long v, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % c8);
+    const long long r = i / c8;
+    const long long vv = r % v;
+    const int nn = (int)(r / v);
+    float f[8];
+    ld8(x1, x1.off(nn, q * 8, vv), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= a;
+    if (x2.ptr) {
+      float h[8];
+      ld8(x2, x2.off(nn, q * 8, vv), h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += b * h[j];
+    }
+    st8(y, y.off(nn, q * 8, vv), f);
+  }
+}
+
+// g = dy * lrelu'(y), all channels-last, 8 channels per thread (no per-channel scales)
+__global__ void lrelu_bwd_cl8_kernel(View dy, View yv, float slope, View g, int c8, long long v, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % c8);
+    const long long r = i / c8;
+    const long long vv = r % v;
+    const int nn = (int)(r / v);
+    float d[8], o[8];
+    ld8(dy, dy.off(nn, q * 8, vv), d);
+    ld8(yv, yv.off(nn, q * 8, vv), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : slope * d[j];
+    st8(g, g.off(nn, q * 8, vv), d);
+  }
+}
+
 __global__ void axpby_kernel(View x1, float a, View x2, float b, View y, int n, int c, long long v,
                              int c_fastest) {
   long long total = (long long)n * c * v;
@@ -476,6 +552,9 @@ int copy_launch(const View& src, const View& dst, int n, int c, long long v, cud
     int vpr = c / per;
     copy_vec_kernel<<<grid_for(rows * vpr), kBlock, 0, st>>>((const uint4*)src.ptr, (uint4*)dst.ptr, rows, vpr,
                                                             src.vs / per, dst.vs / per);
+  } else if (vec8_ok(src, c) && vec8_ok(dst, c)) {
+    // channels-last both sides, converting dtype: the 8-channel axpby kernel with a = 1 (exact)
+    axpby_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(src, 1.f, View(), 0.f, dst, c / 8, v, total / 8);
   } else {
     copy_kernel<<<grid_for(total), kBlock, 0, st>>>(src, dst, n, c, v, c_fastest_of(dst));
   }
@@ -487,6 +566,11 @@ int axpby_launch(const View& x1, float a, const View& x2, float b, const View& y
                  cudaStream_t st) {
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
+  if (vec8_ok(x1, c) && vec8_ok(x2, c) && vec8_ok(y, c)) {
+    axpby_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(x1, a, x2, b, y, c / 8, v, total / 8);
+    WS_POST_LAUNCH(1);
+    return 0;
+  }
   axpby_kernel<<<grid_for(total), kBlock, 0, st>>>(x1, a, x2, b, y, n, c, v, c_fastest_of(y));
   WS_POST_LAUNCH(1);
   return 0;
@@ -496,6 +580,11 @@ int lrelu_bwd_launch(const View& dy, const View& yv, float slope, const float* c
                      const View& g, int n, int c, long long v, cudaStream_t st) {
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
+  if (!chan_scale && !oscale && vec8_ok(dy, c) && vec8_ok(yv, c) && vec8_ok(g, c)) {
+    lrelu_bwd_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dy, yv, slope, g, c / 8, v, total / 8);
+    WS_POST_LAUNCH(1);
+    return 0;
+  }
   lrelu_bwd_kernel<<<grid_for(total), kBlock, 0, st>>>(dy, yv, slope, chan_scale, oscale, g, n, c, v,
                                                       c_fastest_of(g));
   WS_POST_LAUNCH(1);

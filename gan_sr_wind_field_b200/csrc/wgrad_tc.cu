@@ -416,4 +416,65 @@ int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, i
   return 0;
 }
 
+
+// ---- merged weight gradient of the dense convs of one residual dense block ---------------------------------------
+// The k dense convs of an RDB (torch_blocks.py:256-267) all read a prefix of the same concat buffer and each
+// produces gc (=32) channels, so their weight gradients are one GEMM: M = buffer channels [0, cin_max), N = the
+// k*gc gradient channels side by side, K = voxels, per tap.  N = 160 instead of five launches at N = 32 (the MMA
+// costs max(72, N/2) cycles either way).  The (ci >= cin_i) corner of conv i is computed and dropped.
+namespace {
+struct RdbSlices {
+  int nconv;
+  int cin[8];
+  float* dw[8];
+};
+__global__ void wgrad_tc_finalize_rdb(const float* __restrict__ wsp, const RdbSlices t, int taps, int gc, int wcin,
+                                      int wcout) {
+  // wsp [tap][i*gc + co][ci] -> dw_i [co][ci][tap]
+  const int i = blockIdx.y;
+  if (i >= t.nconv || !t.dw[i]) return;
+  const int cin = t.cin[i];
+  const long long total = (long long)taps * cin * gc;
+  float* __restrict__ dw = t.dw[i];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % taps);
+    const long long r = e / taps;
+    const int ci = (int)(r % cin), co = (int)(r / cin);
+    dw[e] = wsp[((long long)tap * wcout + (i * gc + co)) * wcin + ci];
+  }
+}
+}  // namespace
+
+size_t tc_rdb_wgrad_workspace_bytes(int taps, int cin_max, int nconv, int gc) {
+  return (size_t)taps * cin_max * nconv * gc * sizeof(float);
+}
+
+// gm: pseudo conv (cin = cin_max, cout = nconv*gc); x = concat buffer, g = the nconv*gc gradient channels.
+int tc_rdb_wgrad(const ConvGeom& gm, const View& x, const View& g, float* const* dw, const int* cin, int nconv,
+                 int gc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const size_t need = tc_rdb_wgrad_workspace_bytes(gm.taps(), gm.cin, nconv, gc);
+  WS_REQUIRE(workspace && workspace_bytes >= need, "rdb wgrad workspace too small: %zu < %zu", workspace_bytes, need);
+  WS_REQUIRE(nconv <= 8 && gm.cout == nconv * gc && gm.cout <= 256, "rdb wgrad: bad channel layout");
+  float* wsp = (float*)workspace;
+  WS_CHECK_CUDA(cudaMemsetAsync(wsp, 0, need, st));
+  if (int e = launch_one(gm, x, g, wsp, 1, gm.cin, 0, gm.cout, st)) return e;
+  RdbSlices t;
+  memset(&t, 0, sizeof(t));
+  t.nconv = nconv;
+  long long most = 0;
+  for (int i = 0; i < nconv; ++i) {
+    t.cin[i] = cin[i];
+    t.dw[i] = dw[i];
+    const long long e = (long long)gm.taps() * cin[i] * gc;
+    if (e > most) most = e;
+  }
+  int blocks = (int)((most + 255) / 256);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  wgrad_tc_finalize_rdb<<<dim3((unsigned)blocks, (unsigned)nconv), 256, 0, st>>>(wsp, t, gm.taps(), gc, gm.cin,
+                                                                                  gm.cout);
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
 }  // namespace ws

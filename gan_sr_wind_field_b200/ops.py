@@ -601,7 +601,7 @@ class RDBFn(torch.autograd.Function):
             dy = dy.float().contiguous(memory_format=torch.channels_last_3d)
         dbuf = empty_cl(n, ctot, X, Y, Z, torch.float32, dev)
         g_lff = empty_cl(n, f, X, Y, Z, cdt, dev)
-        g = empty_cl(n, max(gc, 1), X, Y, Z, cdt, dev)
+        g = empty_cl(n, max(nconv * gc, 1), X, Y, Z, cdt, dev)
         dx = empty_cl(n, f, X, Y, Z, torch.float32, dev) if need[0] else None
         grads = [None] * (nconv + 2)
         dw_arr = None
@@ -613,8 +613,7 @@ class RDBFn(torch.autograd.Function):
                 db = torch.empty_like(params[nconv + 1], dtype=torch.float32)
                 grads[nconv + 1] = db
             dw_arr = _ptr_array(grads[:nconv + 1])
-        nbytes = max(int(params[i].numel()) for i in range(nconv + 1)) * 4
-        wsp = _workspace(nbytes, dev)
+        wsp = _workspace(int(lib.ws_rdb_backward_workspace_bytes(C.byref(desc))), dev)
         dyv, bv, dbv, glv, gv = view(dy), view(buf), view(dbuf), view(g_lff), view(g)
         dxv = view(dx) if dx is not None else null_view()
         wd = [p.detach() for p in params[:nconv + 1]]

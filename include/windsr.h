@@ -157,8 +157,11 @@ size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int conv_index /* 0..nconv-1 de
 int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* outer, const ws_tensor* buf,
                    const ws_tensor* out, const float* const* w, void* const* packed, const float* lff_bias,
                    void* stream);
+/* bytes of the `workspace` ws_rdb_backward needs */
+size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d);
 /* dy: fp32 gradient of `out`.  Scratch: dbuf fp32 (n, f+nconv*gc, ..), g_lff activation-dtype (n,f,..),
- * g activation-dtype (n,gc,..).  dx (optional) = dL/dx incl. the beta1 skip.  dw[i] (optional, torch layout)
+ * g activation-dtype (n,nconv*gc,..) — the output gradients of all dense convs side by side (their weight
+ * gradients are one merged GEMM on the tensor-core path).  dx (optional) = dL/dx incl. the beta1 skip.  dw[i] (optional, torch layout)
  * and db_lff receive the parameter gradients (overwritten).  packed[i]: buffers of ws_rdb_packed_bytes(i, 1). */
 int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* buf, const ws_tensor* dbuf,
                     const ws_tensor* g_lff, const ws_tensor* g, const ws_tensor* dx, const float* const* w,

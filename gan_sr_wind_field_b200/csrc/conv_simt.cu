@@ -6,6 +6,7 @@
 //   * the strided discriminator dgrad until the tcgen05 parity-class kernel lands.
 // Operands are gathered straight from the (strided) activation views, so both the reference's NCXYZ
 // boundary tensors and the internal channels-last buffers are read in place.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ws {
@@ -604,6 +605,77 @@ conv_small_cin_wgrad(ConvGeom g, View in, View dy, float* __restrict__ wsp /*[ta
   }
 }
 
+// wgrad for Cin <= 3, kz == 3, sz == 1 and CO = 8/16/32 output channels (terrain_convs.0: 1 -> 16,
+// Generator_3D_Resnet_ESRGAN.py:120-137; discriminator features.0: 3 -> 32).  Thread (lane, group): the group is one
+// (ci, kx-tap, ky-tap), the 32 lanes of a warp take different (n, x, y) columns.  Walking z, a thread keeps the 3-wide
+// x window in registers and does 3*CO FMAs per {1 x load + one CO-vector dy load}: FMA-bound instead of load-bound.
+// The 3*CO partial sums are warp-reduced and added to wsp[tap][cin][cout] with one atomic each per warp.
+template <int CO>
+__global__ void __launch_bounds__(512)
+conv_small_cin_wgrad_z3(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long cols_per_block) {
+  const int lane = threadIdx.x, grp = threadIdx.y;  // blockDim = (32, kx*ky), blockIdx.y = input channel
+  const int ci = blockIdx.y, ti = grp / g.ky, tj = grp % g.ky;
+  const long long ncols = (long long)g.n * g.xo * g.yo;
+  const long long cbeg = (long long)blockIdx.x * cols_per_block;
+  const long long cend = cbeg + cols_per_block < ncols ? cbeg + cols_per_block : ncols;
+  float acc[3][CO];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[t][c] = 0.f;
+  const bool dy_vec = dy.dtype == WS_BF16 && dy.cs == 1 && dy.vs % 8 == 0 && dy.ns % 8 == 0 &&
+                      ((uintptr_t)dy.ptr % 16) == 0;
+  for (long long col = cbeg + lane; col < cend; col += 32) {
+    const int yo = (int)(col % g.yo);
+    const int xo = (int)((col / g.yo) % g.xo);
+    const int n = (int)(col / ((long long)g.yo * g.xo));
+    const int xi = xo * g.sx - g.px + ti, yi = yo * g.sy - g.py + tj;
+    if (xi < 0 || xi >= g.x || yi < 0 || yi >= g.y) continue;
+    const long long xin = in.off(n, ci, ((long long)xi * g.y + yi) * g.z);
+    const long long dyo = dy.off(n, 0, ((long long)xo * g.yo + yo) * g.zo);
+    // window w0..w2 = x[z - pz + 0..2]
+    float w0 = (-g.pz >= 0 && -g.pz < g.z) ? in.ld(xin + (long long)(-g.pz) * in.vs) : 0.f;
+    float w1 = (1 - g.pz >= 0 && 1 - g.pz < g.z) ? in.ld(xin + (long long)(1 - g.pz) * in.vs) : 0.f;
+    for (int zo = 0; zo < g.zo; ++zo) {
+      const int z2 = zo - g.pz + 2;
+      const float w2 = (z2 >= 0 && z2 < g.z) ? in.ld(xin + (long long)z2 * in.vs) : 0.f;
+      float d[CO];
+      if (dy_vec) {
+        const uint4* src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)dy.ptr + dyo + (long long)zo * dy.vs);
+#pragma unroll
+        for (int q = 0; q < CO / 8; ++q) {
+          const uint4 r = src[q];
+          const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d[q * 8 + 2 * j] = __uint_as_float(u[j] << 16);
+            d[q * 8 + 2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CO; ++c) d[c] = dy.ld(dyo + (long long)zo * dy.vs + (long long)c * dy.cs);
+      }
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        acc[0][c] = fmaf(w0, d[c], acc[0][c]);
+        acc[1][c] = fmaf(w1, d[c], acc[1][c]);
+        acc[2][c] = fmaf(w2, d[c], acc[2][c]);
+      }
+      w0 = w1; w1 = w2;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int tap = (ti * g.ky + tj) * g.kz + t;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const float v = warp_sum(acc[t][c]);
+      if (lane == 0) atomicAdd(&wsp[((long long)tap * g.cin + ci) * g.cout + c], v);
+    }
+  }
+}
+
 bool vec_ok(const View& v, int channels) {
   if (v.cs != 1) return false;
   int q = 4;  // 4 elements per vector access
@@ -691,6 +763,21 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   float* wsp = (float*)workspace;
   WS_CHECK_CUDA(cudaMemsetAsync(wsp, 0, need, st));
   const long long K = (long long)g.n * g.vout();
+  const int groups = g.kx * g.ky;
+  if (g.kz == 3 && g.sz == 1 && groups <= 16 && g.cin <= 4 && (g.cout == 8 || g.cout == 16 || g.cout == 32) &&
+      !getenv("WS_DISABLE_SMALL_CIN_Z3")) {
+    const long long ncols = (long long)g.n * g.xo * g.yo;
+    long long blocks = 148LL * 4 / g.cin;
+    long long cpb = (ncols + blocks - 1) / blocks;
+    if (cpb < 32) cpb = 32;
+    blocks = (ncols + cpb - 1) / cpb;
+    dim3 block(32, (unsigned)groups);
+    if (g.cout == 8) conv_small_cin_wgrad_z3<8><<<dim3((unsigned)blocks, (unsigned)g.cin), block, 0, st>>>(g, in, dy, wsp, cpb);
+    else if (g.cout == 16) conv_small_cin_wgrad_z3<16><<<dim3((unsigned)blocks, (unsigned)g.cin), block, 0, st>>>(g, in, dy, wsp, cpb);
+    else conv_small_cin_wgrad_z3<32><<<dim3((unsigned)blocks, (unsigned)g.cin), block, 0, st>>>(g, in, dy, wsp, cpb);
+    WS_POST_LAUNCH(1);
+    return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
+  }
   if (g.cin <= 4 && g.taps() * g.cin * g.cout <= 8 * 512) {
     const int O = g.taps() * g.cin * g.cout;
     int threads = O < 512 ? (O + 31) / 32 * 32 : 512;

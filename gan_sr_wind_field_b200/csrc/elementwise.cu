@@ -179,8 +179,9 @@ __global__ void axpby_cl8_kernel(View x1, float a, View x2, float b, View y, int
   }
 }
 
-// g = dy * lrelu'(y), all channels-last, 8 channels per thread (no per-channel scales)
-__global__ void lrelu_bwd_cl8_kernel(View dy, View yv, float slope, View g, int c8, long long v, long long total) {
+// g = dy * lrelu'(y) [* chan_scale[n][c]] [* oscale[c]], all channels-last, 8 channels per thread
+__global__ void lrelu_bwd_cl8_kernel(View dy, View yv, float slope, const float* __restrict__ chan_scale,
+                                     const float* __restrict__ oscale, View g, int c8, long long v, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % c8);
@@ -192,6 +193,15 @@ __global__ void lrelu_bwd_cl8_kernel(View dy, View yv, float slope, View g, int 
     ld8(yv, yv.off(nn, q * 8, vv), o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : slope * d[j];
+    if (chan_scale) {
+      const float* cs = chan_scale + (long long)nn * c8 * 8 + q * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] *= cs[j];
+    }
+    if (oscale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] *= oscale[q * 8 + j];
+    }
     st8(g, g.off(nn, q * 8, vv), d);
   }
 }
@@ -342,6 +352,31 @@ __global__ void upsample_bwd_generic(View dout, View din, int n, int c, int x, i
   }
 }
 
+// channels-last both sides: one 8-channel vector of din per thread = sum of the 2x2 block of dout
+__global__ void upsample_bwd_cl8(View dout, View din, int c8, int x, int y, int z, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % c8);
+    long long r = i / c8;
+    const int zz = (int)(r % z); r /= z;
+    const int yy = (int)(r % y); r /= y;
+    const int xx = (int)(r % x);
+    const int nn = (int)(r / x);
+    const long long Y2 = 2LL * y;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        float f[8];
+        ld8(dout, dout.off(nn, q * 8, ((2LL * xx + dx) * Y2 + 2 * yy + dy) * z + zz), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    st8(din, din.off(nn, q * 8, ((long long)xx * y + yy) * z + zz), s);
+  }
+}
+
 // ---- x-fold (narrow-output conv, see windsr.h) -----------------------------------------------------------
 __global__ void xfold_sum_kernel(View y, const float* __restrict__ bias, View out, int n, int co, int kx, int pad,
                                  int X, int Y, int Z) {
@@ -381,6 +416,34 @@ __global__ void xunfold_kernel(View dout, View u, int n, int co, int kx, int pad
       if (xs >= 0 && xs < X) val = dout.ld(nn, c, v + (long long)(pad - dx) * sx);
     }
     u.st(nn, ch, v, val);
+  }
+}
+
+// same, u channels-last with cpad % 8 == 0: one 8-channel vector store per thread
+__global__ void xunfold_st8_kernel(View dout, View u, int co, int kx, int pad, int cpad8, int X, int Y, int Z,
+                                   long long total) {
+  const long long V = (long long)X * Y * Z;
+  const long long sx = (long long)Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cpad8);
+    const long long r = i / cpad8;
+    const long long v = r % V;
+    const int nn = (int)(r / V);
+    const int xx = (int)(v / sx);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = q * 8 + j;
+      float val = 0.f;
+      if (ch < kx * co) {
+        const int dx = ch / co, c = ch - dx * co;
+        const int xs = xx - dx + pad;
+        if (xs >= 0 && xs < X) val = dout.ld(nn, c, v + (long long)(pad - dx) * sx);
+      }
+      f[j] = val;
+    }
+    st8(u, u.off(nn, q * 8, v), f);
   }
 }
 
@@ -580,8 +643,9 @@ int lrelu_bwd_launch(const View& dy, const View& yv, float slope, const float* c
                      const View& g, int n, int c, long long v, cudaStream_t st) {
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
-  if (!chan_scale && !oscale && vec8_ok(dy, c) && vec8_ok(yv, c) && vec8_ok(g, c)) {
-    lrelu_bwd_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dy, yv, slope, g, c / 8, v, total / 8);
+  if (vec8_ok(dy, c) && vec8_ok(yv, c) && vec8_ok(g, c)) {
+    lrelu_bwd_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dy, yv, slope, chan_scale, oscale, g, c / 8, v,
+                                                                total / 8);
     WS_POST_LAUNCH(1);
     return 0;
   }
@@ -615,6 +679,11 @@ int upsample_bwd_launch(const View& dout, const View& din, int n, int c, int x, 
                         cudaStream_t st) {
   long long total = (long long)n * c * x * y * z;
   if (total <= 0) return 0;
+  if (vec8_ok(dout, c) && vec8_ok(din, c)) {
+    upsample_bwd_cl8<<<grid_for(total / 8), kBlock, 0, st>>>(dout, din, c / 8, x, y, z, total / 8);
+    WS_POST_LAUNCH(1);
+    return 0;
+  }
   upsample_bwd_generic<<<grid_for(total), kBlock, 0, st>>>(dout, din, n, c, x, y, z, c_fastest_of(din));
   WS_POST_LAUNCH(1);
   return 0;
@@ -633,6 +702,11 @@ int xunfold_launch(const View& dout, const View& u, int n, int co, int kx, int p
                    cudaStream_t st) {
   long long total = (long long)n * cpad * X * Y * Z;
   if (total <= 0) return 0;
+  if (vec8_ok(u, cpad)) {
+    xunfold_st8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dout, u, co, kx, pad, cpad / 8, X, Y, Z, total / 8);
+    WS_POST_LAUNCH(1);
+    return 0;
+  }
   xunfold_kernel<<<grid_for(total), kBlock, 0, st>>>(dout, u, n, co, kx, pad, cpad, X, Y, Z);
   WS_POST_LAUNCH(1);
   return 0;

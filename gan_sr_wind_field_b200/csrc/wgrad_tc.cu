@@ -20,6 +20,8 @@
 // Replaces the weight-gradient half of autograd's convolution_backward for torch_blocks.py:17,278 and
 // Generator_3D_Resnet_ESRGAN.py:105.
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -306,22 +308,35 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   const double unit_mma = (p.rows / 16) * per_mma;
   const double unit_load = (double)sh_alloc * blk / 33.0;
   const double unit = unit_mma > unit_load ? unit_mma : unit_load;
-  const double atom = 128.0 * p.n_umma * 1.1;
+  const double atom = 128.0 * p.n_umma * 0.35;  // coalesced red.global.add epilogue of one tap (measured)
   const int max_tpc = 512 / p.n_umma;
   double best = 1e30;
   int best_tpc = 1;
   long long best_tps = p.total_tiles;
   for (int tpc = 1; tpc <= max_tpc && tpc <= p.taps; ++tpc) {
     const int tg = (p.taps + tpc - 1) / tpc;
-    for (int target = 148; target <= 444; target += 148) {
+    for (int target : {37, 74, 148, 296, 444}) {
       long long splits = (target + (long long)tg * mz - 1) / ((long long)tg * mz);
       if (splits > p.total_tiles) splits = p.total_tiles;
       if (splits < 1) splits = 1;
       const long long tps = (p.total_tiles + splits - 1) / splits;
       const long long ctas = (long long)tg * mz * ((p.total_tiles + tps - 1) / tps);
       const long long waves = (ctas + 147) / 148;
-      const double t = (double)waves * (tps * (tpc * unit + (double)fix_alloc * blk / 33.0) + tpc * atom + 8000.0);
+      // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many
+      // splits of a short K loop the sum over the CTAs of a wave, not one CTA's epilogue, is what is waited for
+      const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;
+      const double atom_chip = wave_ctas * tpc * 128.0 * p.n_umma / 512.0;
+      const double atom_t = tpc * atom > atom_chip ? tpc * atom : atom_chip;
+      const double t = (double)waves * (tps * (tpc * unit + (double)fix_alloc * blk / 33.0) + atom_t + 8000.0);
       if (t < best) { best = t; best_tpc = tpc; best_tps = tps; }
+    }
+  }
+  // experiment hook: WS_WGRAD_FORCE="taps_per_cta,splits" (read at every launch)
+  if (const char* f = getenv("WS_WGRAD_FORCE")) {
+    int ftpc = 0, fsplits = 0;
+    if (sscanf(f, "%d,%d", &ftpc, &fsplits) == 2 && ftpc >= 1 && ftpc <= max_tpc && fsplits >= 1) {
+      best_tpc = ftpc;
+      best_tps = (p.total_tiles + fsplits - 1) / fsplits;
     }
   }
   p.taps_per_cta = best_tpc;
@@ -337,10 +352,12 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
 
-  // workspace layout is always [tap][cout][cin]
+  // workspace layout: the M index is always the contiguous one, so that the 32 lanes of an epilogue warp (one
+  // accumulator row each) hit consecutive floats with every red.global.add — [tap][cout][cin] when M = cin
+  // (swap), [tap][cin][cout] when M = cout.  (Lane stride = cin made the 1x1x1 LFF gradient atomic-bound: 39 us.)
   p.tap_stride = (long long)g.cout * g.cin;
-  if (!swap) { p.m_stride = g.cin; p.n_stride = 1; }
-  else { p.m_stride = 1; p.n_stride = g.cin; }
+  p.m_stride = 1;
+  p.n_stride = swap ? g.cin : g.cout;
 
   auto make_map = [&](const View& v, int channels, int X, int Y, int Z, bool strided, CUtensorMap* out) -> int {
     MapKey k;
@@ -382,13 +399,14 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
 }
 
 __global__ void wgrad_tc_finalize(const float* __restrict__ wsp, float* __restrict__ dw, int taps, int cin,
-                                  int cout, int accumulate) {
-  // wsp [tap][co][ci] -> dw [co][ci][tap]
+                                  int cout, int accumulate, int cin_major) {
+  // wsp [tap][co][ci] (cin_major == 0) or [tap][ci][co] (cin_major == 1) -> dw [co][ci][tap]
   long long total = (long long)taps * cin * cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int tap = (int)(i % taps);
     long long r = i / taps;  // co*cin + ci
+    if (cin_major) r = (r % cin) * cout + r / cin;
     float v = wsp[(long long)tap * cin * cout + r];
     dw[i] = accumulate ? dw[i] + v : v;
   }
@@ -411,7 +429,7 @@ int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, i
   long long total = (long long)g.taps() * g.cin * g.cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_tc_finalize<<<blocks, 256, 0, st>>>(wsp, dw, g.taps(), g.cin, g.cout, accumulate);
+  wgrad_tc_finalize<<<blocks, 256, 0, st>>>(wsp, dw, g.taps(), g.cin, g.cout, accumulate, swap ? 0 : 1);
   WS_POST_LAUNCH(1);
   return 0;
 }

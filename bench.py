@@ -228,9 +228,12 @@ def run_native(args):
                 "loss_read": "async D2H into pinned memory every step, consumed on the host one step later"},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "tensor", "kernel": "conv3d_tc_kernel (hr_convs.0 fwd, 5x5x5 144->144 @128x128x10, B=8)",
+        "roofline": {"bound": "tensor", "kernel": "conv3d_tc2_kernel<true> (hr_convs.0 fwd, 5x5x5 144->144 @128x128x10, B=8)",
                      "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
-                     "frac": achieved / tflops_peak if tflops_peak else None, "traffic": None,
+                     "frac": achieved / tflops_peak if tflops_peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
+                     # profiles/r01_ncu_conv3d_tc2_pair_g7_fwd_v2.md (algorithmic: 760.1 MB)
+                     "traffic": 720.0e6, "traffic_unit": "bytes/launch",
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "kernel_ms": k_avg,
                      "kernel_launches_timed": len(k_ms), "flops_per_launch": flops},
     }

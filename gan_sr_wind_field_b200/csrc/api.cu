@@ -47,6 +47,7 @@ int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&,
 bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
+int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t);
 int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
                  cudaStream_t);
 size_t tc_rdb_wgrad_workspace_bytes(int, int, int, int);
@@ -426,6 +427,35 @@ ws_conv_shape rdb_merged_shape(const ws_rdb_desc* d) {
                      1, (d->k - 1) / 2, (d->k - 1) / 2, (d->k - 1) / 2};
   return s;
 }
+// (Re)pack all weights of the block for one direction: the tensor-core packings go out as ONE launch.
+// act: the operand view whose layout decides the path of the dense convs' / LFF's input (forward: the concat buffer;
+// backward: g_lff for the LFF and a gc-channel slice of gbuf for the dense convs).
+int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act, const ws_tensor* dense_act,
+               const float* const* w, void* const* packed, int dgrad, cudaStream_t st) {
+  const float* bw[WS_RDB_MAX_CONVS + 1];
+  void* bp[WS_RDB_MAX_CONVS + 1];
+  ConvGeom bg[WS_RDB_MAX_CONVS + 1] = {};
+  int nb = 0;
+  for (int i = 0; i <= d->nconv; ++i) {
+    const ws_conv_shape* s = i < d->nconv ? &r.dense[i] : &r.lff;
+    ConvGeom g(*s);
+    bool tc;
+    if (!dgrad) {
+      tc = fwd_path(g, View(lff_act), d->math) == WS_PATH_TCGEN05;  // every conv reads the concat buffer
+    } else if (i < d->nconv) {
+      ws_tensor gs = slice(*dense_act, i * d->gc);
+      tc = dgrad_path(g, View(&gs), d->math) == WS_PATH_TCGEN05;
+    } else {
+      tc = dgrad_path(g, View(lff_act), d->math) == WS_PATH_TCGEN05;
+    }
+    if (tc) {
+      bw[nb] = w[i]; bp[nb] = packed[i]; bg[nb] = g; ++nb;
+    } else if (int e = pack_weights_launch(w[i], g, dgrad ? WS_PACK_SIMT_DGRAD : WS_PACK_SIMT_FWD, packed[i], st)) {
+      return e;
+    }
+  }
+  return pack_tc_batch_launch(nb, bw, bg, dgrad, bp, st);
+}
 bool rdb_merged_wgrad_ok(const ws_rdb_desc* d, const ws_tensor* buf, const ws_tensor* gbuf) {
   if (d->nconv < 2 || d->nconv * d->gc > 256 || d->gc % 16 != 0 || getenv("WS_DISABLE_RDB_MERGED_WGRAD")) return false;
   ws_conv_shape s = rdb_merged_shape(d);
@@ -468,25 +498,16 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   // buf[:, :f] = x (cast to the activation dtype)
   ws_tensor b0 = *buf;
   if (int e = copy_launch(View(x), View(&b0), d->n, d->f, v, st)) return e;
+  if (d->repack)
+    if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st)) return e;
   for (int i = 0; i < d->nconv; ++i) {
     const ws_conv_shape* s = &r.dense[i];
-    ConvGeom g(*s);
     ws_tensor in = *buf, o = slice(*buf, s->cin);
-    View vin(&in), vout(&o);
-    const bool tc = fwd_path(g, vin, d->math) == WS_PATH_TCGEN05;
-    if (d->repack)
-      if (int e = pack_weights_launch(w[i], g, tc ? WS_PACK_TC_FWD : WS_PACK_SIMT_FWD, packed[i], st)) return e;
     ws_epilogue ep = plain_epilogue();
     ep.lrelu_slope = d->slope;
     if (int e = ws_conv3d_fwd(s, &in, packed[i], &o, &ep, d->math, stream)) return e;
   }
   {
-    ConvGeom g(r.lff);
-    View vin(buf);
-    const bool tc = fwd_path(g, vin, d->math) == WS_PATH_TCGEN05;
-    if (d->repack)
-      if (int e = pack_weights_launch(w[d->nconv], g, tc ? WS_PACK_TC_FWD : WS_PACK_SIMT_FWD, packed[d->nconv], st))
-        return e;
     ws_epilogue ep = plain_epilogue();
     ep.bias = lff_bias;
     ep.alpha = d->alpha;
@@ -521,13 +542,9 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
                                 stream))
       return e;
   }
+  if (d->repack)
+    if (int e = rdb_repack(d, r, g_lff, gbuf, w, packed, 1, st)) return e;
   {
-    ConvGeom g(r.lff);
-    const bool tc = dgrad_path(g, View(g_lff), d->math) == WS_PATH_TCGEN05;
-    if (d->repack)
-      if (int e = pack_weights_launch(w[d->nconv], g, tc ? WS_PACK_TC_DGRAD : WS_PACK_SIMT_DGRAD,
-                                      packed[d->nconv], st))
-        return e;
     ws_epilogue ep = plain_epilogue();
     if (int e = ws_conv3d_dgrad(&r.lff, g_lff, packed[d->nconv], dbuf, &ep, d->math, stream)) return e;
   }
@@ -544,9 +561,6 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
       if (int e = ws_conv3d_wgrad(s, buf, gi, dw[i], nullptr, 0, d->math, workspace, workspace_bytes, stream))
         return e;
     }
-    const bool tc = dgrad_path(g, View(gi), d->math) == WS_PATH_TCGEN05;
-    if (d->repack)
-      if (int e = pack_weights_launch(w[i], g, tc ? WS_PACK_TC_DGRAD : WS_PACK_SIMT_DGRAD, packed[i], st)) return e;
     ws_epilogue ep = plain_epilogue();
     ep.res1 = *dbuf; ep.beta1 = 1.f;  // accumulate into dbuf[:, :cin]
     if (int e = ws_conv3d_dgrad(s, gi, packed[i], dbuf, &ep, d->math, stream)) return e;

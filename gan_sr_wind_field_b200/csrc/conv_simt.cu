@@ -457,6 +457,46 @@ __global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, 
   }
 }
 
+// channels-last dy (bf16 or fp32, 8-channel vectors): a block takes a run of voxel rows, thread (q, r) sums the
+// 8 channels of group q over rows r, r + R, ...; partials meet in shared memory, one atomic per channel per block.
+__global__ void __launch_bounds__(256)
+bias_grad_cl8_kernel(View dy, float* __restrict__ db, int c8, long long v, long long rows_total, long long rows_per_block) {
+  __shared__ float red[256][9];
+  const int q = threadIdx.x % c8, r = threadIdx.x / c8, R = blockDim.x / c8;
+  const long long beg = (long long)blockIdx.x * rows_per_block;
+  const long long end = beg + rows_per_block < rows_total ? beg + rows_per_block : rows_total;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r < R) {
+    for (long long i = beg + r; i < end; i += R) {
+      const long long o = dy.off((int)(i / v), q * 8, i % v);
+      if (dy.dtype == WS_F32) {
+        const float4 a = *reinterpret_cast<const float4*>((const float*)dy.ptr + o);
+        const float4 b = *reinterpret_cast<const float4*>((const float*)dy.ptr + o + 4);
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)dy.ptr + o);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[2 * j] += __uint_as_float(w[j] << 16);
+          s[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  // thread t < c sums channel t over the R row-threads
+  const int c = c8 * 8;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int qq = ch / 8, j = ch % 8;
+    float t = 0.f;
+    for (int rr = 0; rr < R; ++rr) t += red[rr * c8 + qq][j];
+    atomicAdd(&db[ch], t);
+  }
+}
+
 // ---- narrow-input layers (Cin <= 4: feature_conv, terrain_convs.0, D's first conv) -------------------------
 // The implicit-GEMM tiling above wastes 13/16 of every K chunk when Cin = 3.  Direct form instead: one thread per
 // output voxel, 16 output channels per thread, the (taps x Cin x 16) weight slice in shared memory (warp-wide
@@ -735,6 +775,19 @@ int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumula
   if (c <= 0) return 0;
   if (!accumulate) WS_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
   long long total = (long long)n * v;
+  {
+    const int al = dy.dtype == WS_F32 ? 4 : 8;
+    if (dy.cs == 1 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && dy.vs % al == 0 && dy.ns % al == 0 &&
+        ((uintptr_t)dy.ptr % 16) == 0) {
+      long long blocks = (total + 255) / 256;
+      if (blocks > 148 * 4) blocks = 148 * 4;
+      const long long rpb = (total + blocks - 1) / blocks;
+      blocks = (total + rpb - 1) / rpb;
+      bias_grad_cl8_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, db, c / 8, v, total, rpb);
+      WS_POST_LAUNCH(1);
+      return 0;
+    }
+  }
   int slices = (int)((total + 8191) / 8192);
   int max_slices = (148 * 8 + c - 1) / c;
   if (slices > max_slices) slices = max_slices;

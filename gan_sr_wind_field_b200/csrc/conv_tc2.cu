@@ -45,6 +45,9 @@ struct Tc2Params {
   int a_bufs;        // halo buffers in the ring (2..kMaxABufs)
   int a_sub_slabs;   // x-slabs per TMA instruction of the halo load
   int a_ops;         // TMA instructions per halo load
+  int vol;           // 1: volume mode — ONE padded halo box per 64-channel chunk, all kx*ky*kz taps = row offsets
+  int pitch_y;       // rows between consecutive y lines of the tile (DZ, or DZ + kz - 1 in volume mode)
+  int box_y, box_z;  // TMA box extents in y and z (by, DZ, plus the ky-1 / kz-1 halo in volume mode)
   int tap_base;      // first tap of the packed weights this launch uses
   int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
@@ -55,7 +58,7 @@ struct Tc2Params {
 // A tiles with the pair's combined B tile.  Per SM this halves the weight traffic from L2 and the B-operand reads
 // from shared memory (measured: a cta_group::1 N=144 MMA already saturates the 128 B/clk SMEM port).
 template <bool kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kPair ? 1 : 2)  // non-pair tiles are costed for two CTAs per SM: <= 168 regs
 conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const Tc2Params p, const View dst, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -119,8 +122,10 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
     const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * 128u;
-    for (int yz = 0; yz < nyz; ++yz) {
-      const int tj = yz / p.kz, tl = yz % p.kz;
+    const int ngroups = p.vol ? 1 : nyz;             // activation loads per 64-channel chunk
+    const int ntaps = p.vol ? p.kx * nyz : p.kx;     // weight tiles per activation load
+    for (int yz = 0; yz < ngroups; ++yz) {
+      const int tj = p.vol ? 0 : yz / p.kz, tl = p.vol ? 0 : yz % p.kz;
       for (int ch = 0; ch < p.kchunks; ++ch) {
         ptx::mbar_wait(a_empty(ab), aph ^ 1u);
         if (ptx::elect_one()) {
@@ -138,8 +143,9 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         __syncwarp();
         if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
-        for (int ti = 0; ti < p.kx; ++ti) {
-          const int tap = p.tap_base + (ti * p.ky + tj) * p.kz + tl;
+        for (int tt = 0; tt < ntaps; ++tt) {
+          // volume mode walks the packed taps in storage order (ti, tj, tl); otherwise the kx taps of this (tj, tl)
+          const int tap = p.tap_base + (p.vol ? tt : (tt * p.ky + tj) * p.kz + tl);
           ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(w_full(wsl), w_cta_bytes * tx_mult);
@@ -157,19 +163,29 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);  // everything but the start address
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
-    const int iters = nyz * p.kchunks;
+    const int ntaps = p.vol ? p.kx * nyz : p.kx;
+    const int iters = (p.vol ? 1 : nyz) * p.kchunks;
     for (int it = 0; it < iters; ++it) {
       const int ch = it % p.kchunks;
       const int nk = (ch == p.kchunks - 1) ? p.last_k16 : 4;
       ptx::mbar_wait(a_full(ab), aph);
       const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
-      for (int ti = 0; ti < p.kx; ++ti) {
+      for (int tt = 0; tt < ntaps; ++tt) {
         ptx::mbar_wait(w_full(wsl), wph);
         ptx::tc_fence_after();
         const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_bytes) >> 4) & 0x3fffu);
-        const uint32_t acc0 = (it > 0 || ti > 0) ? 1u : 0u;
+        const uint32_t acc0 = (it > 0 || tt > 0) ? 1u : 0u;
+        // tap -> first A row.  Any 128-byte row of the 1024-byte-aligned tile is a valid SWIZZLE_128B operand
+        // start with base_offset 0: the swizzle is a function of the absolute address bits
+        // (scripts/micro/row_offset.cu), so ky / kz shifts need no 8-row alignment.
+        int roff = tt * p.slabrows;
+        if (p.vol) {
+          const int ti = tt / nyz, tyz = tt - ti * nyz;
+          const int tj = tyz / p.kz, tl = tyz - tj * p.kz;
+          roff = ti * p.slabrows + tj * p.pitch_y + tl;
+        }
         for (int m = 0; m < p.t_m; ++m) {
-          const uint32_t am = a_addr + (uint32_t)(m * 128 + ti * p.slabrows) * 128u;
+          const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * 128u;
           const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
           if (ptx::elect_one()) {
@@ -209,17 +225,36 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int r = m * 128 + sub * 32 + lane;  // row inside the CTA's output region
       const int rx = r / p.slabrows;
       const int rem = r - rx * p.slabrows;
-      const int ry = rem / p.bz, rz = rem - ry * p.bz;
+      const int ry = rem / p.pitch_y, rz = rem - ry * p.pitch_y;
       const int gx = x0 + rx, gy = y0 + ry;
-      const bool row_ok = tile_ok && r < p.out_rows && gx < p.DX && gy < p.DY;
+      const bool row_ok = tile_ok && r < p.out_rows && ry < p.by && rz < p.bz && gx < p.DX && gy < p.DY;
       const long long v = ((long long)(gx * p.omx + p.oax) * p.ODY + (gy * p.omy + p.oay)) * p.ODZ + (rz * p.omz + p.oaz);
-      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
-        if (n0 + c0 >= p.cn) break;
-        uint32_t rr[16];
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
-        ptx::tmem_ld_wait();
-        if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr);
-        else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
+      if (simple && ep.res1.ptr) {
+        // accumulate-into-residual epilogue (dense-conv dgrads, LFF): the res1 reads of the NEXT 16 channels are in
+        // flight while the current 16 are converted and stored, so the L2 round trips overlap instead of
+        // serialising one per chunk (the dgrad chain was bound by exactly that latency).
+        const int climit = p.cn - n0 < p.n_umma ? p.cn - n0 : p.n_umma;  // columns of this tile that exist
+        const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma);
+        float cur[16], nxt[16];
+        prefetch_res16(ep, ev, n, v, n0, p.cn, n0 + climit, row_ok, cur);
+        for (int c0 = 0; c0 < climit; c0 += 16) {
+          uint32_t rr[16];
+          ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
+          prefetch_res16(ep, ev, n, v, n0 + c0 + 16, p.cn, n0 + climit, row_ok, nxt);
+          ptx::tmem_ld_wait();
+          epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, cur);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+        }
+      } else {
+        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+          if (n0 + c0 >= p.cn) break;
+          uint32_t rr[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
+          ptx::tmem_ld_wait();
+          if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr);
+          else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
+        }
       }
     }
     ptx::tc_fence_before();
@@ -298,14 +333,81 @@ bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool p
   return found;
 }
 
+// Volume mode: the CTA's tile is tx x by x DZ outputs and its activation operand is the (tx+kx-1) x (by+ky-1) x
+// (DZ+kz-1) padded halo, fetched ONCE per 64-channel chunk; rows are ordered (x, y, z) with the padded pitches, so
+// tap (ti, tj, tl) is the row offset ti*PY*PZ + tj*PZ + tl.  Pad positions inside the row span are computed and
+// dropped by the epilogue.  Against the per-(ky,kz) halo this cuts the L2 -> SMEM activation traffic and the number
+// of pipeline stages by ~ky*kz: it is for the small-volume trunk convs, which are bound by exactly that.
+bool choose_cfg_vol_search(int N, int DX, int DY, int DZ, int kx, int ky, int kz, int n_umma, int kchunks,
+                           Tc2Params& p) {
+  const int tmax = 512 / n_umma < 4 ? 512 / n_umma : 4;
+  if (tmax < 1) return false;
+  const int PZ = DZ + kz - 1;
+  const int taps = kx * ky * kz;
+  double best = 1e30;
+  bool found = false;
+  static int force_by = 0, force_tx = 0;
+  static const bool forced = [] {
+    const char* v = getenv("WS_TC2_FORCE");
+    return v && sscanf(v, "%d,%d", &force_by, &force_tx) == 2;
+  }();
+  for (int by = 1; by <= DY; ++by) {
+    if (forced && by != force_by) continue;
+    const int PY = by + ky - 1;
+    if (PY > 256 || PZ > 256) break;
+    const int slab = PY * PZ;
+    for (int tx = 1; tx <= DX; ++tx) {
+      if (forced && tx != force_tx) continue;
+      if (tx + kx - 1 > 256) break;
+      const int span = (tx - 1) * slab + (by - 1) * PZ + DZ;
+      const int t_m = (span + 127) / 128;
+      if (t_m > tmax) break;
+      const int halo = (tx + kx - 1) * slab;
+      int a_rows = t_m * 128 + (kx - 1) * slab + (ky - 1) * PZ + kz - 1;
+      for (int want = 1; want <= 4; ++want) {
+        const int sub = (tx + kx - 1 + want - 1) / want;
+        const int ops_rows = ((tx + kx - 1 + sub - 1) / sub) * sub * slab;
+        if (a_rows < ops_rows) a_rows = ops_rows;
+      }
+      const int a_bytes = (a_rows * 128 + 1023) / 1024 * 1024;
+      const int w_bytes = n_umma * 128;
+      const int nbuf = kchunks > 1 ? 2 : 1;
+      if (nbuf * a_bytes + 3 * w_bytes + 2048 > kSmemBudget) continue;
+      const double per_mma = n_umma / 2.0 > 72.0 ? n_umma / 2.0 : 72.0;
+      const double mma = (double)t_m * taps * 4 * per_mma;
+      const double load = (halo * 128.0 + (double)taps * w_bytes) / 34.0;
+      const long long ctas = (long long)N * ((DX + tx - 1) / tx) * ((DY + by - 1) / by);
+      const int smem_min = nbuf * a_bytes + 4 * w_bytes + 2048;
+      int cols = 32;
+      while (cols < t_m * n_umma) cols <<= 1;
+      const int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 ? 2 : 1;
+      const long long per_sm = (ctas + 147) / 148;
+      const int r = per_sm < cps ? (int)per_sm : cps;
+      const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
+      const double chunk = (mma > load ? mma : load) * r + (150.0 * taps + 300.0) / r;
+      const double cost = (double)waves * (chunk * kchunks + 6000.0 + 2500.0 * t_m);
+      if (cost < best) {
+        best = cost;
+        found = true;
+        p.by = by; p.tx = tx; p.t_m = t_m; p.slabrows = slab; p.halo_rows = halo; p.a_buf_bytes = a_bytes;
+        p.w_bytes = w_bytes;
+        p.a_bufs = r;  // CTAs per SM this config was costed with (see choose_cfg_search)
+      }
+    }
+  }
+  return found;
+}
+
 // The search above costs ~10 us of host time; the trunk launches ~500 convs per step, so memoise it per geometry.
-bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
+bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p, int vol = 0, int ky = 1,
+                int kz = 1, int kchunks = 1) {
   struct Hit { bool ok; int by, tx, t_m, slabrows, halo_rows, a_buf_bytes, w_bytes, a_bufs; };
   static std::mutex mu;
   static std::unordered_map<unsigned long long, Hit> memo;
   unsigned long long key = 1469598103934665603ull;
   for (long long v : {(long long)N, (long long)DX, (long long)DY, (long long)DZ, (long long)kx, (long long)n_umma,
-                      (long long)pair})
+                      (long long)pair, (long long)vol, (long long)(vol ? ky : 1), (long long)(vol ? kz : 1),
+                      (long long)(vol ? kchunks : 1)})
     key = (key ^ (unsigned long long)v) * 1099511628211ull;
   {
     std::lock_guard<std::mutex> lk(mu);
@@ -317,7 +419,8 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc
       return h.ok;
     }
   }
-  const bool ok = choose_cfg_search(N, DX, DY, DZ, kx, n_umma, pair, p);
+  const bool ok = vol ? choose_cfg_vol_search(N, DX, DY, DZ, kx, ky, kz, n_umma, kchunks, p)
+                      : choose_cfg_search(N, DX, DY, DZ, kx, n_umma, pair, p);
   Hit h = {ok, p.by, p.tx, p.t_m, p.slabrows, p.halo_rows, p.a_buf_bytes, p.w_bytes, p.a_bufs};
   std::lock_guard<std::mutex> lk(mu);
   memo[key] = h;
@@ -369,12 +472,22 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   const long long vox = (long long)p.N * p.DX * p.DY * p.DZ;
   bool pair = env_pair >= 0 ? env_pair != 0 : (p.n_umma >= 128 && vox >= 148LL * 2 * 384);
   if (n_tiles != 1) pair = false;
-  if (!choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, pair, p)) return -1;
-  p.out_rows = p.tx * p.slabrows;
-  p.tiles_x = (p.DX + p.tx - 1) / p.tx;
-  p.tiles_y = (p.DY + p.by - 1) / p.by;
   p.kchunks = (p.ck + 63) / 64;
   p.last_k16 = (p.ck - 64 * (p.kchunks - 1) + 15) / 16;
+  // volume mode is opt-in (WS_TC2_VOL=1): measured on the RRDB trunk it is parity-clean but not faster (dense
+  // conv 54 vs 48 us, dgrad 46 vs 45 us) — those layers are bound by the N=32 MMA floor and by the weight
+  // stream, not by the activation re-reads this mode removes.
+  static const int env_vol = getenv("WS_TC2_VOL") ? atoi(getenv("WS_TC2_VOL")) : 0;
+  bool vol = !pair && p.ky * p.kz > 1 && env_vol != 0;
+  if (vol && !choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, false, p, 1, p.ky, p.kz, p.kchunks)) vol = false;
+  if (!vol && !choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, pair, p)) return -1;
+  p.vol = vol ? 1 : 0;
+  p.pitch_y = vol ? p.DZ + p.kz - 1 : p.DZ;
+  p.box_z = p.pitch_y;
+  p.box_y = vol ? p.by + p.ky - 1 : p.by;
+  p.out_rows = vol ? (p.tx - 1) * p.slabrows + (p.by - 1) * p.pitch_y + p.DZ : p.tx * p.slabrows;
+  p.tiles_x = (p.DX + p.tx - 1) / p.tx;
+  p.tiles_y = (p.DY + p.by - 1) / p.by;
   static const int env_split = getenv("WS_TC2_ASPLIT") ? atoi(getenv("WS_TC2_ASPLIT")) : 4;
   static const int env_bufs = getenv("WS_TC2_ABUFS") ? atoi(getenv("WS_TC2_ABUFS")) : kMaxABufs;
   {
@@ -387,11 +500,16 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   const int budget = p.a_bufs >= 2 ? (227 * 1024) / 2 - 1024 : kSmemBudget;
   // weight ring: at least kx + 1 slots when they fit, then as many halo buffers as the rest allows
   p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : (p.kx + 1 < 3 ? 3 : p.kx + 1);
-  while (p.w_slots > 2 && 2 * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > budget) --p.w_slots;
+  {
+    const int need_bufs = (vol && p.kchunks == 1) ? 1 : 2;
+    while (p.w_slots > 2 && need_bufs * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > budget) --p.w_slots;
+  }
   p.a_bufs = (budget - 2048 - p.w_slots * p.w_bytes) / p.a_buf_bytes;
   if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
   if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
-  if (p.a_bufs < 2 || p.w_slots < 2) return -1;
+  const int loads = (vol ? 1 : p.ky * p.kz) * p.kchunks;  // activation loads of the whole kernel
+  if (p.a_bufs > loads) p.a_bufs = loads;
+  if (p.a_bufs < (loads > 1 ? 2 : 1) || p.w_slots < 2) return -1;
   {
     int spare = (budget - 2048 - p.a_bufs * p.a_buf_bytes) / p.w_bytes;
     if (spare > kMaxWSlots) spare = kMaxWSlots;
@@ -411,7 +529,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   ka.strides[1] = (uint64_t)src.vs * 2 * SZ;
   ka.strides[2] = (uint64_t)src.vs * 2 * SZ * SY;
   ka.strides[3] = (uint64_t)src.ns * 2;
-  ka.box[0] = 64; ka.box[1] = (uint32_t)p.bz; ka.box[2] = (uint32_t)p.by; ka.box[3] = (uint32_t)p.a_sub_slabs;
+  ka.box[0] = 64; ka.box[1] = (uint32_t)p.box_z; ka.box[2] = (uint32_t)p.box_y; ka.box[3] = (uint32_t)p.a_sub_slabs;
   ka.box[4] = 1;
   for (int i = 0; i < 5; ++i) ka.estr[i] = 1;
   CUtensorMap tmA, tmB;

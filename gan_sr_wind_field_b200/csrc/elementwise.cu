@@ -2,6 +2,7 @@
 // (the dense-concat and layout changes of torch_blocks.py:214,286 / Generator…py:228), axpby, LeakyReLU
 // backward, the x/y nearest upsample and its 2x2 block-sum backward (torch_blocks.py:347), and the
 // BatchNorm3d statistics finalize / apply / backward (torch_blocks.py:24-25).
+#include <string.h>
 #include "common.cuh"
 
 namespace ws {
@@ -58,6 +59,38 @@ __global__ void pack_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__
       if (row < cout && col < cin) v = w[((long long)row * cin + col) * taps + tp];
     } else {
       if (row < cin && col < cout) v = w[((long long)col * cin + row) * taps + (taps - 1 - tp)];
+    }
+    p[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Several stride-1 tcgen05 packings in one launch (blockIdx.y = entry): the residual dense block executor repacks
+// all of its convs after every optimizer step, and five 3-us launches per block direction added up to 1.4 ms.
+struct PackEntry {
+  const float* w;
+  __nv_bfloat16* p;
+  int cout, cin, taps, rows_pad, cols_pad, dgrad;
+};
+struct PackTable {
+  int n;
+  PackEntry e[WS_RDB_MAX_CONVS + 1];
+};
+__global__ void pack_tc_multi(const PackTable t) {
+  const PackEntry& e = t.e[blockIdx.y];
+  const float* __restrict__ w = e.w;
+  __nv_bfloat16* __restrict__ p = e.p;
+  const long long total = (long long)e.taps * e.rows_pad * e.cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % e.cols_pad);
+    const long long r = i / e.cols_pad;
+    const int row = (int)(r % e.rows_pad);
+    const int tp = (int)(r / e.rows_pad);
+    float v = 0.f;
+    if (!e.dgrad) {
+      if (row < e.cout && col < e.cin) v = w[((long long)row * e.cin + col) * e.taps + tp];
+    } else {
+      if (row < e.cin && col < e.cout) v = w[((long long)col * e.cin + row) * e.taps + (e.taps - 1 - tp)];
     }
     p[i] = __float2bfloat16_rn(v);
   }
@@ -596,6 +629,31 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
     pack_tc<<<grid_for(total), kBlock, 0, st>>>(w, (__nv_bfloat16*)packed, g.cout, g.cin, taps, rows, cols,
                                                dgrad);
   }
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+// stride-1 tensor-core packings of up to WS_RDB_MAX_CONVS + 1 convs in one launch
+int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dgrad, void* const* packed,
+                         cudaStream_t st) {
+  if (n <= 0) return 0;
+  WS_REQUIRE(n <= WS_RDB_MAX_CONVS + 1, "pack_tc_batch: too many entries");
+  PackTable t;
+  memset(&t, 0, sizeof(t));
+  t.n = n;
+  long long most = 0;
+  for (int i = 0; i < n; ++i) {
+    PackEntry& e = t.e[i];
+    e.w = w[i]; e.p = (__nv_bfloat16*)packed[i];
+    e.cout = g[i].cout; e.cin = g[i].cin; e.taps = g[i].taps(); e.dgrad = dgrad;
+    e.rows_pad = dgrad ? (g[i].cin + 15) / 16 * 16 : (g[i].cout + 15) / 16 * 16;
+    e.cols_pad = dgrad ? (g[i].cout + 7) / 8 * 8 : (g[i].cin + 7) / 8 * 8;
+    const long long total = (long long)e.taps * e.rows_pad * e.cols_pad;
+    if (total > most) most = total;
+  }
+  int bx = (int)((most + kBlock - 1) / kBlock);
+  if (bx > 148 * 2) bx = 148 * 2;
+  pack_tc_multi<<<dim3((unsigned)bx, (unsigned)n), kBlock, 0, st>>>(t);
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -90,9 +90,10 @@ __device__ __forceinline__ void store16(const View& t, bool vec, int n, int c0, 
 // was ~80 % epilogue); this one is ~6 instructions per element.
 __device__ __forceinline__ bool epi_is_simple(const Epi& ep) { return !ep.mask.ptr && !ep.stat_sum; }
 
+// `r1`: the res1 values of this chunk when the caller prefetched them (software-pipelined epilogue), else null
 __device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& ev, const View& dst, int n,
                                                   long long v, int cbase, int cn, bool row_ok,
-                                                  const uint32_t (&rr)[16]) {
+                                                  const uint32_t (&rr)[16], const float* r1 = nullptr) {
   if (!row_ok) return;
   float y[16];
   const float slope = ep.lrelu_slope, alpha = ep.alpha;
@@ -114,10 +115,15 @@ __device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& e
     for (int j = 0; j < 16; ++j) y[j] *= (cbase + j < cn ? cs[j] : 0.f);
   }
   if (ep.res1.ptr) {
-    float r[16];
-    load16(ep.res1, ev.res1, n, cbase, v, cn, r);
+    if (r1) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta1, r[j], y[j]);
+      for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta1, r1[j], y[j]);
+    } else {
+      float r[16];
+      load16(ep.res1, ev.res1, n, cbase, v, cn, r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta1, r[j], y[j]);
+    }
   }
   if (ep.res2.ptr) {
     float r[16];
@@ -127,6 +133,12 @@ __device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& e
   }
   store16(dst, ev.dst, n, cbase, v, cn, y);
   if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
+}
+
+// res1 values of one 16-channel chunk, fetched one chunk ahead of the TMEM load that needs them
+__device__ __forceinline__ void prefetch_res16(const Epi& ep, const EpiVec& ev, int n, long long v, int cbase, int cn,
+                                               int climit, bool row_ok, float (&r)[16]) {
+  if (row_ok && cbase < climit) load16(ep.res1, ev.res1, n, cbase, v, cn, r);
 }
 
 // One 16-column chunk of fp32 accumulators `rr` (tcgen05.ld 32x32b.x16) for accumulator row = voxel (n, v).

@@ -25,6 +25,7 @@ bounded sample (batch 1) of the same workload.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -144,13 +145,36 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        # Python's cyclic GC is kept out of the timed region (collected between legs instead): a generation-2 pass
+        # over the autograd graphs of a 2000-launch step takes ~100 ms on one rank and, under data parallelism,
+        # stalls every rank at the next all-reduce.
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed_inner(fn, steps)
+        finally:
+            gc.enable()
+
+    def _timed_inner(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks, host = [], []
         e0.record()
         for i in range(steps):
+            h0 = time.perf_counter()
             fn(i)
+            if os.environ.get("BENCH_DEBUG_LEGS"):
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
+                host.append(round(1e3 * (time.perf_counter() - h0), 1))
         e1.record()
         barrier()
+        if marks:
+            prev, per = e0, []
+            for m in marks:
+                per.append(round(prev.elapsed_time(m), 1))
+                prev = m
+            print(f"[rank {rank}] per-step ms: {per} host enqueue ms: {host}", file=sys.stderr, flush=True)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -195,9 +219,14 @@ def run_native(args):
     # roofline leg: time the dominant kernel (hr_convs.0 forward: 5x5x5, 144->144 @128x128x10, 69.6 % of G's
     # FLOPs) in-stream during the timed region
     is_g7 = lambda kind, s: kind == "fwd" and s.kx == 5 and s.cin == s.cout and s.x == HR_XY
-    ops.set_kernel_timer(is_g7)
+    if os.environ.get("BENCH_DEBUG_LEGS"):  # diagnostic: the resident leg without timer / sampler, per rank
+        ms_plain = timed(step_resident, args.steps)
+        print(f"[rank {rank}] resident leg without kernel timer / clock sampler: {ms_plain / args.steps:.2f} ms/step",
+              file=sys.stderr, flush=True)
+    if os.environ.get("BENCH_DEBUG_LEGS") != "notimer":
+        ops.set_kernel_timer(is_g7)
     launches0 = ops.launch_count()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if os.environ.get("BENCH_DEBUG_LEGS") != "nosampler" else -1)
     ms = timed(step_resident, args.steps)
     clock_info = clocks.stop()
     launches = ops.launch_count() - launches0

@@ -66,6 +66,7 @@ class wind_field_GAN_3D(BaseGAN):
         self.max_diff_squared = torch.tensor(4.0, device=self.device)  # HR is in [-1, 1]
         self.epsilon_PSNR = torch.tensor(1e-8, device=self.device)
         self.feature_extractor = None
+        self._inflight = []  # CUDA events of the last training steps (bounded host run-ahead)
         self._D_requires_grad = None  # cached state of the D.parameters() requires_grad toggle
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
@@ -126,8 +127,9 @@ class wind_field_GAN_3D(BaseGAN):
             raise NotImplementedError(f"Only relativistic and relativisticavg GAN are implemented, not {t.gan_type}")
         self.criterion = nn.BCEWithLogitsLoss()
         if self.world_size > 1:
-            self.sync_G = GradSync(self.G.parameters())
-            self.sync_D = GradSync(self.D.parameters())
+            bucket = int(float(os.environ.get("WINDSR_BUCKET_MB", "25")) * (1 << 20))
+            self.sync_G = GradSync(self.G.parameters(), bucket_bytes=bucket)
+            self.sync_D = GradSync(self.D.parameters(), bucket_bytes=bucket)
 
     # ---------------------------------------------------------------------------------------------------
     def feed_xy_niter(self, x, y, niter, d_g_train_ratio, d_g_train_period):
@@ -314,6 +316,16 @@ class wind_field_GAN_3D(BaseGAN):
 
     def optimize_parameters(self, LR, HR, Z, it):
         self.compute_losses_and_optimize(LR, HR, Z, it, training_iteration=True)
+        # The step has no host synchronisation, so the host could run arbitrarily far ahead of the device.  Under
+        # data parallelism that let the ranks drift apart until the NCCL kernels of one rank spun on the other's
+        # backlog (measured: 100-170 ms stalls in ~1 of 6 steps at 2 GPUs).  Bound the run-ahead to two steps: wait
+        # for the step before the previous one — it has normally finished already, so this costs nothing.
+        if HR.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._inflight.append(ev)
+            if len(self._inflight) > 2:
+                self._inflight.pop(0).synchronize()
 
     def validation(self, LR, HR, Z, it):
         self.compute_losses_and_optimize(LR, HR, Z, it, training_iteration=False)

@@ -1,5 +1,7 @@
 // common.cuh — shared device helpers: tensor views, the fused epilogue, error plumbing.
 #pragma once
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -34,6 +36,44 @@ void count_launch(int n);
       return 2;                    \
     }                              \
   } while (0)
+
+// Launch with programmatic stream serialization (and optionally as clusters of `cluster_x` CTAs).  ONLY for
+// kernels that execute ptx::griddep_wait() before touching global memory a predecessor may still be writing.
+// WS_DISABLE_PDL=1 falls back to plain stream order.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("WS_DISABLE_PDL");
+    return !(v && v[0] && v[0] != '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Device-side copy of ws_tensor with typed accessors.
 struct View {

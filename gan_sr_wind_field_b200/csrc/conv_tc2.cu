@@ -88,6 +88,9 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int x0 = tile_ok ? txi * p.tx : p.DX + p.kx, y0 = tyi * p.by;
   const int n0 = blockIdx.y * p.n_tile;
 
+  // programmatic dependent launch: let the next kernel of the stream start its prologue as soon as every CTA of
+  // this grid is running; this kernel's own global-memory traffic starts after griddep_wait() below
+  if (threadIdx.x == 0) ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -119,6 +122,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // single issuing thread, not the tensor pipe, bounded the kernel.)
   if (warp == 0) {
     // ===== TMA producer =====
+    ptx::griddep_wait();  // the predecessor's activations / packed weights must be complete before the first load
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
     const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * 128u;
@@ -217,6 +221,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 2) {
     // ===== epilogue =====
     const int sub = warp & 3;
+    ptx::griddep_wait();  // residual reads / output writes also order after the predecessor
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
     const EpiVec ev = make_epi_vec(dst, ep);
@@ -559,20 +564,11 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   const unsigned tiles = (unsigned)(p.N * p.tiles_x * p.tiles_y);
   if (!pair) {
     dim3 grid(tiles, (unsigned)n_tiles);
-    conv3d_tc2_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, p, dst, ep);
+    WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<false>, grid, dim3(kThreads), smem, st, 1, tmA, tmB, p, dst, ep));
   } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((tiles + 1) / 2 * 2, 1, 1);  // pairs of adjacent tiles; an odd tail gets a padding CTA
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    WS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc2_kernel<true>, tmA, tmB, p, dst, ep));
+    // pairs of adjacent tiles; an odd tail gets a padding CTA
+    WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<true>, dim3((tiles + 1) / 2 * 2, 1, 1), dim3(kThreads), smem, st, 2, tmA,
+                             tmB, p, dst, ep));
   }
   WS_POST_LAUNCH(1);
   return 0;

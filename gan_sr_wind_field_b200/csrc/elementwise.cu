@@ -192,6 +192,9 @@ inline bool vec8_ok(const View& t, int c) {
 
 // y = a*x1 (+ b*x2), all channels-last, 8 channels per thread
 __global__ void axpby_cl8_kernel(View x1, float a, View x2, float b, View y, int c8, long long v, long long total) {
+  // programmatic dependent launch (common.cuh launch_pdl): start early, wait for the predecessor's data here
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % c8);
@@ -215,6 +218,8 @@ __global__ void axpby_cl8_kernel(View x1, float a, View x2, float b, View y, int
 // g = dy * lrelu'(y) [* chan_scale[n][c]] [* oscale[c]], all channels-last, 8 channels per thread
 __global__ void lrelu_bwd_cl8_kernel(View dy, View yv, float slope, const float* __restrict__ chan_scale,
                                      const float* __restrict__ oscale, View g, int c8, long long v, long long total) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % c8);
@@ -675,7 +680,8 @@ int copy_launch(const View& src, const View& dst, int n, int c, long long v, cud
                                                             src.vs / per, dst.vs / per);
   } else if (vec8_ok(src, c) && vec8_ok(dst, c)) {
     // channels-last both sides, converting dtype: the 8-channel axpby kernel with a = 1 (exact)
-    axpby_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(src, 1.f, View(), 0.f, dst, c / 8, v, total / 8);
+    WS_CHECK_CUDA(launch_pdl(axpby_cl8_kernel, dim3(grid_for(total / 8)), dim3(kBlock), 0, st, 1, src, 1.f, View(), 0.f,
+                             dst, c / 8, v, total / 8));
   } else {
     copy_kernel<<<grid_for(total), kBlock, 0, st>>>(src, dst, n, c, v, c_fastest_of(dst));
   }
@@ -688,7 +694,8 @@ int axpby_launch(const View& x1, float a, const View& x2, float b, const View& y
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
   if (vec8_ok(x1, c) && vec8_ok(x2, c) && vec8_ok(y, c)) {
-    axpby_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(x1, a, x2, b, y, c / 8, v, total / 8);
+    WS_CHECK_CUDA(launch_pdl(axpby_cl8_kernel, dim3(grid_for(total / 8)), dim3(kBlock), 0, st, 1, x1, a, x2, b, y, c / 8,
+                             v, total / 8));
     WS_POST_LAUNCH(1);
     return 0;
   }
@@ -702,8 +709,8 @@ int lrelu_bwd_launch(const View& dy, const View& yv, float slope, const float* c
   long long total = (long long)n * c * v;
   if (total <= 0) return 0;
   if (vec8_ok(dy, c) && vec8_ok(yv, c) && vec8_ok(g, c)) {
-    lrelu_bwd_cl8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dy, yv, slope, chan_scale, oscale, g, c / 8, v,
-                                                                total / 8);
+    WS_CHECK_CUDA(launch_pdl(lrelu_bwd_cl8_kernel, dim3(grid_for(total / 8)), dim3(kBlock), 0, st, 1, dy, yv, slope,
+                             chan_scale, oscale, g, c / 8, v, total / 8));
     WS_POST_LAUNCH(1);
     return 0;
   }

@@ -194,6 +194,14 @@ __device__ __forceinline__ void mma_commit2(uint32_t bar) {
       : "memory");
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running; griddep_wait() blocks until that predecessor has completed and its writes are visible,
+// so everything before it (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.
+// griddep_launch() lets the successor start launching once every CTA of this grid has issued it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- descriptors ----------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (SWIZZLE_128B): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | base_offset [49,52) | layout_type=2 [61,64).

@@ -87,6 +87,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   const long long tile_lo = (long long)split * p.tiles_per_split;
   const long long tile_hi = min(p.total_tiles, tile_lo + p.tiles_per_split);
 
+  if (threadIdx.x == 0) ptx::griddep_launch();  // programmatic dependent launch, see conv_tc2.cu
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmM);
     ptx::prefetch_tmap(&tmN);
@@ -110,6 +111,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
 
   // Both loops run warp-uniformly and elect one lane only around UTMALDG / UTCHMMA (see conv_tc2.cu).
   if (warp == 0) {
+    ptx::griddep_wait();
     if (has_work) {
       // ===== TMA producer =====
       int as = 0, bs = 0;
@@ -195,6 +197,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     // ===== epilogue: TMEM -> red.global.add into the fp32 workspace =====
     const int sub = warp & 3;
     const int m = sub * 32 + lane;
+    ptx::griddep_wait();  // the workspace memset / earlier reductions precede the atomics
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
     for (int tp = 0; tp < ntap; ++tp) {
@@ -392,8 +395,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
   dim3 grid((unsigned)p.tap_groups, (unsigned)splits, (unsigned)mz);
-  if (!swap) wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_dy, tm_x, p, wsp);
-  else wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_dy, p, wsp);
+  if (!swap) WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_dy, tm_x, p, wsp));
+  else WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_x, tm_dy, p, wsp));
   WS_POST_LAUNCH(1);
   return 0;
 }

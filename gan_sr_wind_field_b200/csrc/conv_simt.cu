@@ -461,6 +461,8 @@ __global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, 
 // 8 channels of group q over rows r, r + R, ...; partials meet in shared memory, one atomic per channel per block.
 __global__ void __launch_bounds__(256)
 bias_grad_cl8_kernel(View dy, float* __restrict__ db, int c8, long long v, long long rows_total, long long rows_per_block) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float red[256][9];
   const int q = threadIdx.x % c8, r = threadIdx.x / c8, R = blockDim.x / c8;
   const long long beg = (long long)blockIdx.x * rows_per_block;
@@ -783,7 +785,8 @@ int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumula
       if (blocks > 148 * 4) blocks = 148 * 4;
       const long long rpb = (total + blocks - 1) / blocks;
       blocks = (total + rpb - 1) / rpb;
-      bias_grad_cl8_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, db, c / 8, v, total, rpb);
+      WS_CHECK_CUDA(launch_pdl(bias_grad_cl8_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, dy, db, c / 8, v, total,
+                               rpb));
       WS_POST_LAUNCH(1);
       return 0;
     }

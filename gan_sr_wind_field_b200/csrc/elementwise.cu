@@ -76,6 +76,8 @@ struct PackTable {
   PackEntry e[WS_RDB_MAX_CONVS + 1];
 };
 __global__ void pack_tc_multi(const PackTable t) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const PackEntry& e = t.e[blockIdx.y];
   const float* __restrict__ w = e.w;
   __nv_bfloat16* __restrict__ p = e.p;
@@ -658,7 +660,7 @@ int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dg
   }
   int bx = (int)((most + kBlock - 1) / kBlock);
   if (bx > 148 * 2) bx = 148 * 2;
-  pack_tc_multi<<<dim3((unsigned)bx, (unsigned)n), kBlock, 0, st>>>(t);
+  WS_CHECK_CUDA(launch_pdl(pack_tc_multi, dim3((unsigned)bx, (unsigned)n), dim3(kBlock), 0, st, 1, t));
   WS_POST_LAUNCH(1);
   return 0;
 }

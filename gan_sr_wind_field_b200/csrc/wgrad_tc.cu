@@ -403,6 +403,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
 
 __global__ void wgrad_tc_finalize(const float* __restrict__ wsp, float* __restrict__ dw, int taps, int cin,
                                   int cout, int accumulate, int cin_major) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // wsp [tap][co][ci] (cin_major == 0) or [tap][ci][co] (cin_major == 1) -> dw [co][ci][tap]
   long long total = (long long)taps * cin * cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -432,7 +434,8 @@ int tc_conv_wgrad(const ConvGeom& g, const View& x, const View& dy, float* dw, i
   long long total = (long long)g.taps() * g.cin * g.cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_tc_finalize<<<blocks, 256, 0, st>>>(wsp, dw, g.taps(), g.cin, g.cout, accumulate, swap ? 0 : 1);
+  WS_CHECK_CUDA(launch_pdl(wgrad_tc_finalize, dim3(blocks), dim3(256), 0, st, 1, wsp, dw, g.taps(), g.cin, g.cout,
+                           accumulate, swap ? 0 : 1));
   WS_POST_LAUNCH(1);
   return 0;
 }
@@ -451,6 +454,8 @@ struct RdbSlices {
 };
 __global__ void wgrad_tc_finalize_rdb(const float* __restrict__ wsp, const RdbSlices t, int taps, int gc, int wcin,
                                       int wcout) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // wsp [tap][i*gc + co][ci] -> dw_i [co][ci][tap]
   const int i = blockIdx.y;
   if (i >= t.nconv || !t.dw[i]) return;
@@ -492,8 +497,8 @@ int tc_rdb_wgrad(const ConvGeom& gm, const View& x, const View& g, float* const*
   }
   int blocks = (int)((most + 255) / 256);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  wgrad_tc_finalize_rdb<<<dim3((unsigned)blocks, (unsigned)nconv), 256, 0, st>>>(wsp, t, gm.taps(), gc, gm.cin,
-                                                                                  gm.cout);
+  WS_CHECK_CUDA(launch_pdl(wgrad_tc_finalize_rdb, dim3((unsigned)blocks, (unsigned)nconv), dim3(256), 0, st, 1, wsp, t,
+                           gm.taps(), gc, gm.cin, gm.cout));
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -187,19 +187,43 @@ def run_native(args):
     # the usual logging pattern of a training loop: the loss of step i is copied to pinned memory right after the
     # step is enqueued and consumed (event wait + float) while step i+1 runs; the last one is drained inside the
     # timed region by the closing synchronize.
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    LAG = 2  # the host consumes the loss of step i - LAG while step i is enqueued (bounded run-ahead, as in the step)
+    loss_host = torch.zeros(LAG + 1, dtype=torch.float32).pin_memory()
+    loss_ready = [torch.cuda.Event() for _ in range(LAG + 1)]
     loss_log = []
+    # Input pipeline of the e2e leg: the batch of step i+1 is copied from pinned host memory into the other of two
+    # device staging buffers on a copy stream while step i computes (the usual prefetch-to-device pattern); every
+    # step's H2D copy is issued inside the timed region.  A copy on the compute stream itself exposed the step to
+    # PCIe hiccups of this shared host (sporadic 40-120 ms stalls in half of the runs).
+    copy_stream = torch.cuda.Stream()
+    stage = [[torch.empty_like(v, device=dev) for v in host] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(k):
+        buf = k % 2
+        copy_stream.wait_event(freed[buf])  # the step that last read this buffer has finished
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(stage[buf], host):
+                dst.copy_(src, non_blocking=True)
+            ready[buf].record()
 
     def step_e2e(i):
-        lr, hr, z = (v.to(dev, non_blocking=True) for v in host)
+        if i == 0:
+            issue_copy(0)
+        buf = i % 2
+        torch.cuda.current_stream().wait_event(ready[buf])
+        lr, hr, z = stage[buf]
         gan.optimize_parameters(lr, hr, z, 1 + i)
-        slot = i & 1
+        freed[buf].record()
+        issue_copy(i + 1)  # prefetch the next batch behind this step's kernels
+        slot = i % (LAG + 1)
         loss_host[slot:slot + 1].copy_(gan.get_G_train_loss_dict_ref()["total"].detach().reshape(1), non_blocking=True)
         loss_ready[slot].record()
-        if i > 0:
-            loss_ready[slot ^ 1].synchronize()
-            loss_log.append(float(loss_host[slot ^ 1]))
+        if i >= LAG:
+            old = (i - LAG) % (LAG + 1)
+            loss_ready[old].synchronize()
+            loss_log.append(float(loss_host[old]))
 
     for i in range(args.warmup):
         step_resident(i)
@@ -211,7 +235,10 @@ def run_native(args):
         if prev is not None and abs(cur - prev) <= 0.03 * prev:
             break
         prev = cur
-    for i in range(2):
+    # pre-roll: ~0.6 s of back-to-back steps before the first timed leg.  The settle loop above synchronises after
+    # every step, so the first CONTINUOUS run of steps used to start inside the timed region — and 40-130 ms stalls
+    # showed up 3-4 steps (~0.2 s) into it in half of the runs (never in the later legs).
+    for i in range(10):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     if not all(math.isfinite(v) for v in loss_log):
@@ -291,7 +318,7 @@ def run_native(args):
         "e2e": {"value": vox / (ms_e2e / args.steps * 1e-3), "unit": "HR voxels/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
-                "loss_read": "async D2H into pinned memory every step, consumed on the host one step later"},
+                "loss_read": "async D2H into pinned memory every step, consumed on the host two steps later"},
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": {"bound": "tensor", "kernel": "conv3d_tc2_kernel<true> (hr_convs.0 fwd, 5x5x5 144->144 @128x128x10, B=8)",

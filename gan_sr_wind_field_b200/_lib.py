@@ -71,7 +71,8 @@ SYMBOLS = [
     ("ws_conv3d_wgrad", _I, [_SP, _TP, _TP, _P, _P, _I, _I, _P, _Z, _P]),
     ("ws_rdb_packed_bytes", _Z, [C.POINTER(WsRdbDesc), _I, _I]),
     ("ws_rdb_backward_workspace_bytes", _Z, [C.POINTER(WsRdbDesc)]),
-    ("ws_rdb_forward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P, _P]),
+    ("ws_rdb_forward_workspace_bytes", _Z, [C.POINTER(WsRdbDesc)]),
+    ("ws_rdb_forward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P, _P, _Z, _P]),
     ("ws_rdb_backward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P),
                              C.POINTER(_P), _P, _P, _Z, _P]),
     ("ws_upsample_nearest_xy_fwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),

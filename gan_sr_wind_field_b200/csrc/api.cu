@@ -47,7 +47,8 @@ int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&,
 bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
-int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t);
+int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t, const int*);
+int xfold_sum_lrelu_launch(const View&, const View&, float, int, int, int, int, int, int, int, cudaStream_t);
 int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
                  cudaStream_t);
 size_t tc_rdb_wgrad_workspace_bytes(int, int, int, int);
@@ -431,10 +432,11 @@ ws_conv_shape rdb_merged_shape(const ws_rdb_desc* d) {
 // act: the operand view whose layout decides the path of the dense convs' / LFF's input (forward: the concat buffer;
 // backward: g_lff for the LFF and a gc-channel slice of gbuf for the dense convs).
 int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act, const ws_tensor* dense_act,
-               const float* const* w, void* const* packed, int dgrad, cudaStream_t st) {
+               const float* const* w, void* const* packed, int dgrad, cudaStream_t st, bool fold_fwd = false) {
   const float* bw[WS_RDB_MAX_CONVS + 1];
   void* bp[WS_RDB_MAX_CONVS + 1];
   ConvGeom bg[WS_RDB_MAX_CONVS + 1] = {};
+  int bf[WS_RDB_MAX_CONVS + 1] = {};
   int nb = 0;
   for (int i = 0; i <= d->nconv; ++i) {
     const ws_conv_shape* s = i < d->nconv ? &r.dense[i] : &r.lff;
@@ -449,12 +451,30 @@ int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act,
       tc = dgrad_path(g, View(lff_act), d->math) == WS_PATH_TCGEN05;
     }
     if (tc) {
-      bw[nb] = w[i]; bp[nb] = packed[i]; bg[nb] = g; ++nb;
+      bw[nb] = w[i]; bp[nb] = packed[i]; bg[nb] = g; bf[nb] = (fold_fwd && !dgrad && i < d->nconv) ? 1 : 0; ++nb;
     } else if (int e = pack_weights_launch(w[i], g, dgrad ? WS_PACK_SIMT_DGRAD : WS_PACK_SIMT_FWD, packed[i], st)) {
       return e;
     }
   }
-  return pack_tc_batch_launch(nb, bw, bg, dgrad, bp, st);
+  return pack_tc_batch_launch(nb, bw, bg, dgrad, bp, st, bf);
+}
+// x-folded forward of the dense convs: the kx taps go side by side on the UMMA N dimension (N = kx*gc = 96 instead of
+// 32 — an MMA costs the same 72 cycles either way), the conv runs as a (1,k,k) conv into an fp32 scratch U and a small
+// vector kernel forms y[x] = lrelu(sum_dx U[x+dx-p][dx]) into the concat-buffer slice.
+ws_conv_shape rdb_fold_shape(const ws_rdb_desc* d, int i) {
+  ws_conv_shape s = {d->n, d->x, d->y, d->z, d->f + i * d->gc, d->k * d->gc, 1, d->k, d->k, 1, 1, 1,
+                     0, (d->k - 1) / 2, (d->k - 1) / 2};
+  return s;
+}
+bool rdb_fold_ok(const ws_rdb_desc* d, const ws_tensor* buf) {
+  if (d->nconv < 1 || d->k < 2 || d->k * d->gc > 256 || d->gc % 8 != 0 || d->math != WS_MATH_BF16 ||
+      getenv("WS_DISABLE_RDB_XFOLD"))
+    return false;
+  for (int i = 0; i < d->nconv; ++i) {
+    ws_conv_shape s = rdb_fold_shape(d, i);
+    if (fwd_path(ConvGeom(s), View(buf), d->math) != WS_PATH_TCGEN05) return false;
+  }
+  return true;
 }
 bool rdb_merged_wgrad_ok(const ws_rdb_desc* d, const ws_tensor* buf, const ws_tensor* gbuf) {
   if (d->nconv < 2 || d->nconv * d->gc > 256 || d->gc % 16 != 0 || getenv("WS_DISABLE_RDB_MERGED_WGRAD")) return false;
@@ -462,6 +482,11 @@ bool rdb_merged_wgrad_ok(const ws_rdb_desc* d, const ws_tensor* buf, const ws_te
   return wgrad_path(ConvGeom(s), View(buf), View(gbuf), d->math) == WS_PATH_TCGEN05;
 }
 }  // namespace
+
+extern "C" size_t ws_rdb_forward_workspace_bytes(const ws_rdb_desc* d) {
+  if (!d || d->nconv < 1) return 0;
+  return (size_t)d->n * d->x * d->y * d->z * d->k * d->gc * sizeof(float);
+}
 
 extern "C" size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d) {
   RdbGeom r;
@@ -489,7 +514,8 @@ extern "C" size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int i, int dgrad) {
 
 extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* outer,
                               const ws_tensor* buf, const ws_tensor* out, const float* const* w,
-                              void* const* packed, const float* lff_bias, void* stream) {
+                              void* const* packed, const float* lff_bias, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   RdbGeom r;
   if (int e = rdb_geom(d, r)) return e;
   WS_REQUIRE(x && x->ptr && buf && buf->ptr && out && out->ptr && w && packed, "ws_rdb_forward: null pointer");
@@ -498,11 +524,22 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   // buf[:, :f] = x (cast to the activation dtype)
   ws_tensor b0 = *buf;
   if (int e = copy_launch(View(x), View(&b0), d->n, d->f, v, st)) return e;
+  const bool fold = workspace && workspace_bytes >= ws_rdb_forward_workspace_bytes(d) && rdb_fold_ok(d, buf);
   if (d->repack)
-    if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st)) return e;
+    if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st, fold)) return e;
   for (int i = 0; i < d->nconv; ++i) {
     const ws_conv_shape* s = &r.dense[i];
     ws_tensor in = *buf, o = slice(*buf, s->cin);
+    if (fold) {
+      ws_conv_shape fs = rdb_fold_shape(d, i);
+      ws_tensor u = {workspace, WS_F32, 0, v * fs.cout, fs.cout, 1};
+      ws_epilogue ep = plain_epilogue();
+      if (int e = ws_conv3d_fwd(&fs, &in, packed[i], &u, &ep, d->math, stream)) return e;
+      if (int e = xfold_sum_lrelu_launch(View(&u), View(&o), d->slope, d->n, d->gc, d->k, (d->k - 1) / 2, d->x, d->y,
+                                         d->z, st))
+        return e;
+      continue;
+    }
     ws_epilogue ep = plain_epilogue();
     ep.lrelu_slope = d->slope;
     if (int e = ws_conv3d_fwd(s, &in, packed[i], &o, &ep, d->math, stream)) return e;

@@ -70,6 +70,7 @@ struct PackEntry {
   const float* w;
   __nv_bfloat16* p;
   int cout, cin, taps, rows_pad, cols_pad, dgrad;
+  int fold;  // > 0: x-fold forward packing — `fold` = kx taps side by side on the rows: p[(ky,kz)][dx*cout+co][ci]
 };
 struct PackTable {
   int n;
@@ -89,7 +90,11 @@ __global__ void pack_tc_multi(const PackTable t) {
     const int row = (int)(r % e.rows_pad);
     const int tp = (int)(r / e.rows_pad);
     float v = 0.f;
-    if (!e.dgrad) {
+    if (e.fold) {
+      // e.taps = ky*kz here; the full kernel has fold*e.taps taps, ordered (kx, ky, kz)
+      const int dx = row / e.cout, co = row - dx * e.cout;
+      if (dx < e.fold && col < e.cin) v = w[((long long)co * e.cin + col) * (e.fold * e.taps) + dx * e.taps + tp];
+    } else if (!e.dgrad) {
       if (row < e.cout && col < e.cin) v = w[((long long)row * e.cin + col) * e.taps + tp];
     } else {
       if (row < e.cin && col < e.cout) v = w[((long long)col * e.cin + row) * e.taps + (e.taps - 1 - tp)];
@@ -459,6 +464,36 @@ __global__ void xunfold_kernel(View dout, View u, int n, int co, int kx, int pad
   }
 }
 
+// y[x] = lrelu(sum_dx U[x + dx - pad][dx*co + c]) for a channels-last fp32 U and output, 8 channels per thread:
+// the tail of the x-folded dense convs of a residual dense block (api.cu: ws_rdb_forward)
+__global__ void xfold_sum_lrelu_cl8(View u, View out, float slope, int co8, int co, int kx, int pad, int X, int Y, int Z,
+                                    long long total) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const long long V = (long long)X * Y * Z;
+  const long long sx = (long long)Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % co8);
+    const long long r = i / co8;
+    const long long v = r % V;
+    const int nn = (int)(r / V);
+    const int xx = (int)(v / sx);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int dx = 0; dx < kx; ++dx) {
+      const int xs = xx + dx - pad;
+      if (xs < 0 || xs >= X) continue;
+      float f[8];
+      ld8(u, u.off(nn, dx * co + q * 8, v + (long long)(dx - pad) * sx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : slope * acc[j];
+    st8(out, out.off(nn, q * 8, v), acc);
+  }
+}
+
 // same, u channels-last with cpad % 8 == 0: one 8-channel vector store per thread
 __global__ void xunfold_st8_kernel(View dout, View u, int co, int kx, int pad, int cpad8, int X, int Y, int Z,
                                    long long total) {
@@ -642,7 +677,7 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
 
 // stride-1 tensor-core packings of up to WS_RDB_MAX_CONVS + 1 convs in one launch
 int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dgrad, void* const* packed,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int* fold) {
   if (n <= 0) return 0;
   WS_REQUIRE(n <= WS_RDB_MAX_CONVS + 1, "pack_tc_batch: too many entries");
   PackTable t;
@@ -655,6 +690,11 @@ int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dg
     e.cout = g[i].cout; e.cin = g[i].cin; e.taps = g[i].taps(); e.dgrad = dgrad;
     e.rows_pad = dgrad ? (g[i].cin + 15) / 16 * 16 : (g[i].cout + 15) / 16 * 16;
     e.cols_pad = dgrad ? (g[i].cout + 7) / 8 * 8 : (g[i].cin + 7) / 8 * 8;
+    if (fold && fold[i] > 0 && !dgrad) {
+      e.fold = g[i].kx;
+      e.taps = g[i].ky * g[i].kz;
+      e.rows_pad = (g[i].kx * g[i].cout + 15) / 16 * 16;
+    }
     const long long total = (long long)e.taps * e.rows_pad * e.cols_pad;
     if (total > most) most = total;
   }
@@ -761,6 +801,17 @@ int xfold_sum_launch(const View& y, const float* bias, const View& out, int n, i
   long long total = (long long)n * co * X * Y * Z;
   if (total <= 0) return 0;
   xfold_sum_kernel<<<grid_for(total), kBlock, 0, st>>>(y, bias, out, n, co, kx, pad, X, Y, Z);
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+int xfold_sum_lrelu_launch(const View& u, const View& out, float slope, int n, int co, int kx, int pad, int X, int Y,
+                           int Z, cudaStream_t st) {
+  const long long total = (long long)n * X * Y * Z * (co / 8);
+  if (total <= 0) return 0;
+  WS_REQUIRE(vec8_ok(u, co) && vec8_ok(out, co), "xfold_sum_lrelu: operands must be 8-channel vectorisable");
+  WS_CHECK_CUDA(launch_pdl(xfold_sum_lrelu_cl8, dim3(grid_for(total)), dim3(kBlock), 0, st, 1, u, out, slope, co / 8, co,
+                           kx, pad, X, Y, Z, total));
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -574,8 +574,10 @@ class RDBFn(torch.autograd.Function):
         xv, bv, ov = view(x), view(buf), view(out)
         outer_v = view(outer) if outer is not None else null_view()
         wd = [p.detach() for p in params[:nconv + 1]]
+        wsp = _workspace(int(lib.ws_rdb_forward_workspace_bytes(C.byref(desc))), x.device)
         check(lib.ws_rdb_forward(C.byref(desc), C.byref(xv), C.byref(outer_v), C.byref(bv), C.byref(ov),
-                                 _ptr_array(wd), _ptr_array(packed), ptr(b_lff), stream_ptr()), "ws_rdb_forward")
+                                 _ptr_array(wd), _ptr_array(packed), ptr(b_lff), wsp.data_ptr(), wsp.numel(),
+                                 stream_ptr()), "ws_rdb_forward")
         ctx.cfg = cfg
         ctx.desc_args = (n, X, Y, Z, f, gc, nconv, k, kl)
         ctx.has_outer = outer is not None

@@ -154,9 +154,13 @@ size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int conv_index /* 0..nconv-1 de
 /* x: fp32 trunk state (n,f,..); outer: optional fp32 (RRDB input); buf: (n, f+nconv*gc, ..) activation-dtype
  * concat buffer (filled here, saved for backward); out: fp32 (n,f,..).
  * w[i]: torch-layout fp32 weights, packed[i]: device buffers of ws_rdb_packed_bytes(i, 0). */
+/* workspace (optional, ws_rdb_forward_workspace_bytes): fp32 scratch of the x-folded dense convs — with it the
+ * tensor-core path runs each k^3 dense conv as a (1,k,k) conv with the kx taps side by side on N (3x fewer MMAs)
+ * plus a shifted sum + LeakyReLU pass; without it (NULL) the convs run in their direct form. */
+size_t ws_rdb_forward_workspace_bytes(const ws_rdb_desc* d);
 int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* outer, const ws_tensor* buf,
                    const ws_tensor* out, const float* const* w, void* const* packed, const float* lff_bias,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
 /* bytes of the `workspace` ws_rdb_backward needs */
 size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d);
 /* dy: fp32 gradient of `out`.  Scratch: dbuf fp32 (n, f+nconv*gc, ..), g_lff activation-dtype (n,f,..),

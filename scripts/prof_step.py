@@ -13,26 +13,32 @@ from gan_sr_wind_field_b200.synthetic import make_batch
 
 dev = torch.device("cuda:0")
 ops.set_precision("bf16")
+# usage: prof_step.py [g|d]   (d: the D step of the full GAN schedule, BASELINE config #3)
+WHICH = sys.argv[1] if len(sys.argv) > 1 else "g"
 cfg = Config(bench.INI)
 cfg.is_train, cfg.gpu_id, cfg.device = True, 0, dev
+if WHICH == "d":
+    cfg.training.adversarial_loss_weight = 0.0005
+    cfg.training.d_g_train_ratio, cfg.training.d_g_train_period = 1, 1
 torch.manual_seed(2001)
 gan = wind_field_GAN_3D(cfg)
 LR, HR, Z, x, y = make_batch(8, 128, 10, 8, seed=2001, device=dev)
 t = cfg.training
 gan.feed_xy_niter(x, y, torch.tensor(t.niter, device=dev), t.d_g_train_ratio, t.d_g_train_period)
-for i in range(3):
-    gan.optimize_parameters(LR, HR, Z, 1 + i)
+IT = 5 if WHICH == "d" else 4   # with period 1 / ratio 1 odd iterations are D steps
+for i in range(4):
+    gan.optimize_parameters(LR, HR, Z, i)
 torch.cuda.synchronize()
 import time
 for i in range(3):
     t0 = time.perf_counter()
-    gan.optimize_parameters(LR, HR, Z, 4)
+    gan.optimize_parameters(LR, HR, Z, IT)
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print(f"step: CPU enqueue {1e3*(t1-t0):.1f} ms (includes the one host read before backward), total {1e3*(t2-t0):.1f} ms")
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    gan.optimize_parameters(LR, HR, Z, 5)
+    gan.optimize_parameters(LR, HR, Z, IT)
     torch.cuda.synchronize()
 path = os.path.join(ROOT, "gpurun_out", "step_trace.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)
@@ -58,5 +64,5 @@ rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
 for (name, grid), (n, us) in rows[:45]:
     print(f"{name:42s} {str(grid):18s} n={n:4d} {us/1e3:8.3f} ms {100*us/tot:5.1f}%")
 json.dump([dict(kernel=k[0], grid=list(k[1]), launches=v[0], ms=v[1] / 1e3) for k, v in rows],
-          open(os.path.join(ROOT, "gpurun_out", "step_kernels.json"), "w"), indent=1)
+          open(os.path.join(ROOT, "gpurun_out", "step_kernels.json" if WHICH == "g" else "dstep_kernels.json"), "w"), indent=1)
 os.remove(path)

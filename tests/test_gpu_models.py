@@ -325,3 +325,26 @@ def test_packed_weights_follow_fused_optimizer(mode):
             y2 = fresh(x).float()
     assert rel_l2(y1, y0.detach().float()) > 1e-3  # the step moved the output
     assert rel_l2(y1, y2) <= 1e-6  # and the cached operands saw it
+
+
+@pytest.mark.gpu
+def test_full_size_upscale16_generator_vs_oracle():
+    """BASELINE.json config #4 shapes: the shipped upscale16 architecture (one more UpConv stage), LR (1,4,8,8,10) ->
+    SR (1,3,128,128,10), bf16, against the CPU oracle with the same weights."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    from gan_sr_wind_field_b200.tools import initialization
+    from oracle import wind_oracle as wo
+    torch.manual_seed(2001)
+    G = Generator_3D(4, 3, 128, 16, upscale=16, hr_kern_size=5, lff_kern_size=1, dropout_probability=0.1)
+    initialization.init_weights(G, 0.1)
+    G.eval()
+    LR, HR, Z, x, y = wo.synthetic_batch(1, hr_xy=128, nz=10, scale=16, seed=2001)
+    assert LR.shape == (1, 4, 8, 8, 10)
+    with torch.no_grad():
+        ref = wo.generator_forward(G.state_dict(), LR, Z)
+    G.cuda()
+    with ops.precision("bf16"), torch.no_grad():
+        out = G(LR.cuda(), Z.cuda())
+    assert out.shape == (1, 3, 128, 128, 10)
+    assert rel_l2(out, ref) <= TOL["bf16"]

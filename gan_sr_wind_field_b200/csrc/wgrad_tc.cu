@@ -41,7 +41,8 @@ struct WgParams {
   int bx, by, bz, rows;  // voxel tile (in OUTPUT / dy coordinates); rows % 16 == 0
   int tiles_x, tiles_y, tiles_z;
   long long total_tiles;       // N * tiles
-  long long tiles_per_split;
+  long long items;             // tap_groups * total_tiles: the (tap group, voxel tile) work items of one M block
+  long long items_per_cta;     // each CTA takes a contiguous run of items -> one or more (tap group, tile range) segments
   int kx, ky, kz, sx, sy, sz, px, py, pz;
   int taps, taps_per_cta, tap_groups;
   int m_total;           // channels of the M operand covered by this launch (grid.z blocks of 128)
@@ -72,20 +73,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   auto b_full = [&](int s) { return bar_base + 8u * (4 + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (4 + kMaxBSlots + s); };
   const uint32_t accum_bar = bar_base + 8u * (4 + 2 * kMaxBSlots);
-  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * kMaxBSlots);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (5 + 2 * kMaxBSlots));
+  const uint32_t tmem_free = bar_base + 8u * (5 + 2 * kMaxBSlots);
+  const uint32_t tmem_slot = bar_base + 8u * (6 + 2 * kMaxBSlots);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (6 + 2 * kMaxBSlots));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = p.m0 + (int)blockIdx.z * 128;                       // this CTA's 128-row M block
   const int m_valid = min(128, p.m_total - (int)blockIdx.z * 128);
   const int m_blocks = (m_valid + 63) / 64;
-  const int tap_group = blockIdx.x;
-  const int split = blockIdx.y;
-  const int tap_lo = tap_group * p.taps_per_cta;
-  const int tap_hi = min(p.taps, tap_lo + p.taps_per_cta);
-  const int ntap = tap_hi - tap_lo;
-  const long long tile_lo = (long long)split * p.tiles_per_split;
-  const long long tile_hi = min(p.total_tiles, tile_lo + p.tiles_per_split);
+  // Work = (tap group, voxel tile) items in group-major order; CTA b owns items [b*per, (b+1)*per): the same load
+  // for every CTA however taps and tiles divide (hr_convs.0: 63 groups x 2 splits left 22 of 148 SMs idle).  A run
+  // that crosses a group boundary is processed as consecutive SEGMENTS, each with its own accumulate / reduce phase.
+  const long long item_lo = (long long)blockIdx.x * p.items_per_cta;
+  const long long item_hi = min(p.items, item_lo + p.items_per_cta);
 
   if (threadIdx.x == 0) ptx::griddep_launch();  // programmatic dependent launch, see conv_tc2.cu
   if (warp == 0 && lane == 0) {
@@ -94,6 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_slots; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
     ptx::mbar_init(accum_bar, 1);
+    ptx::mbar_init(tmem_free, 4);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -104,7 +105,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const bool has_work = tile_hi > tile_lo && ntap > 0;
+  const bool has_work = item_hi > item_lo;
 
   const uint32_t blk_bytes = (uint32_t)p.rows * 128u;  // one 64-channel block of one voxel tile
   const int tiles_per_n = p.tiles_x * p.tiles_y * p.tiles_z;
@@ -123,7 +124,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       const int sh_blocks = p.shift_on_m ? m_blocks : p.n_blocks;
       const int fix_c0 = p.shift_on_m ? p.n0 : m0;
       const int sh_c0 = p.shift_on_m ? m0 : p.n0;
-      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+      for (long long item = item_lo; item < item_hi; ++item) {
+        const long long tile = item % p.total_tiles;
+        const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+        const int tap_hi = min(p.taps, tap_lo + p.taps_per_cta);
         int t = (int)(tile % tiles_per_n);
         const int n = (int)(tile / tiles_per_n);
         const int tz = t % p.tiles_z; t /= p.tiles_z;
@@ -163,7 +167,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       uint32_t aph = 0, bph = 0;
       const int k16 = p.rows / 16;
       uint32_t acc_tile = 0;
-      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
+      int seg = 0;
+      for (long long item = item_lo; item < item_hi; ++item) {
+        const long long tile = item % p.total_tiles;
+        const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+        const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+        if (item > item_lo && tile == 0) {
+          // group boundary: hand the finished accumulators to the epilogue, then wait until it has drained them
+          if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+          __syncwarp();
+          ptx::mbar_wait(tmem_free, (uint32_t)(seg & 1));
+          ptx::tc_fence_after();
+          ++seg;
+          acc_tile = 0;
+        }
         ptx::mbar_wait(a_full(as), aph);
         const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
         for (int tp = 0; tp < ntap; ++tp) {
@@ -194,26 +211,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       __syncwarp();
     }
   } else if (has_work) {
-    // ===== epilogue: TMEM -> red.global.add into the fp32 workspace =====
+    // ===== epilogue: TMEM -> red.global.add into the fp32 workspace, once per segment =====
     const int sub = warp & 3;
     const int m = sub * 32 + lane;
     ptx::griddep_wait();  // the workspace memset / earlier reductions precede the atomics
-    ptx::mbar_wait(accum_bar, 0);
-    ptx::tc_fence_after();
-    for (int tp = 0; tp < ntap; ++tp) {
-      const int tap = tap_lo + tp;
-      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
-        if (c0 >= p.n_valid) break;
-        uint32_t r[16];
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tp * p.n_umma + c0), r);
-        ptx::tmem_ld_wait();
-        if (m < m_valid) {
-          float* dst = wsp + (long long)tap * p.tap_stride + (long long)(m0 + m) * p.m_stride +
-                       (long long)(p.n0 + c0) * p.n_stride;
+    int seg = 0;
+    for (long long item = item_lo; item < item_hi; ++seg) {
+      const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+      const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+      const long long seg_end = min(item_hi, (item / p.total_tiles + 1) * p.total_tiles);
+      ptx::mbar_wait(accum_bar, (uint32_t)(seg & 1));
+      ptx::tc_fence_after();
+      for (int tp = 0; tp < ntap; ++tp) {
+        const int tap = tap_lo + tp;
+        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+          if (c0 >= p.n_valid) break;
+          uint32_t r[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tp * p.n_umma + c0), r);
+          ptx::tmem_ld_wait();
+          if (m < m_valid) {
+            float* dst = wsp + (long long)tap * p.tap_stride + (long long)(m0 + m) * p.m_stride +
+                         (long long)(p.n0 + c0) * p.n_stride;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.n_valid) atomicAdd(dst + (long long)j * p.n_stride, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.n_valid) atomicAdd(dst + (long long)j * p.n_stride, __uint_as_float(r[j]));
+          }
         }
+      }
+      item = seg_end;
+      if (item < item_hi) {  // more segments follow: release the accumulators
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_free);
       }
     }
     ptx::tc_fence_before();
@@ -304,8 +333,9 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
   WS_REQUIRE(p.b_slots >= 2, "wgrad: shared memory budget too small for 2 operand slots");
 
-  // Work split: tap groups x voxel-tile splits x M blocks.  Modelled cost per CTA =
-  //   tiles * taps_per_cta * max(MMA, L2->SMEM) + taps_per_cta * (128 x N red.global.add epilogue) + fixed,
+  // Work split: (tap group, voxel tile) items of an M block dealt out in equal contiguous runs to `ncta` CTAs
+  // (grid.x), M blocks in grid.z.  Modelled cost per CTA =
+  //   items * (taps_per_cta * max(MMA, L2->SMEM) + unshifted tile load) + segments * (reduce epilogue) + fixed,
   // MMA at the measured max(72, N/2) cycles per K=16 step.  Few taps per CTA keep the atomic epilogue short.
   const double per_mma = p.n_umma / 2.0 > 72.0 ? p.n_umma / 2.0 : 72.0;
   const double unit_mma = (p.rows / 16) * per_mma;
@@ -315,42 +345,43 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   const int max_tpc = 512 / p.n_umma;
   double best = 1e30;
   int best_tpc = 1;
-  long long best_tps = p.total_tiles;
+  long long best_ncta = 1;
   for (int tpc = 1; tpc <= max_tpc && tpc <= p.taps; ++tpc) {
     const int tg = (p.taps + tpc - 1) / tpc;
+    const long long items = (long long)tg * p.total_tiles;
     for (int target : {37, 74, 148, 296, 444}) {
-      long long splits = (target + (long long)tg * mz - 1) / ((long long)tg * mz);
-      if (splits > p.total_tiles) splits = p.total_tiles;
-      if (splits < 1) splits = 1;
-      const long long tps = (p.total_tiles + splits - 1) / splits;
-      const long long ctas = (long long)tg * mz * ((p.total_tiles + tps - 1) / tps);
+      long long ncta = target / mz;
+      if (ncta < 1) ncta = 1;
+      if (ncta > items) ncta = items;
+      const long long per = (items + ncta - 1) / ncta;
+      ncta = (items + per - 1) / per;
+      const long long ctas = ncta * mz;
       const long long waves = (ctas + 147) / 148;
-      // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many
-      // splits of a short K loop the sum over the CTAs of a wave, not one CTA's epilogue, is what is waited for
+      const double segs = 1.0 + (double)(per - 1) / (double)p.total_tiles + (per < p.total_tiles ? 1.0 : 0.0) * 0.5;
+      // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many CTAs on a
+      // short K loop the sum over a wave, not one CTA's epilogue, is what is waited for
       const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;
-      const double atom_chip = wave_ctas * tpc * 128.0 * p.n_umma / 512.0;
-      const double atom_t = tpc * atom > atom_chip ? tpc * atom : atom_chip;
-      const double t = (double)waves * (tps * (tpc * unit + (double)fix_alloc * blk / 33.0) + atom_t + 8000.0);
-      if (t < best) { best = t; best_tpc = tpc; best_tps = tps; }
+      const double atom_chip = wave_ctas * segs * tpc * 128.0 * p.n_umma / 512.0;
+      const double atom_t = segs * tpc * atom > atom_chip ? segs * tpc * atom : atom_chip;
+      const double t = (double)waves * (per * (tpc * unit + (double)fix_alloc * blk / 33.0) + atom_t + 8000.0);
+      if (t < best) { best = t; best_tpc = tpc; best_ncta = ncta; }
     }
   }
-  // experiment hook: WS_WGRAD_FORCE="taps_per_cta,splits" (read at every launch)
+  // experiment hook: WS_WGRAD_FORCE="taps_per_cta,ctas" (read at every launch)
   if (const char* f = getenv("WS_WGRAD_FORCE")) {
-    int ftpc = 0, fsplits = 0;
-    if (sscanf(f, "%d,%d", &ftpc, &fsplits) == 2 && ftpc >= 1 && ftpc <= max_tpc && fsplits >= 1) {
+    int ftpc = 0, fcta = 0;
+    if (sscanf(f, "%d,%d", &ftpc, &fcta) == 2 && ftpc >= 1 && ftpc <= max_tpc && fcta >= 1) {
       best_tpc = ftpc;
-      best_tps = (p.total_tiles + fsplits - 1) / fsplits;
+      best_ncta = fcta;
     }
   }
   p.taps_per_cta = best_tpc;
   p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
-  p.tiles_per_split = best_tps;
-  long long splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  if (splits > 65535) {
-    splits = 65535;
-    p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
-    splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  }
+  p.items = (long long)p.tap_groups * p.total_tiles;
+  if (best_ncta > p.items) best_ncta = p.items;
+  if (best_ncta > 65535LL * 32) best_ncta = 65535LL * 32;
+  p.items_per_cta = (p.items + best_ncta - 1) / best_ncta;
+  const long long ncta = (p.items + p.items_per_cta - 1) / p.items_per_cta;
   uint32_t cols = 32;
   while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
@@ -386,7 +417,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   if (int e = make_map(x, g.cin, g.x, g.y, g.z, true, &tm_x)) return e;
   if (int e = make_map(dy, g.cout, g.xo, g.yo, g.zo, false, &tm_dy)) return e;
 
-  size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 8 * (6 + 2 * kMaxBSlots) + 1024;
+  size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 8 * (7 + 2 * kMaxBSlots) + 1024;
   static std::once_flag* once = new std::once_flag;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(*once, [] {
@@ -394,7 +425,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
-  dim3 grid((unsigned)p.tap_groups, (unsigned)splits, (unsigned)mz);
+  dim3 grid((unsigned)ncta, 1u, (unsigned)mz);
   if (!swap) WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_dy, tm_x, p, wsp));
   else WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_x, tm_dy, p, wsp));
   WS_POST_LAUNCH(1);

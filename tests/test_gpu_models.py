@@ -348,3 +348,43 @@ def test_full_size_upscale16_generator_vs_oracle():
         out = G(LR.cuda(), Z.cuda())
     assert out.shape == (1, 3, 128, 128, 10)
     assert rel_l2(out, ref) <= TOL["bf16"]
+
+
+@pytest.mark.gpu
+def test_trunk_size_rrdb_forward_backward_vs_oracle():
+    """One RRDB at the shipped trunk size (128 features, gc 32, 4 dense convs + LFF per RDB, 16x16x10 volume, B=2)
+    in bf16: forward (x-folded dense convs), dL/dx and every parameter gradient (merged dense-conv weight gradient)
+    against the CPU oracle in fp32, each bounded by the intrinsic bf16-operand envelope measured on the CPU."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.torch_blocks import RRDB
+    from oracle import wind_oracle as wo
+    from tests.util import bf16_operand_emulation
+    torch.manual_seed(11)
+    blk = RRDB(128, 32, 5, 1, lrelu_negative_slope=0.2, RDB_residual_scaling=0.2, RRDB_residual_scaling=0.2, mode="3D")
+    x = torch.randn(2, 128, 16, 16, 10)
+    gy = torch.randn(2, 128, 16, 16, 10)
+
+    def oracle_run():
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+        xi = x.clone().requires_grad_(True)
+        y = wo.rrdb(sd, "", xi, n_rdb=3, n_dense=4)
+        y.backward(gy)
+        return y.detach(), xi.grad, {k: v.grad for k, v in sd.items()}
+
+    y_ref, dx_ref, g_ref = oracle_run()
+    with bf16_operand_emulation():
+        y_emu, dx_emu, g_emu = oracle_run()
+    blk.cuda()
+    xg = x.cuda().contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    with ops.precision("bf16"):
+        y = blk(xg)
+        y.backward(gy.cuda())
+    bound = lambda emu, ref: 1.5 * rel_l2(emu, ref) + 2e-2
+    assert rel_l2(y, y_ref) <= bound(y_emu, y_ref)
+    assert rel_l2(xg.grad, dx_ref) <= bound(dx_emu, dx_ref)
+    worst = 0.0
+    for k, p in blk.named_parameters():
+        err, lim = rel_l2(p.grad, g_ref[k]), bound(g_emu[k], g_ref[k])
+        worst = max(worst, err / lim)
+        assert err <= lim, (k, err, lim)
+    print(f"trunk RRDB bf16: fwd {rel_l2(y, y_ref):.2e}, dx {rel_l2(xg.grad, dx_ref):.2e}, worst grad/bound {worst:.2f}")

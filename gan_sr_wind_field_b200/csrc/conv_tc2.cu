@@ -30,7 +30,6 @@ namespace ws {
 
 namespace {
 
-constexpr int kThreads = 192;
 constexpr int kMaxWSlots = 6;
 constexpr int kMaxABufs = 6;
 
@@ -57,8 +56,12 @@ struct Tc2Params {
 // epilogue, but only HALF of every weight tile; the leader issues one M=256 MMA per step that multiplies both CTAs'
 // A tiles with the pair's combined B tile.  Per SM this halves the weight traffic from L2 and the B-operand reads
 // from shared memory (measured: a cta_group::1 N=144 MMA already saturates the 128 B/clk SMEM port).
-template <bool kPair>
-__global__ void __launch_bounds__(kThreads, kPair ? 1 : 2)  // non-pair tiles are costed for two CTAs per SM: <= 168 regs
+// kEpiWarps: 4 or 8 epilogue warps.  A warp can only read the TMEM lane quarter (warp % 4); with 8 warps two of them
+// share a quarter and take alternate 16-column chunks — twice the loads / stores in flight for the wide fp32
+// accumulate epilogues, used when the CTA has the SM to itself anyway (ncu: the dense-conv dgrad spent ~60 % of its
+// cycles in a latency-bound 4-warp epilogue).
+template <bool kPair, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, (kPair || kEpiWarps == 8) ? 1 : 2)  // 2 CTAs/SM: <= 168 regs
 conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const Tc2Params p, const View dst, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -221,6 +224,8 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 2) {
     // ===== epilogue =====
     const int sub = warp & 3;
+    constexpr int kParts = kEpiWarps / 4;       // warps sharing one TMEM lane quarter
+    const int part = (warp - 2) >> 2;           // this warp takes chunks part, part + kParts, ...
     ptx::griddep_wait();  // residual reads / output writes also order after the predecessor
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
@@ -241,18 +246,18 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int climit = p.cn - n0 < p.n_umma ? p.cn - n0 : p.n_umma;  // columns of this tile that exist
         const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma);
         float cur[16], nxt[16];
-        prefetch_res16(ep, ev, n, v, n0, p.cn, n0 + climit, row_ok, cur);
-        for (int c0 = 0; c0 < climit; c0 += 16) {
+        prefetch_res16(ep, ev, n, v, n0 + 16 * part, p.cn, n0 + climit, row_ok, cur);
+        for (int c0 = 16 * part; c0 < climit; c0 += 16 * kParts) {
           uint32_t rr[16];
           ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
-          prefetch_res16(ep, ev, n, v, n0 + c0 + 16, p.cn, n0 + climit, row_ok, nxt);
+          prefetch_res16(ep, ev, n, v, n0 + c0 + 16 * kParts, p.cn, n0 + climit, row_ok, nxt);
           ptx::tmem_ld_wait();
           epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, cur);
 #pragma unroll
           for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
         }
       } else {
-        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+        for (int c0 = 16 * part; c0 < p.n_umma; c0 += 16 * kParts) {
           if (n0 + c0 >= p.cn) break;
           uint32_t rr[16];
           ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
@@ -555,20 +560,35 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv3d_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    auto set = [](const void* f) {
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    };
+    set((const void*)conv3d_tc2_kernel<false, 4>);
+    set((const void*)conv3d_tc2_kernel<false, 8>);
+    set((const void*)conv3d_tc2_kernel<true, 4>);
+    set((const void*)conv3d_tc2_kernel<true, 8>);
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "conv_tc2: smem request %zu too large", smem);
   const unsigned tiles = (unsigned)(p.N * p.tiles_x * p.tiles_y);
+  // 8 epilogue warps when the CTA cannot share its SM anyway (SMEM) and there is more than one chunk per warp
+  static const int env_epi = getenv("WS_TC2_EPI8") ? atoi(getenv("WS_TC2_EPI8")) : -1;
+  const bool single = smem > 113 * 1024 || pair;
+  const bool epi8 = env_epi >= 0 ? (env_epi != 0 && single) : (single && p.n_umma >= 32);
   if (!pair) {
     dim3 grid(tiles, (unsigned)n_tiles);
-    WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<false>, grid, dim3(kThreads), smem, st, 1, tmA, tmB, p, dst, ep));
+    if (epi8)
+      WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<false, 8>, grid, dim3(320), smem, st, 1, tmA, tmB, p, dst, ep));
+    else
+      WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<false, 4>, grid, dim3(192), smem, st, 1, tmA, tmB, p, dst, ep));
   } else {
     // pairs of adjacent tiles; an odd tail gets a padding CTA
-    WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<true>, dim3((tiles + 1) / 2 * 2, 1, 1), dim3(kThreads), smem, st, 2, tmA,
-                             tmB, p, dst, ep));
+    const dim3 grid((tiles + 1) / 2 * 2, 1, 1);
+    if (epi8)
+      WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<true, 8>, grid, dim3(320), smem, st, 2, tmA, tmB, p, dst, ep));
+    else
+      WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<true, 4>, grid, dim3(192), smem, st, 2, tmA, tmB, p, dst, ep));
   }
   WS_POST_LAUNCH(1);
   return 0;

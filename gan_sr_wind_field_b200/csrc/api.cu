@@ -571,6 +571,7 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   if (int e = axpby_launch(View(dy), d->alpha, View((const ws_tensor*)nullptr), 0.f, View(g_lff), d->n, d->f, v, st))
     return e;
   const bool want_w = dw != nullptr;
+  bool dx_done = false;
   // gbuf holds the gradients of ALL dense conv outputs side by side (n, nconv*gc, ..): the dgrad chain consumes
   // slice i as it goes, the weight gradients of the dense convs are then one merged GEMM at the end.
   const bool merged = want_w && rdb_merged_wgrad_ok(d, buf, gbuf);
@@ -600,6 +601,14 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
     }
     ws_epilogue ep = plain_epilogue();
     ep.res1 = *dbuf; ep.beta1 = 1.f;  // accumulate into dbuf[:, :cin]
+    if (i == 0 && dx && dx->ptr) {
+      // conv0 reads exactly the block input (cin = f): its data-gradient epilogue also adds the skip term and
+      // writes dL/dx directly — dx = dbuf[:, :f] + dgrad_0 + beta1 * dy — instead of a separate axpby pass
+      ep.res2 = *dy; ep.beta2 = d->beta1;
+      if (int e = ws_conv3d_dgrad(s, gi, packed[i], dx, &ep, d->math, stream)) return e;
+      dx_done = true;
+      continue;
+    }
     if (int e = ws_conv3d_dgrad(s, gi, packed[i], dbuf, &ep, d->math, stream)) return e;
   }
   if (merged) {
@@ -610,7 +619,7 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
                              workspace_bytes, st))
       return e;
   }
-  if (dx && dx->ptr) {
+  if (dx && dx->ptr && !dx_done) {
     if (int e = axpby_launch(View(dbuf), 1.f, View(dy), d->beta1, View(dx), d->n, d->f, v, st)) return e;
   }
   return 0;

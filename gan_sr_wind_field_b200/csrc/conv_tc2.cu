@@ -295,7 +295,8 @@ bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool p
   }();
   for (int by = 1; by <= DY && by * DZ <= 128 * tmax; ++by) {
     const int slab = by * DZ;
-    if (slab % 8) continue;
+    // (any slab size works: a SWIZZLE_128B operand may start at any 128-byte row, scripts/micro/row_offset.cu)
+    if (slab % 8 && !getenv("WS_TC2_ANY_SLAB")) continue;
     if (forced && by != force_by) continue;
     for (int tx = 1; tx <= DX && tx * slab <= 128 * tmax; ++tx) {
       if (forced && tx != force_tx) continue;

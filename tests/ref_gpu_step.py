@@ -1,7 +1,7 @@
 """Context number (NOT the product path, NOT bench.py's reference arm): the reference's G step restated with stock
 torch ops (oracle/wind_oracle.py) executed on the B200 through cuDNN, in fp32 (TF32 allowed, torch's default for
 convs) and under bf16 autocast — i.e. what a user of the reference gets on this GPU today.
-Usage: python scripts/ref_gpu_step.py [batch]"""
+Usage: python tests/ref_gpu_step.py [batch]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -69,6 +69,7 @@ SYMBOLS = [
     ("ws_conv3d_dgrad", _I, [_SP, _TP, _P, _TP, _EP, _I, _P]),
     ("ws_conv3d_wgrad_workspace_bytes", _Z, [_SP, _I]),
     ("ws_conv3d_wgrad", _I, [_SP, _TP, _TP, _P, _P, _I, _I, _P, _Z, _P]),
+    ("ws_im2col", _I, [C.POINTER(WsConvShape), _TP, _TP, _I, _P]),
     ("ws_rdb_packed_bytes", _Z, [C.POINTER(WsRdbDesc), _I, _I]),
     ("ws_rdb_backward_workspace_bytes", _Z, [C.POINTER(WsRdbDesc)]),
     ("ws_rdb_forward_workspace_bytes", _Z, [C.POINTER(WsRdbDesc)]),

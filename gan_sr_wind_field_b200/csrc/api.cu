@@ -48,6 +48,7 @@ bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
 int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t, const int*);
+int im2col_small_launch(const View&, const View&, const ConvGeom&, int, cudaStream_t);
 int xfold_sum_lrelu_launch(const View&, const View&, float, int, int, int, int, int, int, int, cudaStream_t);
 int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
                  cudaStream_t);
@@ -306,6 +307,12 @@ int ws_xunfold(const ws_tensor* dout, const ws_tensor* u, int n, int co, int kx,
                int z, void* stream) {
   WS_REQUIRE(dout && dout->ptr && u && u->ptr && cpad >= kx * co, "ws_xunfold: bad arguments");
   return xunfold_launch(View(dout), View(u), n, co, kx, pad, cpad, x, yy, z, (cudaStream_t)stream);
+}
+
+int ws_im2col(const ws_conv_shape* s, const ws_tensor* x, const ws_tensor* u, int cpad, void* stream) {
+  if (int e = validate_shape(s)) return e;
+  WS_REQUIRE(x && x->ptr && u && u->ptr, "ws_im2col: null pointer");
+  return im2col_small_launch(View(x), View(u), ConvGeom(*s), cpad, (cudaStream_t)stream);
 }
 
 int ws_copy(const ws_tensor* src, const ws_tensor* dst, int n, int c, int64_t v, void* stream) {

@@ -494,6 +494,53 @@ __global__ void xfold_sum_lrelu_cl8(View u, View out, float slope, int co8, int 
   }
 }
 
+// ---- im2col for the narrow first layers -------------------------------------------------------------------
+// u[n, v, tap*cin + ci] = x[n, ci, v (+) tap] (zero outside the volume and in the pad columns), u channels-last bf16
+// with cpad % 8 == 0 columns: turns a Cin <= 4 conv (D's features.0: 3 -> 32 at 128x128x10) into a 1x1x1 conv with
+// K = taps*cin (81 -> 96) that runs on the tensor-core kernels; one 8-column vector store per thread.
+__global__ void im2col_small_kernel(View x, View u, ConvGeom g, int cpad8, long long total) {
+  // one thread per output voxel: walks the taps once (bounds and offsets resolved per (ti, tj) line), gathers the
+  // taps*cin values into 8-wide groups and stores each group as one 16-byte vector of the voxel's U row
+  const long long VO = (long long)g.xo * g.yo * g.zo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % VO;
+    const int nn = (int)(i / VO);
+    const int zo = (int)(v % g.zo);
+    const int yo = (int)((v / g.zo) % g.yo);
+    const int xo = (int)(v / ((long long)g.zo * g.yo));
+    const long long urow = u.off(nn, 0, v);
+    float f[8];
+    int fill = 0, q = 0;
+    for (int ti = 0; ti < g.kx; ++ti) {
+      const int xi = xo * g.sx - g.px + ti;
+      for (int tj = 0; tj < g.ky; ++tj) {
+        const int yi = yo * g.sy - g.py + tj;
+        const bool line_ok = xi >= 0 && xi < g.x && yi >= 0 && yi < g.y;
+        const long long line = ((long long)xi * g.y + yi) * g.z;
+        for (int tl = 0; tl < g.kz; ++tl) {
+          const int zi = zo * g.sz - g.pz + tl;
+          const bool ok = line_ok && zi >= 0 && zi < g.z;
+          for (int ci = 0; ci < g.cin; ++ci) {
+            f[fill++] = ok ? x.ld(nn, ci, line + zi) : 0.f;
+            if (fill == 8) {
+              st8(u, urow + q * 8, f);
+              ++q;
+              fill = 0;
+            }
+          }
+        }
+      }
+    }
+    // tail group and the zero pad columns
+    for (; q < cpad8; ++q) {
+      for (; fill < 8; ++fill) f[fill] = 0.f;
+      st8(u, urow + q * 8, f);
+      fill = 0;
+    }
+  }
+}
+
 // same, u channels-last with cpad % 8 == 0: one 8-channel vector store per thread
 __global__ void xunfold_st8_kernel(View dout, View u, int co, int kx, int pad, int cpad8, int X, int Y, int Z,
                                    long long total) {
@@ -812,6 +859,67 @@ int xfold_sum_lrelu_launch(const View& u, const View& out, float slope, int n, i
   WS_REQUIRE(vec8_ok(u, co) && vec8_ok(out, co), "xfold_sum_lrelu: operands must be 8-channel vectorisable");
   WS_CHECK_CUDA(launch_pdl(xfold_sum_lrelu_cl8, dim3(grid_for(total)), dim3(kBlock), 0, st, 1, u, out, slope, co / 8, co,
                            kx, pad, X, Y, Z, total));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+// fully unrolled K^3 x CIN variant: the gather buffer stays in registers (static indices)
+template <int K, int CIN>
+__global__ void im2col_k_kernel(View x, View u, ConvGeom g, int cpad8, long long total) {
+  constexpr int kCols = K * K * K * CIN;
+  constexpr int kGroups = (kCols + 7) / 8;
+  const long long VO = (long long)g.xo * g.yo * g.zo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % VO;
+    const int nn = (int)(i / VO);
+    const int zo = (int)(v % g.zo);
+    const int yo = (int)((v / g.zo) % g.yo);
+    const int xo = (int)(v / ((long long)g.zo * g.yo));
+    const long long urow = u.off(nn, 0, v);
+    float f[kGroups * 8];
+#pragma unroll
+    for (int ti = 0; ti < K; ++ti) {
+      const int xi = xo * g.sx - g.px + ti;
+#pragma unroll
+      for (int tj = 0; tj < K; ++tj) {
+        const int yi = yo * g.sy - g.py + tj;
+        const bool line_ok = xi >= 0 && xi < g.x && yi >= 0 && yi < g.y;
+        const long long line = ((long long)xi * g.y + yi) * g.z;
+#pragma unroll
+        for (int tl = 0; tl < K; ++tl) {
+          const int zi = zo * g.sz - g.pz + tl;
+          const bool ok = line_ok && zi >= 0 && zi < g.z;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+            f[((ti * K + tj) * K + tl) * CIN + ci] = ok ? x.ld(nn, ci, line + zi) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = kCols; c < kGroups * 8; ++c) f[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < kGroups; ++q) {
+      float h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = f[q * 8 + j];
+      st8(u, urow + q * 8, h);
+    }
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = kGroups; q < cpad8; ++q) st8(u, urow + q * 8, zero);
+  }
+}
+
+int im2col_small_launch(const View& x, const View& u, const ConvGeom& g, int cpad, cudaStream_t st) {
+  WS_REQUIRE(cpad % 8 == 0 && cpad >= g.taps() * g.cin && vec8_ok(u, cpad) && u.dtype == WS_BF16,
+             "im2col: u must be channels-last bf16 with a multiple of 8 columns >= taps*cin");
+  const long long total = (long long)g.n * g.xo * g.yo * g.zo;
+  if (total <= 0) return 0;
+  const bool k3 = g.kx == 3 && g.ky == 3 && g.kz == 3;
+  if (k3 && g.cin == 3) im2col_k_kernel<3, 3><<<grid_for(total), kBlock, 0, st>>>(x, u, g, cpad / 8, total);
+  else if (k3 && g.cin == 4) im2col_k_kernel<3, 4><<<grid_for(total), kBlock, 0, st>>>(x, u, g, cpad / 8, total);
+  else if (k3 && g.cin == 2) im2col_k_kernel<3, 2><<<grid_for(total), kBlock, 0, st>>>(x, u, g, cpad / 8, total);
+  else im2col_small_kernel<<<grid_for(total), kBlock, 0, st>>>(x, u, g, cpad / 8, total);
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -10,6 +10,7 @@ nothing falls back to torch/cuDNN arithmetic.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -333,6 +334,37 @@ def _as_act(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def _im2col_eligible(shape: WsConvShape, x: torch.Tensor) -> bool:
+    """Narrow-input conv that should run as im2col + 1x1x1 tensor-core conv: bf16 mode, 2 <= Cin <= 4 (Cin = 1 is the
+    terrain conv, whose input is raw altitude in metres and stays on the fp32 CUDA-core path), more than one tap, an
+    output width the UMMA N dimension takes, and a volume large enough for the extra pass to pay (D's features.0:
+    3 -> 32 at 128x128x10; the generator's 4 -> 128 feature conv on the 16x16x10 LR volume stays direct)."""
+    taps = shape.kx * shape.ky * shape.kz
+    xo, yo, zo = out_dims(shape)
+    return (get_precision() == "bf16" and 2 <= shape.cin <= 4 and taps > 1 and shape.cout % 16 == 0
+            and shape.cout <= 256 and shape.n * xo * yo * zo >= 65536 and os.environ.get("WINDSR_IM2COL", "1") != "0")
+
+
+def _im2col(x: torch.Tensor, shape: WsConvShape):
+    """(U, 1x1x1 shape): U[n, v, tap*cin + ci] = x[n, ci, v (+) tap] in channels-last bf16 (ws_im2col)."""
+    taps = shape.kx * shape.ky * shape.kz
+    cpad = (taps * shape.cin + 15) // 16 * 16
+    xo, yo, zo = out_dims(shape)
+    u = empty_cl(shape.n, cpad, xo, yo, zo, torch.bfloat16, x.device)
+    xv, uv = view(x), view(u)
+    check(load().ws_im2col(C.byref(shape), C.byref(xv), C.byref(uv), cpad, stream_ptr()), "ws_im2col")
+    return u, make_shape(u.shape, shape.cout, 1, 1, 0)
+
+
+def _im2col_weight(weight: torch.Tensor, cpad: int) -> torch.Tensor:
+    """w'[co][tap*cin + ci] = w[co][ci][tap], zero pad columns; as a (cout, cpad, 1, 1, 1) conv weight."""
+    co, ci = weight.shape[:2]
+    w2 = weight.detach().reshape(co, ci, -1).permute(0, 2, 1).reshape(co, -1)
+    if w2.shape[1] < cpad:
+        w2 = torch.cat((w2, w2.new_zeros((co, cpad - w2.shape[1]))), 1)
+    return w2.reshape(co, cpad, 1, 1, 1).contiguous()
+
+
 class ConvFn(torch.autograd.Function):
     """y = lrelu(conv(x, w) * oscale + bias) * chan_scale + beta * res
 
@@ -355,9 +387,16 @@ class ConvFn(torch.autograd.Function):
                 out = empty_cl(shape.n, shape.cout, xo, yo, zo, dt, x.device)
         oscale, shift = cfg.get("oscale"), cfg.get("shift")
         b = bias if bias is not None else shift
-        conv_fwd(x, weight, cfg.get("cache"), shape, out, bias=b.detach() if b is not None else None,
-                 oscale=oscale, chan_scale=cfg.get("chan_scale"), slope=cfg.get("slope", 1.0),
-                 res1=res, beta1=cfg.get("beta", 1.0) if res is not None else 0.0)
+        ctx.im2col = _im2col_eligible(shape, x)
+        if ctx.im2col:
+            u, shape1 = _im2col(x, shape)
+            conv_fwd(u, _im2col_weight(weight, u.shape[1]), None, shape1, out,
+                     bias=b.detach() if b is not None else None, oscale=oscale, chan_scale=cfg.get("chan_scale"),
+                     slope=cfg.get("slope", 1.0), res1=res, beta1=cfg.get("beta", 1.0) if res is not None else 0.0)
+        else:
+            conv_fwd(x, weight, cfg.get("cache"), shape, out, bias=b.detach() if b is not None else None,
+                     oscale=oscale, chan_scale=cfg.get("chan_scale"), slope=cfg.get("slope", 1.0),
+                     res1=res, beta1=cfg.get("beta", 1.0) if res is not None else 0.0)
         ctx.shape = shape
         ctx.cfg = cfg
         ctx.has_bias = bias is not None
@@ -424,6 +463,13 @@ class ConvFn(torch.autograd.Function):
             dw = torch.cat((dw_main, dw_rem), 0)
             if need_b and ctx.has_bias:
                 db = g.float().sum((0, 2, 3, 4))
+        elif need_w and ctx.im2col and g.dtype == torch.bfloat16 and not pad_cout:
+            # weight gradient of the im2col form: a 1x1x1 wgrad with K = taps*cin on the tensor cores
+            u, shape1 = _im2col(x, shape)
+            dw2, db = conv_wgrad(u, g, shape1, want_bias=ctx.has_bias and need_b)
+            taps = shape.kx * shape.ky * shape.kz
+            dw = dw2.reshape(shape.cout, -1)[:, :taps * shape.cin].reshape(shape.cout, taps, shape.cin) \
+                .permute(0, 2, 1).reshape(weight.shape).contiguous()
         elif need_w or (need_b and ctx.has_bias):
             dw, db = conv_wgrad(x, g, shape, want_bias=ctx.has_bias and need_b, want_weight=need_w)
             if pad_cout:

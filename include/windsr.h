@@ -136,6 +136,13 @@ size_t ws_conv3d_wgrad_workspace_bytes(const ws_conv_shape* s, int math);
 int ws_conv3d_wgrad(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor* dy, float* dw, float* db,
                     int accumulate, int math, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- im2col for the narrow first layers (Cin <= 4) ------------------------------------------------------ */
+/* u (n, cpad, xo, yo, zo) channels-last bf16, cpad % 8 == 0, cpad >= taps*cin:
+ *   u[n, v, tap*cin + ci] = x[n, ci, v (+) tap]   (zero padding, zero pad columns)
+ * so that conv(x, w) == conv1x1x1(u, w') with w'[co][tap*cin+ci] = w[co][ci][tap]: the 3 -> 32 first conv of the
+ * discriminator (torch_blocks.py:372-521 via Discriminator_3D.py:67-136) then runs on the tensor-core kernels. */
+int ws_im2col(const ws_conv_shape* s, const ws_tensor* x, const ws_tensor* u, int cpad, void* stream);
+
 /* ---- residual dense block executor (torch_blocks.py:217-290, 328-330) ------------------------------- */
 /* One call runs a whole RDB: (re)pack its weights, 4 dense conv + LeakyReLU launches writing channel slices of the
  * concat buffer, then the LFF conv whose epilogue applies  out = alpha*(LFF(buf)+bias) + beta1*x + beta2*outer.

@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const TcParams p, const View dst, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float stat_s[512];  // per-CTA BatchNorm partial sums (epilogue.cuh)
+  if (ep.stat_sum)
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_s[i] = 0.f;  // visible after the prologue barrier
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -181,7 +184,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
       if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r);
-      else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r, lane);
+      else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, r, lane, ep.stat_sum ? stat_s : nullptr, n0);
+    }
+    if (ep.stat_sum) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
+      flush_bn_stats(ep, stat_s, n0, p.n_umma, p.cn, (int)threadIdx.x - 64, 128);
     }
     ptx::tc_fence_before();
   }
@@ -394,11 +401,11 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);  // + 2 KB static
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
              cudaGetErrorString(attr_err));
-  WS_REQUIRE(smem <= 227 * 1024, "tcgen05 conv: smem request %zu too large", smem);
+  WS_REQUIRE(smem <= 225 * 1024, "tcgen05 conv: smem request %zu too large", smem);
   dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y * p.tiles_z), (unsigned)n_tiles);
   conv3d_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p, dst, ep);
   WS_POST_LAUNCH(1);

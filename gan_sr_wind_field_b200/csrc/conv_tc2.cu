@@ -65,9 +65,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, (kPair || kEpiWarps == 8)
 conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const Tc2Params p, const View dst, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float stat_s[512];  // per-CTA BatchNorm partial sums (train-mode discriminator convs)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_base = smem_base + (uint32_t)p.a_bufs * p.a_buf_bytes;
+  if (ep.stat_sum)
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_s[i] = 0.f;  // visible after the prologue barrier
   const uint32_t bar_off = (uint32_t)p.a_bufs * p.a_buf_bytes + (uint32_t)p.w_slots * p.w_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -263,9 +266,14 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
           ptx::tmem_ld_wait();
           if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr);
-          else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane);
+          else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane, ep.stat_sum ? stat_s : nullptr, n0);
         }
       }
+    }
+    if (ep.stat_sum) {
+      // all epilogue warps have added their partial sums: one global atomic per channel for the whole CTA
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+      flush_bn_stats(ep, stat_s, n0, p.n_umma, p.cn, (int)threadIdx.x - 64, 32 * kEpiWarps);
     }
     ptx::tc_fence_before();
   }
@@ -279,7 +287,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-constexpr int kSmemBudget = 225 * 1024;
+constexpr int kSmemBudget = 222 * 1024;  // dynamic SMEM; 2 KB of static SMEM (BN partial sums) sit beside it
 
 // Pick (by, tx): minimise estimated SM-time = waves * max(MMA cycles, L2->SMEM cycles) per K iteration.
 bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
@@ -324,7 +332,7 @@ bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool p
       const int smem_min = 2 * a_bytes + (kx + 1 < 3 ? 3 : kx + 1) * w_bytes + 2048;
       int cols = 32;
       while (cols < t_m * n_umma) cols <<= 1;
-      int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 && !pair ? 2 : 1;
+      int cps = (227 * 1024) / (smem_min + 2048) >= 2 && cols <= 256 && !pair ? 2 : 1;  // + static SMEM
       const long long per_sm = (ctas + 147) / 148;
       const int r = per_sm < cps ? (int)per_sm : cps;  // CTAs actually sharing an SM
       const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
@@ -391,7 +399,7 @@ bool choose_cfg_vol_search(int N, int DX, int DY, int DZ, int kx, int ky, int kz
       const int smem_min = nbuf * a_bytes + 4 * w_bytes + 2048;
       int cols = 32;
       while (cols < t_m * n_umma) cols <<= 1;
-      const int cps = (227 * 1024) / smem_min >= 2 && cols <= 256 ? 2 : 1;
+      const int cps = (227 * 1024) / (smem_min + 2048) >= 2 && cols <= 256 ? 2 : 1;
       const long long per_sm = (ctas + 147) / 148;
       const int r = per_sm < cps ? (int)per_sm : cps;
       const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
@@ -508,7 +516,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     p.a_ops = (slabs + p.a_sub_slabs - 1) / p.a_sub_slabs;
   }
   // SMEM budget: the whole SM for one resident CTA, half of it when the config was costed with two
-  const int budget = p.a_bufs >= 2 ? (227 * 1024) / 2 - 1024 : kSmemBudget;
+  const int budget = p.a_bufs >= 2 ? (227 * 1024) / 2 - 1024 - 2048 : kSmemBudget;  // 2 KB static SMEM per CTA
   // weight ring: at least kx + 1 slots when they fit, then as many halo buffers as the rest allows
   p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : (p.kx + 1 < 3 ? 3 : p.kx + 1);
   {
@@ -563,7 +571,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   std::call_once(once, [] {
     auto set = [](const void* f) {
       if (attr_err == cudaSuccess)
-        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);  // + 2 KB static
     };
     set((const void*)conv3d_tc2_kernel<false, 4>);
     set((const void*)conv3d_tc2_kernel<false, 8>);
@@ -571,7 +579,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     set((const void*)conv3d_tc2_kernel<true, 8>);
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-  WS_REQUIRE(smem <= 227 * 1024, "conv_tc2: smem request %zu too large", smem);
+  WS_REQUIRE(smem <= 225 * 1024, "conv_tc2: smem request %zu too large", smem);
   const unsigned tiles = (unsigned)(p.N * p.tiles_x * p.tiles_y);
   // 8 epilogue warps when the CTA cannot share its SM anyway (SMEM) and there is more than one chunk per warp
   static const int env_epi = getenv("WS_TC2_EPI8") ? atoi(getenv("WS_TC2_EPI8")) : -1;

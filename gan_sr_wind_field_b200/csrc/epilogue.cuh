@@ -143,8 +143,13 @@ __device__ __forceinline__ void prefetch_res16(const Epi& ep, const EpiVec& ev, 
 
 // One 16-column chunk of fp32 accumulators `rr` (tcgen05.ld 32x32b.x16) for accumulator row = voxel (n, v).
 // Must be called by all 32 lanes (the BN-statistics reduction is warp-wide); stores are predicated on row_ok.
+// `stat_s` (optional): 512 floats of shared memory — BN sums of this CTA's column c (0..255, relative to
+// `stat_c0`) at [c], square sums at [256 + c]; the caller flushes them with flush_bn_stats() after its last chunk.
+// Without it every warp sends its partial sums straight to global memory (thousands of CTAs x 4 warps hammering 2 x
+// Cout addresses: D's BN convs spent 3/4 of their time there).
 __device__ __forceinline__ void epilogue16(const Epi& ep, const EpiVec& ev, const View& dst, int n, long long v,
-                                           int cbase, int cn, bool row_ok, const uint32_t (&rr)[16], int lane) {
+                                           int cbase, int cn, bool row_ok, const uint32_t (&rr)[16], int lane,
+                                           float* stat_s = nullptr, int stat_c0 = 0) {
   float y[16], pre[16];
   float r1[16], r2[16], mk[16];
   const bool has1 = ep.res1.ptr != nullptr, has2 = ep.res2.ptr != nullptr;
@@ -177,14 +182,31 @@ __device__ __forceinline__ void epilogue16(const Epi& ep, const EpiVec& ev, cons
       const float s2 = warp_sum(pre[j] * pre[j]);
       const int c = cbase + j;
       if (lane == 0 && c < cn) {
-        atomicAdd(&ep.stat_sum[c], s1);
-        atomicAdd(&ep.stat_sqsum[c], s2);
+        if (stat_s) {
+          atomicAdd(&stat_s[c - stat_c0], s1);
+          atomicAdd(&stat_s[256 + c - stat_c0], s2);
+        } else {
+          atomicAdd(&ep.stat_sum[c], s1);
+          atomicAdd(&ep.stat_sqsum[c], s2);
+        }
       }
     }
   }
   if (row_ok) {
     store16(dst, ev.dst, n, cbase, v, cn, y);
     if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
+  }
+}
+
+// one global atomic per channel and CTA: call from `nthreads` epilogue threads (tid 0..nthreads-1) after they have
+// all finished their chunks and synchronised
+__device__ __forceinline__ void flush_bn_stats(const Epi& ep, const float* stat_s, int c0, int ncols, int cn, int tid,
+                                               int nthreads) {
+  for (int i = tid; i < 2 * ncols; i += nthreads) {
+    const int c = i < ncols ? i : i - ncols;
+    if (c0 + c >= cn) continue;
+    if (i < ncols) atomicAdd(&ep.stat_sum[c0 + c], stat_s[c]);
+    else atomicAdd(&ep.stat_sqsum[c0 + c], stat_s[256 + c]);
   }
 }
 

@@ -35,7 +35,8 @@ class WsEpilogue(C.Structure):
                 ("lrelu_slope", C.c_float), ("alpha", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("res1", WsTensor), ("res2", WsTensor), ("mask", WsTensor),
                 ("mask_c0", C.c_int32), ("mask_c1", C.c_int32), ("mask_slope", C.c_float), ("_pad", C.c_int32),
-                ("out2", WsTensor), ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p)]
+                ("out2", WsTensor), ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p),
+                ("tail_out", WsTensor), ("tail_mask", WsTensor), ("tail_c0", C.c_int32), ("tail_slope", C.c_float)]
 
 
 class WsRdbDesc(C.Structure):

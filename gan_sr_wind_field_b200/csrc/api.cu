@@ -589,8 +589,26 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   }
   if (d->repack)
     if (int e = rdb_repack(d, r, g_lff, gbuf, w, packed, 1, st)) return e;
+  // The gradient of dense conv j's output is final once the data-gradients of the LFF and of the convs i > j have
+  // been accumulated: those are the LAST gc channels of the data-gradient that runs just before conv j's turn, so on
+  // the tensor-core path that epilogue applies the LeakyReLU-backward and writes g_j itself ("tail", windsr.h).
+  auto tail_ok = [&](const ws_conv_shape* s, const ws_tensor* act) {
+    return !getenv("WS_DISABLE_RDB_TAIL") && d->gc % 16 == 0 &&
+           dgrad_path(ConvGeom(*s), View(act), d->math) == WS_PATH_TCGEN05;
+  };
+  auto set_tail = [&](ws_epilogue& ep, int j, int total_c) {  // j: the conv whose output gradient is the tail
+    ep.tail_out = slice(*gbuf, j * d->gc);
+    ep.tail_mask = slice(*buf, r.dense[j].cin);
+    ep.tail_c0 = total_c - d->gc;
+    ep.tail_slope = d->slope;
+  };
+  bool g_ready = false;  // g of the conv about to be processed was produced by the previous epilogue
   {
     ws_epilogue ep = plain_epilogue();
+    if (d->nconv > 0 && tail_ok(&r.lff, g_lff)) {
+      set_tail(ep, d->nconv - 1, r.ctot);
+      g_ready = true;
+    }
     if (int e = ws_conv3d_dgrad(&r.lff, g_lff, packed[d->nconv], dbuf, &ep, d->math, stream)) return e;
   }
   for (int i = d->nconv - 1; i >= 0; --i) {
@@ -599,15 +617,21 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
     ws_tensor dslice = slice(*dbuf, s->cin), yslice = slice(*buf, s->cin), gslice = slice(*gbuf, i * d->gc);
     const ws_tensor* gi = &gslice;
     // g_i = dbuf[:, cin:cin+gc] * lrelu'(buf[:, cin:cin+gc])
-    if (int e = lrelu_bwd_launch(View(&dslice), View(&yslice), d->slope, nullptr, nullptr, View(gi), d->n, d->gc,
-                                 v, st))
-      return e;
+    if (!g_ready)
+      if (int e = lrelu_bwd_launch(View(&dslice), View(&yslice), d->slope, nullptr, nullptr, View(gi), d->n, d->gc,
+                                   v, st))
+        return e;
+    g_ready = false;
     if (want_w && dw[i] && !merged) {
       if (int e = ws_conv3d_wgrad(s, buf, gi, dw[i], nullptr, 0, d->math, workspace, workspace_bytes, stream))
         return e;
     }
     ws_epilogue ep = plain_epilogue();
     ep.res1 = *dbuf; ep.beta1 = 1.f;  // accumulate into dbuf[:, :cin]
+    if (i > 0 && tail_ok(s, gi)) {
+      set_tail(ep, i - 1, s->cin);  // channels [cin - gc, cin) of this gradient = output of conv i-1
+      g_ready = true;
+    }
     if (i == 0 && dx && dx->ptr) {
       // conv0 reads exactly the block input (cin = f): its data-gradient epilogue also adds the skip term and
       // writes dL/dx directly — dx = dbuf[:, :f] + dgrad_0 + beta1 * dy — instead of a separate axpby pass

@@ -115,6 +115,9 @@ struct Epi {
   float mask_slope;
   float* stat_sum;
   float* stat_sqsum;
+  View tail_out, tail_mask;  // see ws_epilogue: fused LeakyReLU-backward of the tail channels
+  int tail_c0;
+  float tail_slope;
   int cout;  // channel count of the output (indexing chan_scale)
 
   __host__ Epi() {}
@@ -126,7 +129,9 @@ struct Epi {
       res1 = View(e->res1); res2 = View(e->res2); mask = View(e->mask); out2 = View(e->out2);
       mask_c0 = e->mask_c0; mask_c1 = e->mask_c1; mask_slope = e->mask_slope;
       stat_sum = e->stat_sum; stat_sqsum = e->stat_sqsum;
+      tail_out = View(e->tail_out); tail_mask = View(e->tail_mask); tail_c0 = e->tail_c0; tail_slope = e->tail_slope;
     } else {
+      tail_c0 = 0; tail_slope = 1.f;
       bias = oscale = chan_scale = nullptr;
       lrelu_slope = 1.f; alpha = 1.f; beta1 = beta2 = 0.f;
       mask_c0 = mask_c1 = 0; mask_slope = 1.f;

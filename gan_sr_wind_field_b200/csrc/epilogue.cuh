@@ -131,6 +131,17 @@ __device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& e
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = fmaf(ep.beta2, r[j], y[j]);
   }
+  if (ep.tail_out.ptr && cbase >= ep.tail_c0) {
+    // tail channels: LeakyReLU-backward against the saved activation, written to the gradient buffer of the
+    // previous conv instead of `dst` (warp-uniform branch: tail_c0 is a multiple of 16)
+    float mk[16];
+    const int ct = cbase - ep.tail_c0, cnt = cn - ep.tail_c0;
+    load16(ep.tail_mask, view_vec_ok(ep.tail_mask), n, ct, v, cnt, mk);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = mk[j] > 0.f ? y[j] : ep.tail_slope * y[j];
+    store16(ep.tail_out, view_vec_ok(ep.tail_out), n, ct, v, cnt, y);
+    return;
+  }
   store16(dst, ev.dst, n, cbase, v, cn, y);
   if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
 }

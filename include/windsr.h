@@ -102,6 +102,13 @@ typedef struct ws_epilogue {
   ws_tensor out2;
   float* stat_sum;
   float* stat_sqsum;
+  /* "tail" channels [tail_c0, cout) (tail_c0 % 16 == 0; tensor-core kernels only): instead of going to `out`, value t
+   * is written as  t * (tail_mask > 0 ? 1 : tail_slope)  to channel (c - tail_c0) of tail_out — the LeakyReLU-backward
+   * of the previous dense conv fused into a data-gradient of the residual dense block (torch_blocks.py:192-214). */
+  ws_tensor tail_out;
+  ws_tensor tail_mask;
+  int32_t tail_c0;
+  float tail_slope;
 } ws_epilogue;
 
 /* ---- library ---------------------------------------------------------------------------------- */

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().ws_version() == 1
     # struct layouts agree with the header (sizes the C side was compiled with)
     assert ctypes.sizeof(_lib.WsTensor) == 40 and ctypes.sizeof(_lib.WsConvShape) == 60
-    assert ctypes.sizeof(_lib.WsEpilogue) == 3 * 8 + 4 * 4 + 3 * 40 + 16 + 40 + 16
+    assert ctypes.sizeof(_lib.WsEpilogue) == 3 * 8 + 4 * 4 + 3 * 40 + 16 + 40 + 16 + 2 * 40 + 8  # + tail fields
 
 
 def test_no_cpu_fallback_and_no_oracle_in_product():

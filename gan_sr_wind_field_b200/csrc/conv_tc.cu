@@ -244,9 +244,12 @@ int get_tensor_map_impl(const MapKey& key, CUtensorMap* out) {
   cuuint32_t box[5], estr[5];
   for (int i = 0; i < 5; ++i) { dims[i] = key.dims[i]; box[i] = key.box[i]; estr[i] = key.estr[i]; }
   for (int i = 0; i < 4; ++i) strides[i] = key.strides[i];
-  CUtensorMapDataType dt = key.dtype == WS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // key.dtype: low byte = element type, bit 8 = SWIZZLE_64B instead of SWIZZLE_128B (tmap.cuh)
+  CUtensorMapDataType dt =
+      (key.dtype & 0xffu) == WS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle swz = (key.dtype & kMapSwizzle64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(&m, dt, key.rank, reinterpret_cast<void*>(key.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WS_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled failed (%d): rank %u dims [%llu %llu %llu %llu %llu] strides [%llu %llu %llu "

@@ -47,6 +47,9 @@ struct Tc2Params {
   int vol;           // 1: volume mode — ONE padded halo box per 64-channel chunk, all kx*ky*kz taps = row offsets
   int pitch_y;       // rows between consecutive y lines of the tile (DZ, or DZ + kz - 1 in volume mode)
   int box_y, box_z;  // TMA box extents in y and z (by, DZ, plus the ky-1 / kz-1 halo in volume mode)
+  int row_bytes;     // bytes of one operand row: 128 (SWIZZLE_128B, 64 channels per chunk) or 64 (SWIZZLE_64B, 32 channels:
+                     // K <= 32 layers — the dense-conv data-gradients — issue 2 K-steps per tap instead of 4 half-empty ones)
+  int kelems;        // channels per K chunk = row_bytes / 2
   int tap_base;      // first tap of the packed weights this launch uses
   int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
@@ -131,7 +134,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::griddep_wait();  // the predecessor's activations / packed weights must be complete before the first load
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
-    const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * 128u;
+    const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * (uint32_t)p.row_bytes;
     const int ngroups = p.vol ? 1 : nyz;             // activation loads per 64-channel chunk
     const int ntaps = p.vol ? p.kx * nyz : p.kx;     // weight tiles per activation load
     for (int yz = 0; yz < ngroups; ++yz) {
@@ -144,10 +147,10 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int o = 0; o < p.a_ops; ++o) {
             const uint32_t d = smem_base + ab * p.a_buf_bytes + o * a_op_bytes;
             if (kPair)
-              ptx::tma_load_5d_2sm(d, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
+              ptx::tma_load_5d_2sm(d, &tmA, a_full(ab), ch * p.kelems, tl - p.pz, y0 - p.py + tj,
                                    x0 - p.px + o * p.a_sub_slabs, n);
             else
-              ptx::tma_load_5d(d, &tmA, a_full(ab), ch * 64, tl - p.pz, y0 - p.py + tj,
+              ptx::tma_load_5d(d, &tmA, a_full(ab), ch * p.kelems, tl - p.pz, y0 - p.py + tj,
                                x0 - p.px + o * p.a_sub_slabs, n);
           }
         }
@@ -159,8 +162,8 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(w_full(wsl), w_cta_bytes * tx_mult);
-            if (kPair) ptx::tma_load_3d_2sm(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, w_row0, tap);
-            else ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * 64, w_row0, tap);
+            if (kPair) ptx::tma_load_3d_2sm(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * p.kelems, w_row0, tap);
+            else ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * p.kelems, w_row0, tap);
           }
           __syncwarp();
           if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
@@ -170,14 +173,19 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1 && leader) {
     // ===== MMA issuer (pair mode: the leader CTA only) =====
     const uint32_t idesc = ptx::make_idesc(1u, kPair ? 256u : 128u, (uint32_t)p.n_umma, 0u, 0u);
-    const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);  // everything but the start address
+    // everything but the start address: SWIZZLE_128B (SBO = 8 rows x 128 B) or SWIZZLE_64B (layout type 4, SBO = 512;
+    // scripts/micro/sw64.cu)
+    const uint64_t desc_hi = p.row_bytes == 128
+                                 ? ptx::make_smem_desc_sw128(0, 16, 1024)
+                                 : (((uint64_t)1 << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) |
+                                    ((uint64_t)4 << 61));
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
     const int ntaps = p.vol ? p.kx * nyz : p.kx;
     const int iters = (p.vol ? 1 : nyz) * p.kchunks;
     for (int it = 0; it < iters; ++it) {
       const int ch = it % p.kchunks;
-      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : 4;
+      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : p.kelems / 16;
       ptx::mbar_wait(a_full(ab), aph);
       const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
       for (int tt = 0; tt < ntaps; ++tt) {
@@ -195,7 +203,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           roff = ti * p.slabrows + tj * p.pitch_y + tl;
         }
         for (int m = 0; m < p.t_m; ++m) {
-          const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * 128u;
+          const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * (uint32_t)p.row_bytes;
           const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
           if (ptx::elect_one()) {
@@ -491,8 +499,13 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   const long long vox = (long long)p.N * p.DX * p.DY * p.DZ;
   bool pair = env_pair >= 0 ? env_pair != 0 : (p.n_umma >= 128 && vox >= 148LL * 2 * 384);
   if (n_tiles != 1) pair = false;
-  p.kchunks = (p.ck + 63) / 64;
-  p.last_k16 = (p.ck - 64 * (p.kchunks - 1) + 15) / 16;
+  // K <= 32 (the gc = 32 data-gradients of the RRDB trunk, D's 32-channel layers): 64-byte operand rows
+  static const bool env_no_sw64 = getenv("WS_DISABLE_SW64") != nullptr;
+  const bool sw64 = ck_pad <= 32 && !pair && !env_no_sw64;
+  p.row_bytes = sw64 ? 64 : 128;
+  p.kelems = p.row_bytes / 2;
+  p.kchunks = (p.ck + p.kelems - 1) / p.kelems;
+  p.last_k16 = (p.ck - p.kelems * (p.kchunks - 1) + 15) / 16;
   // volume mode is opt-in (WS_TC2_VOL=1): measured on the RRDB trunk it is parity-clean but not faster (dense
   // conv 54 vs 48 us, dgrad 46 vs 45 us) — those layers are bound by the N=32 MMA floor and by the weight
   // stream, not by the activation re-reads this mode removes.
@@ -500,6 +513,10 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   bool vol = !pair && p.ky * p.kz > 1 && env_vol != 0;
   if (vol && !choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, false, p, 1, p.ky, p.kz, p.kchunks)) vol = false;
   if (!vol && !choose_cfg(p.N, p.DX, p.DY, p.DZ, p.kx, p.n_umma, pair, p)) return -1;
+  if (sw64) {  // the searches size their buffers for 128-byte rows
+    p.a_buf_bytes = (p.a_buf_bytes / 2 + 1023) / 1024 * 1024;
+    p.w_bytes /= 2;
+  }
   p.vol = vol ? 1 : 0;
   p.pitch_y = vol ? p.DZ + p.kz - 1 : p.DZ;
   p.box_z = p.pitch_y;
@@ -541,14 +558,14 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   MapKey ka;
   memset(&ka, 0, sizeof(ka));
   ka.ptr = reinterpret_cast<uintptr_t>(src.ptr);
-  ka.rank = 5; ka.dtype = WS_BF16;
+  ka.rank = 5; ka.dtype = WS_BF16 | (sw64 ? kMapSwizzle64 : 0u);
   ka.dims[0] = (uint64_t)p.ck; ka.dims[1] = (uint64_t)SZ; ka.dims[2] = (uint64_t)SY; ka.dims[3] = (uint64_t)SX;
   ka.dims[4] = (uint64_t)g.n;
   ka.strides[0] = (uint64_t)src.vs * 2;
   ka.strides[1] = (uint64_t)src.vs * 2 * SZ;
   ka.strides[2] = (uint64_t)src.vs * 2 * SZ * SY;
   ka.strides[3] = (uint64_t)src.ns * 2;
-  ka.box[0] = 64; ka.box[1] = (uint32_t)p.box_z; ka.box[2] = (uint32_t)p.box_y; ka.box[3] = (uint32_t)p.a_sub_slabs;
+  ka.box[0] = (uint32_t)p.kelems; ka.box[1] = (uint32_t)p.box_z; ka.box[2] = (uint32_t)p.box_y; ka.box[3] = (uint32_t)p.a_sub_slabs;
   ka.box[4] = 1;
   for (int i = 0; i < 5; ++i) ka.estr[i] = 1;
   CUtensorMap tmA, tmB;
@@ -556,11 +573,11 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   MapKey kb;
   memset(&kb, 0, sizeof(kb));
   kb.ptr = reinterpret_cast<uintptr_t>(packed_w);
-  kb.rank = 3; kb.dtype = WS_BF16;
+  kb.rank = 3; kb.dtype = WS_BF16 | (sw64 ? kMapSwizzle64 : 0u);
   kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)taps_total;
   kb.strides[0] = (uint64_t)ck_pad * 2;
   kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
-  kb.box[0] = 64; kb.box[1] = (uint32_t)(pair ? p.n_umma / 2 : p.n_umma); kb.box[2] = 1;
+  kb.box[0] = (uint32_t)p.kelems; kb.box[1] = (uint32_t)(pair ? p.n_umma / 2 : p.n_umma); kb.box[2] = 1;
   kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
   if (int e = get_tensor_map(kb, &tmB)) return e;
 

@@ -15,8 +15,9 @@ struct MapKey {
   uint32_t dtype;
 };
 static_assert(sizeof(MapKey) % 8 == 0, "MapKey must hash as 64-bit words");
+constexpr uint32_t kMapSwizzle64 = 1u << 8;  // OR into MapKey::dtype: SWIZZLE_64B (64-byte rows) instead of 128B
 
-// SWIZZLE_128B tiled tensor map for `key` (memset the key to 0 before filling it). Returns 0 on success.
+// SWIZZLE_128B (or, with kMapSwizzle64, SWIZZLE_64B) tiled tensor map for `key` (memset the key to 0 before filling it). Returns 0 on success.
 int get_tensor_map(const MapKey& key, CUtensorMap* out);
 
 }  // namespace ws

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "common.cuh"
 #include "tc_task.cuh"
 
@@ -562,11 +563,30 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   return 0;
 }
 
+namespace {
+// a few reusable events for the main -> auxiliary stream hand-offs of ws_rdb_backward (cudaStreamWaitEvent captures
+// the record that is current when it is called, so re-recording an event later does not disturb earlier waits)
+cudaEvent_t rdb_event() {
+  static std::mutex mu;
+  static cudaEvent_t ring[16];
+  static int next = -1;
+  std::lock_guard<std::mutex> lk(mu);
+  if (next < 0) {
+    for (auto& e : ring)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    next = 0;
+  }
+  cudaEvent_t e = ring[next];
+  next = (next + 1) % 16;
+  return e;
+}
+}  // namespace
+
 extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* buf,
                                const ws_tensor* dbuf, const ws_tensor* g_lff, const ws_tensor* gbuf,
                                const ws_tensor* dx, const float* const* w, void* const* packed,
                                float* const* dw, float* db_lff, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               void* stream, void* aux_stream, void* aux_workspace, size_t aux_workspace_bytes) {
   RdbGeom r;
   if (int e = rdb_geom(d, r)) return e;
   WS_REQUIRE(dy && dy->ptr && buf && buf->ptr && dbuf && dbuf->ptr && g_lff && g_lff->ptr && w && packed,
@@ -582,9 +602,22 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   // gbuf holds the gradients of ALL dense conv outputs side by side (n, nconv*gc, ..): the dgrad chain consumes
   // slice i as it goes, the weight gradients of the dense convs are then one merged GEMM at the end.
   const bool merged = want_w && rdb_merged_wgrad_ok(d, buf, gbuf);
+  // Weight gradients are off the critical path (nothing later in this block, or in the blocks before it, reads them):
+  // with an auxiliary stream they run beside the latency-bound data-gradient chain.  The caller joins the auxiliary
+  // stream before anything consumes dw / db_lff and keeps buf, g_lff, gbuf alive until then.
+  const bool aux = merged && aux_stream && aux_stream != stream && aux_workspace &&
+                   aux_workspace_bytes >= ws_rdb_backward_workspace_bytes(d);
+  cudaStream_t wst = aux ? (cudaStream_t)aux_stream : st;
+  void* wws = aux ? aux_workspace : workspace;
+  const size_t wws_bytes = aux ? aux_workspace_bytes : workspace_bytes;
   if (want_w && (dw[d->nconv] || db_lff)) {
-    if (int e = ws_conv3d_wgrad(&r.lff, buf, g_lff, dw[d->nconv], db_lff, 0, d->math, workspace, workspace_bytes,
-                                stream))
+    if (aux) {
+      cudaEvent_t ev = rdb_event();
+      WS_REQUIRE(ev != nullptr, "ws_rdb_backward: cannot create events");
+      WS_CHECK_CUDA(cudaEventRecord(ev, st));  // g_lff is complete
+      WS_CHECK_CUDA(cudaStreamWaitEvent(wst, ev, 0));
+    }
+    if (int e = ws_conv3d_wgrad(&r.lff, buf, g_lff, dw[d->nconv], db_lff, 0, d->math, wws, wws_bytes, (void*)wst))
       return e;
   }
   if (d->repack)
@@ -632,6 +665,21 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
       set_tail(ep, i - 1, s->cin);  // channels [cin - gc, cin) of this gradient = output of conv i-1
       g_ready = true;
     }
+    if (i == 0 && merged) {
+      // every g_j is complete (the tail epilogues / LeakyReLU-backward passes above): the merged weight gradient of
+      // the dense convs can go — beside conv0's data-gradient when there is an auxiliary stream
+      if (aux) {
+        cudaEvent_t ev = rdb_event();
+        WS_REQUIRE(ev != nullptr, "ws_rdb_backward: cannot create events");
+        WS_CHECK_CUDA(cudaEventRecord(ev, st));
+        WS_CHECK_CUDA(cudaStreamWaitEvent(wst, ev, 0));
+      }
+      ws_conv_shape ms = rdb_merged_shape(d);
+      int cin[WS_RDB_MAX_CONVS];
+      for (int j = 0; j < d->nconv; ++j) cin[j] = r.dense[j].cin;
+      if (int e = tc_rdb_wgrad(ConvGeom(ms), View(buf), View(gbuf), dw, cin, d->nconv, d->gc, wws, wws_bytes, wst))
+        return e;
+    }
     if (i == 0 && dx && dx->ptr) {
       // conv0 reads exactly the block input (cin = f): its data-gradient epilogue also adds the skip term and
       // writes dL/dx directly — dx = dbuf[:, :f] + dgrad_0 + beta1 * dy — instead of a separate axpby pass
@@ -641,14 +689,6 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
       continue;
     }
     if (int e = ws_conv3d_dgrad(s, gi, packed[i], dbuf, &ep, d->math, stream)) return e;
-  }
-  if (merged) {
-    ws_conv_shape ms = rdb_merged_shape(d);
-    int cin[WS_RDB_MAX_CONVS];
-    for (int i = 0; i < d->nconv; ++i) cin[i] = r.dense[i].cin;
-    if (int e = tc_rdb_wgrad(ConvGeom(ms), View(buf), View(gbuf), dw, cin, d->nconv, d->gc, workspace,
-                             workspace_bytes, st))
-      return e;
   }
   if (dx && dx->ptr && !dx_done) {
     if (int e = axpby_launch(View(dbuf), 1.f, View(dy), d->beta1, View(dx), d->n, d->f, v, st)) return e;

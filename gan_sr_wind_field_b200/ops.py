@@ -580,6 +580,46 @@ class RDBState:
         return self.packed[dgrad], int(repack)
 
 
+# ---- auxiliary stream for the off-critical-path weight gradients of the residual dense blocks -------------------
+_AUX = {}           # device -> (torch.cuda.Stream, workspace tensor)
+_AUX_JOIN_QUEUED = [False]
+
+
+def _aux_enabled() -> bool:
+    return os.environ.get("WINDSR_AUX_STREAM", "1") != "0"
+
+
+def _aux_stream(device, nbytes: int):
+    hit = _AUX.get(device)
+    if hit is None or hit[1].numel() < nbytes:
+        stream = hit[0] if hit is not None else torch.cuda.Stream(device=device)
+        hit = (stream, torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device))
+        _AUX[device] = hit
+    return hit
+
+
+def aux_join(device=None) -> None:
+    """Make the current stream wait for the auxiliary stream(s): call before anything reads parameter gradients that
+    an RDB backward produced (the autograd final callback below does it for a plain ``.backward()``; GradSync does it
+    before it packs a bucket)."""
+    for dev, (stream, _) in _AUX.items():
+        if device is None or dev == device:
+            torch.cuda.current_stream(dev).wait_stream(stream)
+
+
+def _queue_aux_join(device) -> None:
+    if _AUX_JOIN_QUEUED[0]:
+        return
+    _AUX_JOIN_QUEUED[0] = True
+
+    def _cb():
+        _AUX_JOIN_QUEUED[0] = False
+        with torch.cuda.device(device):
+            aux_join(device)
+
+    torch.autograd.Variable._execution_engine.queue_callback(_cb)
+
+
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -661,13 +701,25 @@ class RDBFn(torch.autograd.Function):
                 db = torch.empty_like(params[nconv + 1], dtype=torch.float32)
                 grads[nconv + 1] = db
             dw_arr = _ptr_array(grads[:nconv + 1])
-        wsp = _workspace(int(lib.ws_rdb_backward_workspace_bytes(C.byref(desc))), dev)
+        nbytes = int(lib.ws_rdb_backward_workspace_bytes(C.byref(desc)))
+        wsp = _workspace(nbytes, dev)
         dyv, bv, dbv, glv, gv = view(dy), view(buf), view(dbuf), view(g_lff), view(g)
         dxv = view(dx) if dx is not None else null_view()
         wd = [p.detach() for p in params[:nconv + 1]]
+        # weight gradients on the auxiliary stream (they are off the critical path of the backward chain)
+        use_aux = need_params and _aux_enabled() and get_precision() == "bf16"
+        aux_s, aux_w = _aux_stream(dev, nbytes) if use_aux else (None, None)
         check(lib.ws_rdb_backward(C.byref(desc), C.byref(dyv), C.byref(bv), C.byref(dbv), C.byref(glv), C.byref(gv),
                                   C.byref(dxv), _ptr_array(wd), _ptr_array(packed), dw_arr, ptr(db),
-                                  wsp.data_ptr(), wsp.numel(), stream_ptr()), "ws_rdb_backward")
+                                  wsp.data_ptr(), wsp.numel(), stream_ptr(),
+                                  aux_s.cuda_stream if use_aux else None, aux_w.data_ptr() if use_aux else None,
+                                  aux_w.numel() if use_aux else 0), "ws_rdb_backward")
+        if use_aux:
+            # the operands of the weight gradients must outlive this function on the auxiliary stream, and whoever
+            # reads the gradients must wait for it (autograd's final callback; GradSync joins before packing)
+            for t in (buf, g, g_lff, *[t for t in grads if t is not None]):
+                t.record_stream(aux_s)
+            _queue_aux_join(dev)
         douter = None
         if ctx.has_outer and need[1]:
             douter = dy if cfg["beta2"] == 1.0 else dy * cfg["beta2"]

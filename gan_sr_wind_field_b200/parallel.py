@@ -80,6 +80,8 @@ class GradSync:
         live = [p for p in b.params if p.grad is not None]
         if not live:
             return
+        from . import ops
+        ops.aux_join()  # weight gradients of the residual dense blocks are produced on an auxiliary stream
         dev = live[0].grad.device
         if b.flat is None or b.flat.device != dev:
             b.flat = torch.zeros(b.numel, dtype=torch.float32, device=dev)

@@ -177,6 +177,9 @@ int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws_tensor* ou
                    void* workspace, size_t workspace_bytes, void* stream);
 /* bytes of the `workspace` ws_rdb_backward needs */
 size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d);
+/* aux_stream (optional, with its own aux_workspace of ws_rdb_backward_workspace_bytes): the weight gradients run on
+ * it beside the data-gradient chain; the caller must make the consumer of dw / db_lff wait for aux_stream and keep
+ * buf, g_lff, g alive until then.  NULL: everything on `stream`. */
 /* dy: fp32 gradient of `out`.  Scratch: dbuf fp32 (n, f+nconv*gc, ..), g_lff activation-dtype (n,f,..),
  * g activation-dtype (n,nconv*gc,..) — the output gradients of all dense convs side by side (their weight
  * gradients are one merged GEMM on the tensor-core path).  dx (optional) = dL/dx incl. the beta1 skip.  dw[i] (optional, torch layout)
@@ -184,7 +187,8 @@ size_t ws_rdb_backward_workspace_bytes(const ws_rdb_desc* d);
 int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* buf, const ws_tensor* dbuf,
                     const ws_tensor* g_lff, const ws_tensor* g, const ws_tensor* dx, const float* const* w,
                     void* const* packed, float* const* dw, float* db_lff, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    size_t workspace_bytes, void* stream, void* aux_stream, void* aux_workspace,
+                    size_t aux_workspace_bytes);
 
 /* ---- nearest upsample (x2 in x and y, z untouched): nn.Upsample(scale_factor=(2,2,1)) torch_blocks.py:347 */
 /* in: (n, c, x, y, z) view, out: (n, c, 2x, 2y, z) view; bit-exact gather out[x,y,z] = in[x/2, y/2, z] */

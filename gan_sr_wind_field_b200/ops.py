@@ -655,6 +655,7 @@ class RDBFn(torch.autograd.Function):
                               cfg["beta2"] if outer is not None else 0.0, math_mode(), 0)
         state: RDBState = cfg["state"]
         packed, desc.repack = state.buffers(desc, params, 0)
+        _AUX_JOIN_QUEUED[0] = False  # a backward pass that died before its final callback must not mute the next one
         buf = empty_cl(n, ctot, X, Y, Z, cdt, x.device)
         out = empty_cl(n, f, X, Y, Z, torch.float32, x.device)
         xv, bv, ov = view(x), view(buf), view(out)

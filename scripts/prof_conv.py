@@ -28,6 +28,24 @@ acc = layer in ("dg", "dg0")   # dense-conv dgrad look-alike: fp32 output accumu
 y = ops.zeros_cl(n, cout, *vol, torch.float32 if acc or layer.endswith("x") else torch.bfloat16, "cuda")
 cache = ops.PackedWeights()
 kw = dict(res1=y, beta1=1.0) if acc else dict(slope=0.2)
+if len(sys.argv) > 3 and sys.argv[3] == "wgrad":
+    # weight-gradient of the same layer (main 128-row M block only for cout = 144, as the step runs it)
+    co = min(cout, 128)
+    dy = ops.empty_cl(n, co, *vol, torch.bfloat16, "cuda")
+    dy.copy_(torch.randn(n, co, *vol, generator=g, device="cuda"))
+    shape_w = ops.make_shape(x.shape, co, kk, 1, p)
+    ops.conv_wgrad(x, dy, shape_w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.conv_wgrad(x, dy, shape_w)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * n * vol[0] * vol[1] * vol[2] * cin * co * kk[0] * kk[1] * kk[2]
+    print(f"{layer} wgrad ({cin}->{co}): {ms:.3f} ms/launch, {fl / ms / 1e9:.1f} TFLOP/s (dense-MAC convention)")
+    sys.exit(0)
 ops.conv_fwd(x, w, cache, shape, y, **kw)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -41,8 +41,9 @@ struct WgParams {
   int bx, by, bz, rows;  // voxel tile (in OUTPUT / dy coordinates); rows % 16 == 0
   int tiles_x, tiles_y, tiles_z;
   long long total_tiles;       // N * tiles
-  long long items;             // tap_groups * total_tiles: the (tap group, voxel tile) work items of one M block
+  long long items;             // ranges * tap_groups * range_tiles: the (tile range, tap group, tile) work items of one M block
   long long items_per_cta;     // each CTA takes a contiguous run of items -> one or more (tap group, tile range) segments
+  long long range_tiles;       // voxel tiles per range (the last range may be short: tiles >= total_tiles are skipped)
   int kx, ky, kz, sx, sy, sz, px, py, pz;
   int taps, taps_per_cta, tap_groups;
   int m_total;           // channels of the M operand covered by this launch (grid.z blocks of 128)
@@ -81,9 +82,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   const int m0 = p.m0 + (int)blockIdx.z * 128;                       // this CTA's 128-row M block
   const int m_valid = min(128, p.m_total - (int)blockIdx.z * 128);
   const int m_blocks = (m_valid + 63) / 64;
-  // Work = (tap group, voxel tile) items in group-major order; CTA b owns items [b*per, (b+1)*per): the same load
-  // for every CTA however taps and tiles divide (hr_convs.0: 63 groups x 2 splits left 22 of 148 SMs idle).  A run
-  // that crosses a group boundary is processed as consecutive SEGMENTS, each with its own accumulate / reduce phase.
+  // Work = (tile range, tap group, tile) items in that order; CTA b owns items [b*per, (b+1)*per): the same load for
+  // every CTA however taps and tiles divide (hr_convs.0: 63 groups x 2 splits left 22 of 148 SMs idle), and the CTAs
+  // of a wave that share a tile range walk the same tiles at the same time, so a tile is fetched from DRAM once per
+  // pass and re-used out of L2 by the other tap groups (ncu: 27 GB of DRAM reads per launch in group-major order).
+  // A run that crosses a (range, group) boundary is processed as consecutive SEGMENTS, each with its own accumulate
+  // / reduce phase.
   const long long item_lo = (long long)blockIdx.x * p.items_per_cta;
   const long long item_hi = min(p.items, item_lo + p.items_per_cta);
 
@@ -125,8 +129,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       const int fix_c0 = p.shift_on_m ? p.n0 : m0;
       const int sh_c0 = p.shift_on_m ? m0 : p.n0;
       for (long long item = item_lo; item < item_hi; ++item) {
-        const long long tile = item % p.total_tiles;
-        const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+        const long long sg = item / p.range_tiles;
+        const long long tile = (sg / p.tap_groups) * p.range_tiles + item % p.range_tiles;
+        if (tile >= p.total_tiles) continue;  // tail of the last range
+        const int tap_lo = (int)(sg % p.tap_groups) * p.taps_per_cta;
         const int tap_hi = min(p.taps, tap_lo + p.taps_per_cta);
         int t = (int)(tile % tiles_per_n);
         const int n = (int)(tile / tiles_per_n);
@@ -169,10 +175,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       uint32_t acc_tile = 0;
       int seg = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
-        const long long tile = item % p.total_tiles;
-        const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+        const long long sg = item / p.range_tiles;
+        const long long tile = (sg / p.tap_groups) * p.range_tiles + item % p.range_tiles;
+        const int tap_lo = (int)(sg % p.tap_groups) * p.taps_per_cta;
         const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
-        if (item > item_lo && tile == 0) {
+        if (item > item_lo && item % p.range_tiles == 0) {
           // group boundary: hand the finished accumulators to the epilogue, then wait until it has drained them
           if (ptx::elect_one()) ptx::mma_commit(accum_bar);
           __syncwarp();
@@ -181,6 +188,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           ++seg;
           acc_tile = 0;
         }
+        if (tile >= p.total_tiles) continue;  // tail of the last range (never the first item of a segment)
         ptx::mbar_wait(a_full(as), aph);
         const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
         for (int tp = 0; tp < ntap; ++tp) {
@@ -217,9 +225,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     ptx::griddep_wait();  // the workspace memset / earlier reductions precede the atomics
     int seg = 0;
     for (long long item = item_lo; item < item_hi; ++seg) {
-      const int tap_lo = (int)(item / p.total_tiles) * p.taps_per_cta;
+      const int tap_lo = (int)((item / p.range_tiles) % p.tap_groups) * p.taps_per_cta;
       const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
-      const long long seg_end = min(item_hi, (item / p.total_tiles + 1) * p.total_tiles);
+      const long long seg_end = min(item_hi, (item / p.range_tiles + 1) * p.range_tiles);
       ptx::mbar_wait(accum_bar, (uint32_t)(seg & 1));
       ptx::tc_fence_after();
       for (int tp = 0; tp < ntap; ++tp) {
@@ -344,44 +352,58 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   const double atom = 128.0 * p.n_umma * 0.35;  // coalesced red.global.add epilogue of one tap (measured)
   const int max_tpc = 512 / p.n_umma;
   double best = 1e30;
-  int best_tpc = 1;
-  long long best_ncta = 1;
+  int best_tpc = 1, best_gpc = 1;
+  long long best_range = p.total_tiles;
   for (int tpc = 1; tpc <= max_tpc && tpc <= p.taps; ++tpc) {
     const int tg = (p.taps + tpc - 1) / tpc;
-    const long long items = (long long)tg * p.total_tiles;
-    for (int target : {37, 74, 148, 296, 444}) {
-      long long ncta = target / mz;
-      if (ncta < 1) ncta = 1;
-      if (ncta > items) ncta = items;
-      const long long per = (items + ncta - 1) / ncta;
-      ncta = (items + per - 1) / per;
-      const long long ctas = ncta * mz;
-      const long long waves = (ctas + 147) / 148;
-      const double segs = 1.0 + (double)(per - 1) / (double)p.total_tiles + (per < p.total_tiles ? 1.0 : 0.0) * 0.5;
-      // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many CTAs on a
-      // short K loop the sum over a wave, not one CTA's epilogue, is what is waited for
-      const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;
-      const double atom_chip = wave_ctas * segs * tpc * 128.0 * p.n_umma / 512.0;
-      const double atom_t = segs * tpc * atom > atom_chip ? segs * tpc * atom : atom_chip;
-      const double t = (double)waves * (per * (tpc * unit + (double)fix_alloc * blk / 33.0) + atom_t + 8000.0);
-      if (t < best) { best = t; best_tpc = tpc; best_ncta = ncta; }
+    for (int gpc : {1, 2, 3, 4, 6, 8}) {          // tap groups (= segments) per CTA
+      if (gpc > tg) break;
+      for (int s_try : {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128}) {
+        long long S = s_try;                       // tile ranges
+        if (S > p.total_tiles) break;
+        const long long R = (p.total_tiles + S - 1) / S;
+        S = (p.total_tiles + R - 1) / R;
+        const long long ncta = (S * tg + gpc - 1) / gpc;
+        const long long ctas = ncta * mz;
+        if (ctas > 444) break;
+        const long long waves = (ctas + 147) / 148;
+        const long long per = (long long)gpc * R;
+        // CTAs that walk the same tiles at the same time: L2 serves their re-reads (good), but past ~2 dozen the
+        // same lines are hammered by too many SMs at once (measured on hr_convs.0: 63 sharers 8.3 ms, 21 sharers
+        // 5.9 ms, none — group-major order — 6.5 ms with 27 GB of DRAM re-reads)
+        const double sharers = (double)(tg + gpc - 1) / gpc;
+        const double hot = sharers > 24.0 ? 1.0 + (sharers - 24.0) / 40.0 : (sharers < 4.0 ? 1.15 : 1.0);
+        // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many CTAs on a
+        // short K loop the sum over a wave, not one CTA's epilogue, is what is waited for
+        const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;
+        const double atom_chip = wave_ctas * gpc * tpc * 128.0 * p.n_umma / 512.0;
+        const double atom_t = gpc * tpc * atom > atom_chip ? gpc * tpc * atom : atom_chip;
+        const double item_load = hot * (tpc * unit_load + (double)fix_alloc * blk / 33.0);
+        const double item_mma = tpc * unit_mma;
+        const double t =
+            (double)waves * (per * (item_mma > item_load ? item_mma : item_load) + atom_t + 8000.0);
+        if (t < best) { best = t; best_tpc = tpc; best_gpc = gpc; best_range = R; }
+      }
     }
   }
-  // experiment hook: WS_WGRAD_FORCE="taps_per_cta,ctas" (read at every launch)
+  // experiment hook: WS_WGRAD_FORCE="taps_per_cta,groups_per_cta,tile_ranges" (read at every launch)
   if (const char* f = getenv("WS_WGRAD_FORCE")) {
-    int ftpc = 0, fcta = 0;
-    if (sscanf(f, "%d,%d", &ftpc, &fcta) == 2 && ftpc >= 1 && ftpc <= max_tpc && fcta >= 1) {
+    int ftpc = 0, fgpc = 0, fs = 0;
+    if (sscanf(f, "%d,%d,%d", &ftpc, &fgpc, &fs) == 3 && ftpc >= 1 && ftpc <= max_tpc && fgpc >= 1 && fs >= 1) {
       best_tpc = ftpc;
-      best_ncta = fcta;
+      best_gpc = fgpc;
+      best_range = (p.total_tiles + fs - 1) / fs;
     }
   }
   p.taps_per_cta = best_tpc;
   p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
-  p.items = (long long)p.tap_groups * p.total_tiles;
-  if (best_ncta > p.items) best_ncta = p.items;
-  if (best_ncta > 65535LL * 32) best_ncta = 65535LL * 32;
-  p.items_per_cta = (p.items + best_ncta - 1) / best_ncta;
+  p.range_tiles = best_range < 1 ? 1 : best_range;
+  const long long ranges = (p.total_tiles + p.range_tiles - 1) / p.range_tiles;
+  p.items = ranges * p.tap_groups * p.range_tiles;
+  // runs are whole segments: every segment a CTA sees then starts at a valid tile (only range tails are skipped)
+  p.items_per_cta = (long long)best_gpc * p.range_tiles;
   const long long ncta = (p.items + p.items_per_cta - 1) / p.items_per_cta;
+  WS_REQUIRE(ncta <= 2147483647LL, "wgrad: too many CTAs");
   uint32_t cols = 32;
   while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;

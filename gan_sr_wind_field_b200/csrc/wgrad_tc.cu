@@ -358,7 +358,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     const int tg = (p.taps + tpc - 1) / tpc;
     for (int gpc : {1, 2, 3, 4, 6, 8}) {          // tap groups (= segments) per CTA
       if (gpc > tg) break;
-      for (int s_try : {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128}) {
+      for (int s_try = 1; s_try <= 160; s_try += (s_try < 32 ? 1 : (s_try < 64 ? 4 : 16))) {
         long long S = s_try;                       // tile ranges
         if (S > p.total_tiles) break;
         const long long R = (p.total_tiles + S - 1) / S;

@@ -358,21 +358,30 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     const int tg = (p.taps + tpc - 1) / tpc;
     for (int gpc : {1, 2, 3, 4, 6, 8}) {          // tap groups (= segments) per CTA
       if (gpc > tg) break;
-      for (int s_try = 1; s_try <= 160; s_try += (s_try < 32 ? 1 : (s_try < 64 ? 4 : 16))) {
-        long long S = s_try;                       // tile ranges
-        if (S > p.total_tiles) break;
+      // candidates: every range count up to 32, a coarser ladder above, and the counts that fill exactly 1 / 2 / 3
+      // waves of 148 CTAs
+      long long cand[64];
+      int ncand = 0;
+      for (int s_try = 1; s_try <= 160; s_try += (s_try < 32 ? 1 : (s_try < 64 ? 4 : 16))) cand[ncand++] = s_try;
+      for (int k = 1; k <= 3; ++k) {
+        const long long fill = 148LL * k * gpc / ((long long)tg * mz);
+        if (fill >= 1) cand[ncand++] = fill;
+      }
+      for (int ci = 0; ci < ncand; ++ci) {
+        long long S = cand[ci];                    // tile ranges
+        if (S > p.total_tiles) continue;
         const long long R = (p.total_tiles + S - 1) / S;
         S = (p.total_tiles + R - 1) / R;
         const long long ncta = (S * tg + gpc - 1) / gpc;
         const long long ctas = ncta * mz;
-        if (ctas > 444) break;
+        if (ctas > 444) continue;
         const long long waves = (ctas + 147) / 148;
         const long long per = (long long)gpc * R;
         // CTAs that walk the same tiles at the same time: L2 serves their re-reads (good), but past ~2 dozen the
         // same lines are hammered by too many SMs at once (measured on hr_convs.0: 63 sharers 8.3 ms, 21 sharers
         // 5.9 ms, none — group-major order — 6.5 ms with 27 GB of DRAM re-reads)
         const double sharers = (double)(tg + gpc - 1) / gpc;
-        const double hot = sharers > 24.0 ? 1.0 + (sharers - 24.0) / 40.0 : (sharers < 4.0 ? 1.15 : 1.0);
+        const double hot = sharers > 24.0 ? 1.0 + (sharers - 24.0) / 40.0 : 1.0;
         // red.global.add also has a chip-wide rate (a few hundred lanes/clk when coalesced): with many CTAs on a
         // short K loop the sum over a wave, not one CTA's epilogue, is what is waited for
         const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;

@@ -265,3 +265,51 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_im2col_weight_reordering_matches_conv():
+    """Host-side transform of the narrow first layers: conv(x, w) == U @ w'^T with U[v, tap*cin+ci] = x[ci, v (+) tap]
+    (what ws_im2col builds on the device) and w' = ops._im2col_weight(w) — checked with torch ops on the CPU."""
+    import torch.nn.functional as F
+    from gan_sr_wind_field_b200 import ops
+    torch.manual_seed(3)
+    cin, cout, k = 3, 32, 3
+    x = torch.randn(2, cin, 6, 5, 4)
+    w = torch.randn(cout, cin, k, k, k)
+    ref = F.conv3d(x, w, padding=1)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    cols = []
+    for ti in range(k):
+        for tj in range(k):
+            for tl in range(k):
+                for ci in range(cin):
+                    cols.append(xp[:, ci, ti:ti + 6, tj:tj + 5, tl:tl + 4])
+    U = torch.stack(cols, 1)                      # (n, taps*cin, X, Y, Z), tap-major / ci-minor columns
+    cpad = 96
+    w2 = ops._im2col_weight(w, cpad).reshape(cout, cpad)
+    assert torch.all(w2[:, k ** 3 * cin:] == 0)
+    out = torch.einsum("ncxyz,oc->noxyz", U, w2[:, :k ** 3 * cin])
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_xfold_weight_matches_conv():
+    """x-fold of a narrow-output conv (hr_convs.2): a (1,ky,kz) conv with the kx taps stacked on the output channels
+    followed by y[x] = sum_dx U[x + dx - px][dx] equals the direct conv — checked with torch ops on the CPU."""
+    import torch.nn.functional as F
+    from gan_sr_wind_field_b200 import ops
+    torch.manual_seed(4)
+    co, ci, k, p = 3, 8, 5, 2
+    x = torch.randn(1, ci, 7, 6, 5)
+    w = torch.randn(co, ci, k, k, k)
+    ref = F.conv3d(x, w, padding=p)
+    w5 = ops.XFoldConvFn._folded_weight(w)        # (16, ci, 1, k, k): rows dx*co + c, zero padded to 16
+    assert w5.shape == (16, ci, 1, k, k) and torch.all(w5[k * co:] == 0)
+    U = F.conv3d(x, w5, padding=(0, p, p))        # (1, 16, X, Y, Z)
+    X = x.shape[2]
+    out = torch.zeros_like(ref)
+    for dx in range(k):
+        for xx in range(X):
+            xs = xx + dx - p
+            if 0 <= xs < X:
+                out[:, :, xx] += U[:, dx * co:(dx + 1) * co, xs]
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)

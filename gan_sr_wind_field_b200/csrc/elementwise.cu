@@ -543,7 +543,7 @@ __global__ void im2col_small_kernel(View x, View u, ConvGeom g, int cpad8, long 
 
 // same, u channels-last with cpad % 8 == 0: one 8-channel vector store per thread
 __global__ void xunfold_st8_kernel(View dout, View u, int co, int kx, int pad, int cpad8, int X, int Y, int Z,
-                                   long long total) {
+                                   long long total, int src_vec) {
   const long long V = (long long)X * Y * Z;
   const long long sx = (long long)Y * Z;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -554,6 +554,20 @@ __global__ void xunfold_st8_kernel(View dout, View u, int co, int kx, int pad, i
     const int nn = (int)(r / V);
     const int xx = (int)(v / sx);
     float f[8];
+    if (src_vec) {
+      // co % 8 == 0 and a channels-last source: the 8 channels of this chunk come from ONE shifted voxel
+      const int ch0 = q * 8;
+      const int dx = ch0 / co, c0 = ch0 - dx * co;
+      const int xs = xx - dx + pad;
+      if (ch0 < kx * co && xs >= 0 && xs < X) {
+        ld8(dout, dout.off(nn, c0, v + (long long)(pad - dx) * sx), f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      st8(u, u.off(nn, q * 8, v), f);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = q * 8 + j;
@@ -929,7 +943,9 @@ int xunfold_launch(const View& dout, const View& u, int n, int co, int kx, int p
   long long total = (long long)n * cpad * X * Y * Z;
   if (total <= 0) return 0;
   if (vec8_ok(u, cpad)) {
-    xunfold_st8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dout, u, co, kx, pad, cpad / 8, X, Y, Z, total / 8);
+    const int src_vec = (co % 8 == 0 && vec8_ok(dout, co)) ? 1 : 0;
+    xunfold_st8_kernel<<<grid_for(total / 8), kBlock, 0, st>>>(dout, u, co, kx, pad, cpad / 8, X, Y, Z, total / 8,
+                                                              src_vec);
     WS_POST_LAUNCH(1);
     return 0;
   }

@@ -167,3 +167,34 @@ def test_empty_and_ragged_edges():
                 y = ops.empty_cl(1, cout, *ref.shape[2:], dt, "cuda")
                 ops.conv_fwd(_to_act(x, dt), w.cuda(), None, shape, y)
             assert rel_l2(y.float(), ref) <= TOL[mode], (mode, cin, cout, vol)
+
+
+@pytest.mark.gpu
+def test_module_path_144_channels_remainder_xfold_wgrad():
+    """hr_convs.0 as the training step runs it (module + autograd): 144 = 128 + 16 output channels, so the weight
+    gradient is a 128-row tensor-core GEMM plus an x-folded (1,5,5) GEMM for the 16-channel remainder (ws_xunfold);
+    forward, dL/dx and dL/dw against torch's fp32 CPU conv."""
+    import torch.nn.functional as F
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.torch_blocks import Conv3d
+    torch.manual_seed(9)
+    conv = Conv3d(144, 144, 5, 1, 2, bias=False)
+    x = torch.randn(1, 144, 13, 9, 10)
+    gy = torch.randn(1, 144, 13, 9, 10)
+    xr = x.clone().requires_grad_(True)
+    wr = conv.weight.detach().clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, padding=2)
+    yr.backward(gy)
+    conv.cuda()
+    with ops.precision("bf16"):
+        xg = ops.empty_cl(1, 144, 13, 9, 10, torch.bfloat16, "cuda")
+        xg.copy_(x.cuda())
+        xg.requires_grad_(True)
+        y = conv(xg)
+        y.backward(gy.cuda().to(y.dtype))
+    assert rel_l2(y, yr) <= TOL["bf16"]
+    assert rel_l2(xg.grad, xr.grad) <= TOL["bf16"]
+    assert rel_l2(conv.weight.grad, wr.grad) <= TOL["bf16"]
+    # both halves of the output-channel split are right on their own
+    assert rel_l2(conv.weight.grad[:128], wr.grad[:128]) <= TOL["bf16"]
+    assert rel_l2(conv.weight.grad[128:], wr.grad[128:]) <= TOL["bf16"]

@@ -20,6 +20,8 @@
 // Generator_3D_Resnet_ESRGAN.py:105 for the stride-1 layers (dgrad = same kernel, taps flipped, channel
 // roles swapped, pad' = k-1-p) and the strided discriminator forward (torch_blocks.py:467-506).
 #include <cuda.h>
+#include <array>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -293,9 +295,8 @@ void choose_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx,
 void choose_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
   struct Hit { int bx, by, bz; };
   static std::mutex mu;
-  static std::unordered_map<unsigned long long, Hit> memo;
-  unsigned long long key = 1469598103934665603ull;
-  for (int v : {DX, DY, DZ, sx, sy, sz}) key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  static std::map<std::array<int, 6>, Hit> memo;  // keyed by the full geometry (no hash collisions)
+  const std::array<int, 6> key = {DX, DY, DZ, sx, sy, sz};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);

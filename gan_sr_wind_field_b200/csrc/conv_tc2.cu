@@ -17,7 +17,8 @@
 // Generator_3D_Resnet_ESRGAN.py:95-111 (hr_convs).
 #include <cuda.h>
 #include <mutex>
-#include <unordered_map>
+#include <array>
+#include <map>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -430,12 +431,9 @@ bool choose_cfg(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc
                 int kz = 1, int kchunks = 1) {
   struct Hit { bool ok; int by, tx, t_m, slabrows, halo_rows, a_buf_bytes, w_bytes, a_bufs; };
   static std::mutex mu;
-  static std::unordered_map<unsigned long long, Hit> memo;
-  unsigned long long key = 1469598103934665603ull;
-  for (long long v : {(long long)N, (long long)DX, (long long)DY, (long long)DZ, (long long)kx, (long long)n_umma,
-                      (long long)pair, (long long)vol, (long long)(vol ? ky : 1), (long long)(vol ? kz : 1),
-                      (long long)(vol ? kchunks : 1)})
-    key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  static std::map<std::array<int, 11>, Hit> memo;  // keyed by the full geometry (no hash collisions)
+  const std::array<int, 11> key = {N, DX, DY, DZ, kx, n_umma, (int)pair, vol, vol ? ky : 1, vol ? kz : 1,
+                                   vol ? kchunks : 1};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);

@@ -27,7 +27,8 @@
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include <mutex>
-#include <unordered_map>
+#include <array>
+#include <map>
 
 namespace ws {
 
@@ -289,9 +290,8 @@ void choose_wgrad_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, in
 void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
   struct Hit { int bx, by, bz; };
   static std::mutex mu;
-  static std::unordered_map<unsigned long long, Hit> memo;
-  unsigned long long key = 1469598103934665603ull;
-  for (int v : {DX, DY, DZ, sx, sy, sz}) key = (key ^ (unsigned long long)v) * 1099511628211ull;
+  static std::map<std::array<int, 6>, Hit> memo;  // keyed by the full geometry (no hash collisions)
+  const std::array<int, 6> key = {DX, DY, DZ, sx, sy, sz};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);

@@ -43,6 +43,7 @@ class BaseGAN(lc.GlobalLoggingClass):
         if _is_path(discriminator_load_path):
             self.D.load_state_dict(torch.load(discriminator_load_path, map_location="cpu"))
             self.G.eval()
+        self._after_load()
         if not _is_path(state_load_path):
             return None, None
         state = torch.load(state_load_path, map_location=self.device)
@@ -55,7 +56,23 @@ class BaseGAN(lc.GlobalLoggingClass):
             mine.load_state_dict(saved)
         for mine, saved in zip(self.schedulers, scheds):
             mine.load_state_dict(saved)
+        self._after_load()
         return state["epoch"], state["it"]
+
+    def _after_load(self):
+        """Loaded weights / optimiser state invalidate everything derived from the old ones: captured CUDA graphs
+        (they hold pointers to the previous optimiser state), packed operand copies; under data parallelism every
+        rank takes rank 0's weights and buffers (only rank 0 is guaranteed to have read the files)."""
+        from .. import ops
+        from ..parallel import broadcast_module
+        for attr in ("_graphs", "_eager_calls"):
+            if hasattr(self, attr):
+                getattr(self, attr).clear()
+        ops.invalidate_packed_weights()
+        if getattr(self, "world_size", 1) > 1:
+            for m in (self.G, self.D):
+                if m is not None:
+                    broadcast_module(m)
 
     def save_model(self, save_basepath, epoch, it, save_G=True, save_D=True, save_state=True):
         if getattr(self, "rank", 0) != 0:

@@ -10,7 +10,15 @@ is executed:
   (``ops.WindLossFn``); the scalar formula on top is a handful of 0-d tensor ops;
 * the schedule is decided from the host-side iteration counter and the 8 ``isnan/isinf`` probes collapse to a
   single host read per G step (the reference syncs >= 9 times per step);
-* label noise is sampled on the device;
+* label noise is sampled on the device; every iteration-dependent scalar (label values, instance-noise scales, the
+  "labels are exactly 0.9" switch, learning rate) lives in a small device vector, so that
+* a whole G step and a whole D step are each captured ONCE into a CUDA graph (after a few eager warm-up calls) and
+  replayed — ~2 000 kernel launches per step cost the host one ``cudaGraphLaunch`` (``WINDSR_CUDA_GRAPH=0`` keeps
+  the eager path);
+* Adam is ``optim.WindAdam`` (one hand-written multi-tensor kernel with a device-side skip flag);
+* with ``adversarial_loss_weight == 0`` (both shipped pretrained configs) a G step does not run the discriminator:
+  the reference multiplies that branch by 0.0 (:426), so loss and gradients are unchanged
+  (``WINDSR_SKIP_D_WHEN_ZERO=0`` runs it anyway, e.g. to reproduce a NaN coming out of D);
 * with ``torch.distributed`` initialised the step is batch-sharded data parallel: gradients of the network
   being updated are averaged with a bucketed NCCL all-reduce overlapped with backward (``parallel.GradSync``).
   BatchNorm statistics, RaGAN batch means and the loss normalisers stay per-rank (stock DDP semantics; see
@@ -30,7 +38,8 @@ import torch.optim.lr_scheduler as lr_scheduler
 from .. import ops
 from ..CNN_models.Discriminator_3D import Discriminator_3D
 from ..CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
-from ..parallel import GradSync
+from ..optim import WindAdam
+from ..parallel import GradSync, allreduce_max_, broadcast_module
 from ..tools import initialization, trainingtricks
 from .baseGAN import BaseGAN
 
@@ -42,10 +51,36 @@ def _zero():
     return torch.zeros(1)
 
 
+def _leaf_probe(module):
+    """The LAST leaf sub-module: the cheapest place where a partial ``.eval()`` / ``.train()`` done behind this
+    class's back (``D.features.eval()``) shows up next to the top-level flag."""
+    probe = getattr(module, "_windsr_mode_probe", None)
+    if probe is None:
+        leaves = [m for m in module.modules() if not list(m.children())]
+        probe = (leaves[0], leaves[len(leaves) // 2], leaves[-1]) if leaves else (module,)
+        object.__setattr__(module, "_windsr_mode_probe", probe)
+    return probe
+
+
 def _set_mode(module, training: bool):
-    """module.train()/.eval() walks every sub-module (~1000 here): skip it when the mode already matches."""
-    if module.training != training:
+    """module.train()/.eval() walks every sub-module (~1000 here): skip the walk when the top-level flag AND three
+    probe leaves (first / middle / last) already agree; the reference re-applies the mode every step
+    (wind_field_GAN_3D.py:248,274,478), so a mode changed by outside code must not survive."""
+    if module.training != training or any(m.training != training for m in _leaf_probe(module)):
         module.train(training)
+
+
+def _set_requires_grad(module, flag: bool):
+    """``for p in D.parameters(): p.requires_grad = flag`` (wind_field_GAN_3D.py:481-482,536-537) without the walk
+    when first / last parameters already agree."""
+    params = getattr(module, "_windsr_param_probe", None)
+    if params is None:
+        ps = list(module.parameters())
+        params = (ps[0], ps[len(ps) // 2], ps[-1]) if ps else ()
+        object.__setattr__(module, "_windsr_param_probe", params)
+    if any(p.requires_grad != flag for p in params):
+        for p in module.parameters():
+            p.requires_grad = flag
 
 
 class wind_field_GAN_3D(BaseGAN):
@@ -67,7 +102,10 @@ class wind_field_GAN_3D(BaseGAN):
         self.epsilon_PSNR = torch.tensor(1e-8, device=self.device)
         self.feature_extractor = None
         self._inflight = []  # CUDA events of the last training steps (bounded host run-ahead)
-        self._D_requires_grad = None  # cached state of the D.parameters() requires_grad toggle
+        self._graphs = {}       # (kind, shapes, precision) -> graph_step.StepGraph
+        self._eager_calls = {}  # the same key -> eager calls so far (a step is captured after a few of them)
+        self._scalars = None    # device vector of the iteration-dependent scalars (see _write_scalars)
+        self._scalar_ring, self._scalar_slot = [], 0
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
 
@@ -102,15 +140,22 @@ class wind_field_GAN_3D(BaseGAN):
         initialization.init_weights(self.D, scale=d.weight_init_scale)
 
         t = cfg.training
-        # Same Adam as wind_field_GAN_3D.py:147-160; on a GPU the single-kernel ("fused") implementation is used:
-        # it takes a device-side ``found_inf`` flag, which is how the reference's "skip the step when the loss is
-        # not finite" guard (:457) runs without a host read.
-        fused = self.device.type == "cuda" and os.environ.get("WINDSR_FUSED_ADAM", "1") != "0"
-        self._fused_adam = fused
-        self.optimizer_G = torch.optim.Adam(self.G.parameters(), lr=t.learning_rate_g, fused=fused,
-                                            weight_decay=t.adam_weight_decay_g, betas=(t.adam_beta1_g, 0.999))
-        self.optimizer_D = torch.optim.Adam(self.D.parameters(), lr=t.learning_rate_d, fused=fused,
-                                            weight_decay=t.adam_weight_decay_d, betas=(t.adam_beta1_d, 0.999))
+        if self.world_size > 1:
+            # replicas must start from the same weights / BatchNorm buffers whatever the callers seeded, and then
+            # draw DIFFERENT dropout / label-noise / instance-noise streams
+            broadcast_module(self.G)
+            broadcast_module(self.D)
+            seed = int(getattr(getattr(cfg, "env", None), "fixed_seed", 0) or 0)
+            torch.manual_seed(seed + self.rank)
+        # Same Adam as wind_field_GAN_3D.py:147-160, as one hand-written multi-tensor kernel with a device-side
+        # ``found_inf`` flag: the reference's "skip the step when the loss is not finite" guard (:457) without a
+        # host read.  WINDSR_FUSED_ADAM=0: torch's own (host-checked guard).
+        self._fused_adam = self.device.type == "cuda" and os.environ.get("WINDSR_FUSED_ADAM", "1") != "0"
+        adam = WindAdam if self._fused_adam else torch.optim.Adam
+        self.optimizer_G = adam(self.G.parameters(), lr=t.learning_rate_g, weight_decay=t.adam_weight_decay_g,
+                                betas=(t.adam_beta1_g, 0.999))
+        self.optimizer_D = adam(self.D.parameters(), lr=t.learning_rate_d, weight_decay=t.adam_weight_decay_d,
+                                betas=(t.adam_beta1_d, 0.999))
         self.optimizers += [self.optimizer_G, self.optimizer_D]
         if t.multistep_lr_steps:
             self.scheduler_G = lr_scheduler.MultiStepLR(self.optimizer_G, t.multistep_lr_steps, gamma=t.lr_gamma)
@@ -140,12 +185,48 @@ class wind_field_GAN_3D(BaseGAN):
         self.d_g_train_period = d_g_train_period
 
     # ---------------------------------------------------------------------------------------------------
-    def _noise(self, sigma, shape, it):
-        """instance noise U[0,1) * sqrt(sigma * (1 - (it-1)/niter)) (trainingtricks.py:49-58); the scalar is formed
-        on the host (no H2D copy / stream sync per call); past niter+1 it is NaN like the reference's sqrt(<0)."""
-        var = float(sigma) * (1.0 - (float(it) - 1.0) / float(self._niter_host))
-        scale = math.sqrt(var) if var >= 0.0 else float("nan")
-        return torch.rand(shape, device=self.device) * scale
+    # iteration-dependent scalars, kept on the device (so a captured step can be replayed for any iteration)
+    _S_REAL, _S_FAKE, _S_NOISE1, _S_NOISE2, _S_POINT_NINE, _S_COUNT = 0, 1, 2, 3, 4, 8
+
+    def _write_scalars(self, it: int):
+        """real / fake label values (wind_field_GAN_3D.py:627-678), the instance-noise scales
+        sqrt(sigma * (1 - (it-1)/niter)) for sigma = 1 (D steps) and 2 (G steps) (trainingtricks.py:49-58; NaN
+        past niter+1 like the reference's sqrt of a negative), and the "real labels are exactly 0.9" switch of
+        :557-558 — computed on the host, sent with ONE small asynchronous copy from a ring of pinned buffers."""
+        t = self.cfg.training
+        real, fake = 1.0, 0.0
+        frac = float(it) / float(self._niter_host)
+        if t.use_one_sided_label_smoothing and t.flip_labels:
+            fake = 0.1 - 0.1 * frac
+        elif t.use_one_sided_label_smoothing:
+            real = 0.9 + 0.1 * frac
+        var = 1.0 - (float(it) - 1.0) / float(self._niter_host)
+        n1 = math.sqrt(var) if var >= 0.0 else float("nan")
+        n2 = math.sqrt(2.0 * var) if var >= 0.0 else float("nan")
+        target = real if not t.flip_labels else fake
+        # float32(0.9 + 0.1*frac) == float32(0.9) exactly as the reference's device-side comparison sees it
+        nine = float(torch.tensor(target, dtype=torch.float32) == torch.tensor(0.9, dtype=torch.float32))
+        vals = [real, fake, n1, n2, nine, 0.0, 0.0, 0.0]
+        if self._scalars is None:
+            self._scalars = torch.zeros(self._S_COUNT, dtype=torch.float32, device=self.device)
+            if self.device.type == "cuda":
+                self._scalar_ring = [torch.zeros(self._S_COUNT, dtype=torch.float32).pin_memory() for _ in range(8)]
+        if self._scalar_ring:
+            # the host never runs more than two steps ahead (optimize_parameters), so 8 slots cannot be overwritten
+            # before their copy has executed
+            h = self._scalar_ring[self._scalar_slot]
+            self._scalar_slot = (self._scalar_slot + 1) % len(self._scalar_ring)
+            h.copy_(torch.tensor(vals, dtype=torch.float32))
+            self._scalars.copy_(h, non_blocking=True)
+        else:
+            self._scalars.copy_(torch.tensor(vals, dtype=torch.float32))
+
+    def _noisy(self, x, which: int):
+        """x + instance noise (wind_field_GAN_3D.py:250-299): one fused kernel on the GPU."""
+        scale = self._scalars[which:which + 1]
+        if x.is_cuda:
+            return ops.add_instance_noise(x, 1.0, scale_dev=scale)
+        return x + torch.rand(x.shape, device=x.device) * scale
 
     def D_forward(self, HR, fake_HR, it, train_D: bool):
         """D on the real and generated batch (wind_field_GAN_3D.py:221-304): train mode + sigma 1 noise in D
@@ -153,13 +234,13 @@ class wind_field_GAN_3D(BaseGAN):
         noisy = self.cfg.training.use_instance_noise
         if train_D:
             _set_mode(self.D, True)
-            y_pred = self.D(HR + self._noise(1.0, HR.size(), it) if noisy else HR).squeeze()
+            y_pred = self.D(self._noisy(HR, self._S_NOISE1) if noisy else HR).squeeze()
             fake_in = fake_HR.detach()
-            return y_pred, self.D(fake_in + self._noise(1.0, HR.size(), it) if noisy else fake_in).squeeze()
+            return y_pred, self.D(self._noisy(fake_in, self._S_NOISE1) if noisy else fake_in).squeeze()
         _set_mode(self.D, False)
         with torch.no_grad():
-            y_pred = self.D(HR + self._noise(2.0, HR.size(), it) if noisy else HR).squeeze()
-        return y_pred, self.D(fake_HR + self._noise(2.0, HR.size(), it) if noisy else fake_HR).squeeze()
+            y_pred = self.D(self._noisy(HR, self._S_NOISE2) if noisy else HR).squeeze()
+        return y_pred, self.D(self._noisy(fake_HR, self._S_NOISE2) if noisy else fake_HR).squeeze()
 
     # ---------------------------------------------------------------------------------------------------
     def _adversarial(self, first, second, generator_side: bool):
@@ -191,9 +272,18 @@ class wind_field_GAN_3D(BaseGAN):
             pix = torch.zeros((), device=self.device)
         return pix, xy, zg, div, dxy
 
+    def _skip_D_in_G_step(self) -> bool:
+        """adversarial weight exactly 0 and no feature-extractor term: the discriminator contributes exact zeros to
+        the generator loss and to its gradients (the reference still runs it, wind_field_GAN_3D.py:487,426)."""
+        return (float(self.cfg.training.adversarial_loss_weight) == 0.0 and self.feature_extractor is None
+                and not self.use_D_feature_extractor_cost and os.environ.get("WINDSR_SKIP_D_WHEN_ZERO", "1") != "0")
+
     def calculate_optimize_and_log_G_loss(self, HR, fake_HR, Z, y_pred, fake_y_pred, training_iteration: bool):
         t = self.cfg.training
-        adv = self._adversarial(fake_y_pred, y_pred, True) * t.adversarial_loss_weight
+        if y_pred is None:
+            adv = torch.zeros((), device=self.device)
+        else:
+            adv = self._adversarial(fake_y_pred, y_pred, True) * t.adversarial_loss_weight
         feat = torch.zeros(1, device=self.device)
         if self.feature_extractor is not None:
             with torch.no_grad():
@@ -211,19 +301,22 @@ class wind_field_GAN_3D(BaseGAN):
         # The reference's guards (:434-443 and :457): drop the physics terms when any of them is NaN/Inf, and skip
         # the optimiser step when the total is NaN/Inf.  The first is decided ON THE DEVICE (select, with
         # WindLossFn.backward discarding the 0*inf cotangents of the dropped branch); the second is handed to the
-        # fused Adam kernel as its ``found_inf`` flag, so a training step has no host synchronisation at all.
+        # Adam kernel as its ``found_inf`` flag, so a training step has no host synchronisation at all.
         ok_physics = torch.isfinite(physics).all()
         loss_G = base + torch.where(ok_physics, physics, torch.zeros_like(physics))
         if training_iteration:
             if self.sync_G is not None:
                 self.sync_G.begin()
             loss_G.backward()
+            # data parallel: the gradients are averaged over ranks, so the skip decision must be global too —
+            # one rank's NaN poisons everybody's average and every replica has to skip the same step
+            not_finite = (~torch.isfinite(loss_G.detach()).reshape(())).to(torch.float32)
             if self.sync_G is not None:
+                allreduce_max_(not_finite)
                 self.sync_G.finish()
-            not_finite = ~torch.isfinite(loss_G.detach()).reshape(())
             if self._fused_adam:
-                self.optimizer_G.found_inf = not_finite.to(torch.float32)
-                self.optimizer_G.step()  # a no-op on the device when loss_G is not finite
+                self.optimizer_G.found_inf = not_finite
+                self.optimizer_G.step()  # a no-op on the device when loss_G is not finite on any rank
             elif not bool(not_finite):
                 self.optimizer_G.step()
         d = self.train_G_loss_dict if training_iteration else self.validation_G_loss_dict
@@ -238,12 +331,12 @@ class wind_field_GAN_3D(BaseGAN):
         if training_iteration:
             _set_mode(self.G, True)
             fake_HR = self.G(LR, Z)
-            if self._D_requires_grad is not False:
-                for p in self.D.parameters():
-                    p.requires_grad = False
-                self._D_requires_grad = False
+            _set_requires_grad(self.D, False)
             self.G.zero_grad(set_to_none=True)
-            y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
+            if self._skip_D_in_G_step():
+                y_pred = fake_y_pred = None
+            else:
+                y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=False)
             self.calculate_optimize_and_log_G_loss(HR, fake_HR, Z, y_pred, fake_y_pred, True)
         else:
             _set_mode(self.G, False)
@@ -255,24 +348,24 @@ class wind_field_GAN_3D(BaseGAN):
 
     def update_D(self, HR, fake_HR, it, training_epoch: bool):
         if training_epoch:
-            if self._D_requires_grad is not True:
-                for p in self.D.parameters():
-                    p.requires_grad = True
-                self._D_requires_grad = True
+            _set_requires_grad(self.D, True)
             self.optimizer_D.zero_grad(set_to_none=True)
             y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=True)
         else:
             with torch.no_grad():  # the reference validates D in train mode too (:542-543)
                 y_pred, fake_y_pred = self.D_forward(HR, fake_HR, it, train_D=True)
         loss_D = self._adversarial(y_pred, fake_y_pred, False)
-        if self.cfg.training.gan_type == "relativisticavg" and self._labels_are_exactly_point_nine:
-            loss_D = loss_D - 0.1985
+        if self.cfg.training.gan_type == "relativisticavg":
+            # `if torch.all(self.HR_labels == 0.9): loss_D -= 0.1985` (:557-558) as a device-side select
+            loss_D = loss_D - 0.1985 * self._labels_point_nine
         if training_epoch:
             if self.sync_D is not None:
                 self.sync_D.begin()
             loss_D.backward()
             if self.sync_D is not None:
                 self.sync_D.finish()
+            if self._fused_adam:
+                self.optimizer_D.found_inf = None
             self.optimizer_D.step()
         if training_epoch:
             self.D_loss_dict["train_loss"] = loss_D
@@ -286,26 +379,52 @@ class wind_field_GAN_3D(BaseGAN):
         """Alternating blocks of ``d_g_train_period`` iterations (wind_field_GAN_3D.py:585-587)."""
         return (int(it) // self.d_g_train_period) % (self.d_g_train_ratio + 1) == 0
 
+    def _train_step_body(self, kind: str, LR, HR, Z):
+        """Everything of one training iteration that runs on the device; depends on the iteration number only
+        through ``self._scalars`` — this is what gets captured into a CUDA graph."""
+        self.make_new_labels()
+        if kind == "G":
+            self.update_G(LR, HR, Z, None, True)
+        else:
+            with torch.no_grad():
+                _set_mode(self.G, False)
+                fake_HR = self.G(LR, Z)
+            self.update_D(HR, fake_HR, None, True)
+
+    def _graph_eligible(self, LR) -> bool:
+        return (LR.is_cuda and self._fused_adam and not self.use_D_feature_extractor_cost
+                and os.environ.get("WINDSR_CUDA_GRAPH", "1") != "0")
+
     def compute_losses_and_optimize(self, LR, HR, Z, it, training_iteration: bool = False):
         self.batch_size = HR.size(0)
         it_host = int(it)
-        it_dev = it_host  # only the host value is needed: schedule, labels and noise scale are host-side scalars
-        self.make_new_labels(it_host)
+        self._write_scalars(it_host)
         if self.use_D_feature_extractor_cost and it_host % self.cfg.training.feature_D_update_period == 0:
             self.feature_extractor = copy.deepcopy(self.D.features)
             for p in self.feature_extractor.parameters():
                 p.requires_grad = False
         if training_iteration:
-            if self.is_G_iteration(it_host):
-                self.update_G(LR, HR, Z, it_dev, True)
-            else:
-                with torch.no_grad():
-                    _set_mode(self.G, False)
-                    fake_HR = self.G(LR, Z)
-                self.update_D(HR, fake_HR, it_dev, True)
+            kind = "G" if self.is_G_iteration(it_host) else "D"
+            if self._graph_eligible(LR):
+                from .graph_step import run_captured
+                if run_captured(self, kind, LR, HR, Z):
+                    return
+            self._train_step_body(kind, LR, HR, Z)
             return
-        fake_HR = self.update_G(LR, HR, Z, it_dev, False)
-        self.update_D(HR, fake_HR, it_dev, False)
+        self.make_new_labels()
+        fake_HR = self.update_G(LR, HR, Z, it_host, False)
+        self.update_D(HR, fake_HR, it_host, False)
+        if HR.is_cuda and HR.shape[1] == 3:
+            # PSNR of SR and of the trilinear baseline + the trilinear pixel loss from ONE fused pass
+            # (wind_field_GAN_3D.py:597-618, 730-770); everything stays on the device
+            sums = ops.validation_metrics(HR, fake_HR, LR)
+            vox = float(HR.shape[0] * HR.shape[2] * HR.shape[3] * HR.shape[4])
+            mse = (sums[:2] / vox).to(torch.float32)
+            psnr = 10.0 * torch.log10(self.max_diff_squared / (mse + self.epsilon_PSNR))
+            self.metrics_dict["val_PSNR"], self.metrics_dict["Trilinear_PSNR"] = psnr[0], psnr[1]
+            self.metrics_dict["trilinear_pix_loss"] = ((sums[2] if self.pixel_criterion != "l2" else sums[1])
+                                                       / (3.0 * vox)).to(torch.float32)
+            return
         (self.metrics_dict["val_PSNR"], self.metrics_dict["Trilinear_PSNR"]) = compute_PSNR_for_SR_and_trilinear(
             LR, HR, fake_HR, self.max_diff_squared, self.epsilon_PSNR, interpolate=True, device=self.device,
             scale=self.cfg.scale)
@@ -331,30 +450,24 @@ class wind_field_GAN_3D(BaseGAN):
         self.compute_losses_and_optimize(LR, HR, Z, it, training_iteration=False)
 
     # ---------------------------------------------------------------------------------------------------
-    def make_new_labels(self, it):
+    def make_new_labels(self, it=None):
         """Real / fake target vectors (wind_field_GAN_3D.py:627-678): optional flip, one-sided smoothing that
-        anneals 0.9 -> 1.0 over ``niter``, optional Gaussian label noise."""
+        anneals 0.9 -> 1.0 over ``niter``, optional Gaussian label noise — built from the device scalars written by
+        ``_write_scalars`` (``it`` given: write them first; kept for callers of the reference's signature)."""
+        if it is not None:
+            self._write_scalars(int(it))
         t = self.cfg.training
-        real_is_true = not t.flip_labels
-        real, fake = 1.0, 0.0
-        frac = float(it) / float(self._niter_host)
-        if t.use_one_sided_label_smoothing and t.flip_labels:
-            fake = 0.1 - 0.1 * frac
-        elif t.use_one_sided_label_smoothing:
-            real = 0.9 + 0.1 * frac
-        std = 0.05 if t.use_noisy_labels else 0.0
-        mk = lambda kind: trainingtricks.noisy_labels(kind, self.batch_size, noise_stddev=std,
-                                                      true_label_val=real, false_label_val=fake,
-                                                      device=self.device).squeeze()
-        self.HR_labels = mk(real_is_true)
-        self.fake_HR_labels = mk(not real_is_true)
-        if std == 0.0:
-            # float32(0.9 + 0.1*frac) == float32(0.9) exactly as the reference's device-side comparison sees it
-            target = (real if real_is_true else fake)
-            self._labels_are_exactly_point_nine = bool(torch.tensor(target, dtype=torch.float32)
-                                                       == torch.tensor(0.9, dtype=torch.float32))
+        real, fake = self._scalars[self._S_REAL:self._S_REAL + 1], self._scalars[self._S_FAKE:self._S_FAKE + 1]
+        if t.flip_labels:
+            real, fake = fake, real
+        if t.use_noisy_labels:
+            mk = lambda base: torch.clamp(torch.randn(self.batch_size, device=self.device) * 0.05 + base, 0.0, 1.0)
+            self.HR_labels, self.fake_HR_labels = mk(real).squeeze(), mk(fake).squeeze()
+            self._labels_point_nine = torch.all(self.HR_labels == 0.9).to(torch.float32)
         else:
-            self._labels_are_exactly_point_nine = bool(torch.all(self.HR_labels == 0.9))
+            self.HR_labels = real.expand(self.batch_size).squeeze()
+            self.fake_HR_labels = fake.expand(self.batch_size).squeeze()
+            self._labels_point_nine = self._scalars[self._S_POINT_NINE]
 
     # ---------------------------------------------------------------------------------------------------
     def get_G_train_loss_dict_ref(self):

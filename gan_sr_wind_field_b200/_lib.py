@@ -45,6 +45,13 @@ class WsRdbDesc(C.Structure):
                [("math", C.c_int32), ("repack", C.c_int32)]
 
 
+class WsPrepareDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n", "sx", "sy", "sz", "x", "y", "coarseness", "include_pressure",
+                                         "include_z_channel", "include_above_ground_channel")] + \
+               [("sample_stride", C.c_int64)] + \
+               [(k, C.c_double) for k in ("uvw_max", "p_min", "p_max", "z_min", "z_max", "z_above_ground_max")]
+
+
 class WindSRError(RuntimeError):
     pass
 
@@ -93,6 +100,11 @@ SYMBOLS = [
     ("ws_windloss_fwd", _I, [_TP, _TP, _TP, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     ("ws_windloss_bwd_workspace_bytes", _Z, [_I, _I, _I, _I]),
     ("ws_windloss_bwd", _I, [_TP, _TP, _TP, _P, _P, _I, _I, _I, _I, _P, _P, _TP, _P, _Z, _P]),
+    ("ws_adam_chunk_elems", _I, []),
+    ("ws_adam_step", _I, [_P, _P, _I, _I, _P, _F, _F, _F, _F, _F, _F, _P, _P]),
+    ("ws_instance_noise", _I, [_P, _P, _L, _F, _P, C.c_uint64, _P, _P]),
+    ("ws_validation_metrics", _I, [_TP, _TP, _TP, _I, _I, _I, _I, _I, _I, _P, _P]),
+    ("ws_prepare_batch", _I, [C.POINTER(WsPrepareDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 ]
 
 

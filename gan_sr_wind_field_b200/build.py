@@ -14,7 +14,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(os.path.dirname(PKG_DIR), "build")
 LIB_PATH = os.path.join(PKG_DIR, "libwindsr.so")
-SOURCES = ["api.cu", "conv_simt.cu", "elementwise.cu", "windloss.cu", "conv_tc.cu", "conv_tc2.cu", "wgrad_tc.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "elementwise.cu", "windloss.cu", "conv_tc.cu", "conv_tc2.cu", "wgrad_tc.cu",
+           "train_aux.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

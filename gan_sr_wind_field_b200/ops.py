@@ -60,6 +60,31 @@ def act_dtype() -> torch.dtype:
 
 
 # ------------------------------------------------------------------------------------------------------
+# CUDA-graph capture support
+# ------------------------------------------------------------------------------------------------------
+# While torch.cuda.graph() records a training step (GAN_models/graph_step.py) every device buffer a captured kernel
+# touches must stay valid for the lifetime of the graph.  Caches that may later drop or replace their tensors
+# (packed weights, stencil coefficients, auxiliary workspaces) are therefore bypassed during capture: the operand is
+# rebuilt inside the capture — so a replay also re-derives it from the CURRENT weights — and a reference is parked
+# in ``_KEEPALIVE`` until the capturing code collects it (``take_keepalive``).
+_KEEPALIVE = []
+
+
+def capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def keepalive(*tensors):
+    _KEEPALIVE.extend(t for t in tensors if t is not None)
+
+
+def take_keepalive():
+    out = list(_KEEPALIVE)
+    _KEEPALIVE.clear()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 # allocation helpers
 # ------------------------------------------------------------------------------------------------------
 def empty_cl(n, c, x, y, z, dtype, device) -> torch.Tensor:
@@ -126,13 +151,17 @@ class PackedWeights:
         key = (kind, pad_cout)
         stamp = (w._version, w.data_ptr(), shape.cin, shape.cout, _WEIGHTS_EPOCH)
         hit = self._cache.get(key)
-        if hit is not None and hit[0] == stamp:
+        cap = capturing()
+        if hit is not None and hit[0] == stamp and not cap:
             return hit[1]
         src = w
         if pad_cout > w.shape[0]:
             src = torch.cat((w.detach(), w.new_zeros((pad_cout - w.shape[0],) + tuple(w.shape[1:]))), 0)
         packed = pack_weights(src, shape, kind)
-        self._cache[key] = (stamp, packed)
+        if cap:
+            keepalive(packed)  # the captured pack kernel refreshes it on every replay; never served from the cache
+        else:
+            self._cache[key] = (stamp, packed)
         return packed
 
     def clear(self):
@@ -212,9 +241,18 @@ class _timed:
             _KERNEL_TIMER[1].append((self.t0, self.t1))
 
 
+_GRAPH_LAUNCHES = [0]
+
+
+def count_graph_launches(n: int) -> None:
+    """A CUDA-graph replay executed ``n`` libwindsr kernels (counted when the graph was captured)."""
+    _GRAPH_LAUNCHES[0] += int(n)
+
+
 def launch_count() -> int:
-    """CUDA kernels launched by libwindsr.so in this process so far."""
-    return int(load().ws_launch_count())
+    """CUDA kernels of libwindsr.so executed by this process so far: direct launches (counted inside the library,
+    which also sees the launches recorded during a graph capture) plus the kernels of every graph replay."""
+    return int(load().ws_launch_count()) + _GRAPH_LAUNCHES[0]
 
 
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], shape: WsConvShape,
@@ -263,6 +301,8 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _WORKSPACES[key] = buf
+    if capturing():
+        keepalive(buf)
     return buf
 
 
@@ -577,11 +617,15 @@ class RDBState:
         stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + (desc.math, _WEIGHTS_EPOCH)
         repack = stamp != self.stamp[dgrad]
         self.stamp[dgrad] = stamp
+        if capturing():  # a replay must repack from the weights of ITS step; eager calls after it must not trust us
+            repack = True
+            self.stamp[dgrad] = None
         return self.packed[dgrad], int(repack)
 
 
 # ---- auxiliary stream for the off-critical-path weight gradients of the residual dense blocks -------------------
 _AUX = {}           # device -> (torch.cuda.Stream, workspace tensor)
+_AUX_CAPTURE = {}   # device -> workspace tensor allocated inside the current graph capture
 _AUX_JOIN_QUEUED = [False]
 
 
@@ -591,8 +635,22 @@ def _aux_enabled() -> bool:
 
 def _aux_stream(device, nbytes: int):
     hit = _AUX.get(device)
+    if capturing():
+        # a dedicated workspace inside the graph's memory pool: the shared one may be re-grown (freed) by later eager
+        # calls while the graph still points at it
+        stream = hit[0] if hit is not None else torch.cuda.Stream(device=device)
+        if hit is None:
+            _AUX[device] = (stream, torch.empty(1 << 20, dtype=torch.uint8, device=device))
+        cap = _AUX_CAPTURE.get(device)
+        if cap is None or cap.numel() < nbytes:
+            cap = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _AUX_CAPTURE[device] = cap
+        keepalive(cap)
+        return stream, cap
     if hit is None or hit[1].numel() < nbytes:
         stream = hit[0] if hit is not None else torch.cuda.Stream(device=device)
+        if hit is not None:
+            hit[1].record_stream(stream)  # queued auxiliary-stream kernels may still be using the old workspace
         hit = (stream, torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device))
         _AUX[device] = hit
     return hit
@@ -708,7 +766,10 @@ class RDBFn(torch.autograd.Function):
         dxv = view(dx) if dx is not None else null_view()
         wd = [p.detach() for p in params[:nconv + 1]]
         # weight gradients on the auxiliary stream (they are off the critical path of the backward chain)
-        use_aux = need_params and _aux_enabled() and get_precision() == "bf16"
+        # (gradient accumulation: AccumulateGrad would add into an existing .grad on the main stream while the
+        # auxiliary stream is still writing the new one — keep everything on one stream then)
+        use_aux = (need_params and _aux_enabled() and get_precision() == "bf16"
+                   and not any(p is not None and p.grad is not None for p in params))
         aux_s, aux_w = _aux_stream(dev, nbytes) if use_aux else (None, None)
         check(lib.ws_rdb_backward(C.byref(desc), C.byref(dyv), C.byref(bv), C.byref(dbv), C.byref(glv), C.byref(gv),
                                   C.byref(dxv), _ptr_array(wd), _ptr_array(packed), dw_arr, ptr(db),
@@ -899,11 +960,15 @@ def axis_coeffs(coords: torch.Tensor) -> torch.Tensor:
     torch.gradient(spacing=coords) (process_data.py:303)."""
     key = (coords.data_ptr(), coords._version, coords.numel(), str(coords.device))
     hit = _COEF_CACHE.get(key)
-    if hit is not None:
+    cap = capturing()
+    if hit is not None and not cap:
         return hit
     c32 = coords.detach().to(torch.float32).contiguous()
     coef = torch.empty((coords.numel(), 6), dtype=torch.float32, device=coords.device)
     check(load().ws_axis_coeffs(c32.data_ptr(), c32.numel(), coef.data_ptr(), stream_ptr()), "ws_axis_coeffs")
+    if cap:
+        keepalive(c32, coef)
+        return coef
     if len(_COEF_CACHE) > 64:
         _COEF_CACHE.clear()
     _COEF_CACHE[key] = coef
@@ -969,3 +1034,93 @@ class WindLossFn(torch.autograd.Function):
 
 def windloss_slots(hr, sr, Z, x, y) -> torch.Tensor:
     return WindLossFn.apply(hr, sr.float() if sr.dtype != torch.float32 else sr, Z.float(), x, y)
+
+
+# ------------------------------------------------------------------------------------------------------
+# instance noise, validation metrics, input pipeline (csrc/train_aux.cu)
+# ------------------------------------------------------------------------------------------------------
+_NOISE_STATE = {}
+
+
+def _noise_state(device):
+    st = _NOISE_STATE.get(device)
+    if st is None:
+        # seeded from torch's generator so torch.manual_seed() makes runs reproducible; [call counter, block ticket]
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        st = (seed, torch.zeros(2, dtype=torch.int64, device=device))
+        _NOISE_STATE[device] = st
+    return st
+
+
+def reseed_instance_noise(seed: int, device=None) -> None:
+    for dev in list(_NOISE_STATE) if device is None else [device]:
+        _NOISE_STATE[dev] = (int(seed), torch.zeros(2, dtype=torch.int64, device=dev))
+
+
+def add_instance_noise(x: torch.Tensor, scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x + U[0,1) * scale (* scale_dev[0]) — tools/trainingtricks.py:49-58 fused with the add at
+    wind_field_GAN_3D.py:250-299.  Differentiable w.r.t. x (the noise is a constant)."""
+    return _InstanceNoiseFn.apply(x, float(scale), scale_dev)
+
+
+class _InstanceNoiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, scale_dev):
+        _require_cuda(x)
+        xc = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        out = torch.empty_like(xc)
+        seed, state = _noise_state(x.device)
+        check(load().ws_instance_noise(xc.data_ptr(), out.data_ptr(), xc.numel(), scale, ptr(scale_dev), seed,
+                                       state.data_ptr(), stream_ptr()), "ws_instance_noise")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+def validation_metrics(HR: torch.Tensor, SR: Optional[torch.Tensor], LR: torch.Tensor) -> torch.Tensor:
+    """One fused pass -> float64[4]: sum (HR-SR)^2, sum (HR-tri)^2, sum |HR-tri|, sum |HR-SR| with tri the
+    align-corners trilinear upsample of LR[:, :3] (wind_field_GAN_3D.py:730-770, 597-618); nothing materialised."""
+    _require_cuda(HR)
+    n, c, X, Y, Zn = HR.shape
+    if c != 3 or LR.shape[1] < 3 or LR.shape[4] != Zn:
+        raise _lib.WindSRError("validation_metrics expects HR (N,3,X,Y,Z) and LR (N,>=3,x,y,Z)")
+    sums = torch.empty(4, dtype=torch.float64, device=HR.device)
+    hv, lv = view(HR.float()), view(LR.float()[:, :3])
+    sv = view(SR.float()) if SR is not None else null_view()
+    check(load().ws_validation_metrics(C.byref(hv), C.byref(sv), C.byref(lv), n, X, Y, Zn, LR.shape[2], LR.shape[3],
+                                       sums.data_ptr(), stream_ptr()), "ws_validation_metrics")
+    return sums
+
+
+def prepare_batch(u, v, w, z, *, pressure=None, z_above_ground=None, aug=None, crop=None, coarseness=4,
+                  include_pressure=False, include_z_channel=False, include_above_ground_channel=False,
+                  uvw_max=1.0, p_min=0.0, p_max=1.0, z_min=0.0, z_max=1.0, z_above_ground_max=1.0):
+    """(LR, HR, Z) of a training batch from float64 device fields (N, X, Y, Z) — the crop / normalise / subsample /
+    rot90 / flip chain of process_data.py:159-262,420-494 as one gather kernel (``ws_prepare_batch``).
+    aug: int32 (N,5) = x_start, y_start, rotations, flip_x, flip_y (zeros when None); crop: (X, Y) slice size."""
+    _require_cuda(u)
+    n, SX, SY, SZ = u.shape
+    X, Y = crop if crop is not None else (SX, SY)
+    for t in (u, v, w, z, pressure, z_above_ground):
+        if t is not None and (t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != (n, SX, SY, SZ)):
+            raise _lib.WindSRError("prepare_batch: fields must be contiguous float64 (N, X, Y, Z) of one shape")
+    if aug is None:
+        aug = torch.zeros((n, 5), dtype=torch.int32, device=u.device)
+    aug = aug.to(device=u.device, dtype=torch.int32).contiguous()
+    if X != Y and bool((aug[:, 2] % 2 == 1).any()):
+        raise _lib.WindSRError("prepare_batch: odd rotations need a square crop")
+    cf = int(coarseness)
+    xl, yl = (X + cf - 1) // cf, (Y + cf - 1) // cf
+    lr_c = 3 + int(bool(include_pressure)) + (0 if not include_z_channel else (2 if include_above_ground_channel else 1))
+    LR = torch.empty((n, lr_c, xl, yl, SZ), dtype=torch.float32, device=u.device)
+    HR = torch.empty((n, 3, X, Y, SZ), dtype=torch.float32, device=u.device)
+    Zo = torch.empty((n, 1, X, Y, SZ), dtype=torch.float32, device=u.device)
+    d = _lib.WsPrepareDesc(n, SX, SY, SZ, X, Y, cf, int(bool(include_pressure)), int(bool(include_z_channel)),
+                           int(bool(include_above_ground_channel)), SX * SY * SZ, float(uvw_max), float(p_min),
+                           float(p_max), float(z_min), float(z_max), float(z_above_ground_max))
+    check(load().ws_prepare_batch(C.byref(d), u.data_ptr(), v.data_ptr(), w.data_ptr(), ptr(pressure), z.data_ptr(),
+                                  ptr(z_above_ground), aug.data_ptr(), LR.data_ptr(), HR.data_ptr(), Zo.data_ptr(),
+                                  stream_ptr()), "ws_prepare_batch")
+    return LR, HR, Zo

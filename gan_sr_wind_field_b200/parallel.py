@@ -5,8 +5,13 @@ of G and D), so the only exchange is the gradient average of the network being u
 49.2 MB (D) fp32 per step.  ``GradSync`` packs gradients into ~25 MB flat buckets in reverse-registration order
 (the order autograd produces them: ``hr_convs`` / the last UpConv first) and launches one asynchronous
 ``all_reduce`` per bucket as soon as its last gradient has been accumulated, so the NVLink/NVSwitch transfer
-overlaps the remaining backward kernels; ``finish`` waits, averages and scatters the result back into
-``param.grad``.
+overlaps the remaining backward kernels; ``finish`` waits and re-points every ``param.grad`` at its slice of the
+reduced bucket (no copy back).  On NCCL the reduction is ``ReduceOp.AVG`` (the division by the world size happens
+inside the collective); on gloo (CPU tests) it is SUM followed by one in-place scale per bucket.
+
+``broadcast_module`` / ``allreduce_max_`` are the two other exchanges a replica needs: identical initial weights
+and buffers on every rank, and a GLOBAL "loss is not finite" flag so that either every rank skips the optimiser
+step or none does (the gradients have already been averaged when the flag is consumed).
 """
 from __future__ import annotations
 
@@ -35,6 +40,7 @@ class GradSync:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 25 << 20, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.avg_in_collective = dist.is_initialized() and dist.get_backend(group) == "nccl"
         params = [p for p in params]
         self.buckets: List[_Bucket] = []
         cur, cur_bytes = [], 0
@@ -93,7 +99,8 @@ class GradSync:
             else:
                 views.append((p, v))
         torch._foreach_copy_([v for _, v in views], [p.grad.reshape(-1) for p, _ in views])
-        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for every bucket, write the averaged gradients back."""
@@ -108,17 +115,30 @@ class GradSync:
                 if b.work is None:
                     continue
             b.work.wait()
-            dst, src = [], []
+            if not self.avg_in_collective:
+                b.flat.mul_(inv)
             for p, off in zip(b.params, b.offsets):
                 if p.grad is not None:
-                    dst.append(p.grad.reshape(-1))
-                    src.append(b.flat[off:off + p.numel()])
-            if dst:
-                torch._foreach_mul_(src, inv)
-                torch._foreach_copy_(dst, src)
+                    p.grad = b.flat[off:off + p.numel()].view_as(p)  # no copy back: the bucket IS the gradient
             b.work = None
 
     def remove(self):
         for h in self._hooks.values():
             h.remove()
         self._hooks = {}
+
+
+def broadcast_module(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Every rank takes rank ``src``'s parameters and buffers (BatchNorm running statistics included)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
+
+def allreduce_max_(flag: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place MAX over ranks of a small device tensor (stream-ordered; no host synchronisation on NCCL)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return flag

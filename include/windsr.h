@@ -292,6 +292,66 @@ int ws_windloss_bwd(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* z
                     const int64_t* argmax, const ws_tensor* dsr, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- optimiser: multi-tensor Adam (GAN_models/wind_field_GAN_3D.py:151-162; guard :457-460) ---------------------- */
+/* One entry per parameter tensor (all fp32, device pointers).  `step` is the tensor's own step counter (a float, like
+ * torch.optim.Adam's state["step"]), read as t = step + 1 and incremented by the call. */
+typedef struct ws_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* step;
+  int64_t numel;
+} ws_adam_tensor;
+/* elements of one work chunk: the caller lists (tensor index, chunk index) int32 pairs covering every tensor */
+int ws_adam_chunk_elems(void);
+/* torch.optim.Adam's update (amsgrad off) for all tensors in ONE launch (+ a step-counter bump):
+ *   g' = grad * grad_scale + weight_decay * p;  m += (g' - m)(1 - beta1);  v = beta2 v + (1 - beta2) g'^2
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * table: device array of ws_adam_tensor[ntensors]; chunks: device int32[nchunks][2].  lr_dev (optional device scalar)
+ * overrides lr — a CUDA-graph replay then follows the MultiStepLR schedule (wind_field_GAN_3D.py:163-174).
+ * found_inf (optional device float): non-zero -> the whole call is a no-op, the reference's "skip the step when the
+ * loss is NaN/Inf" guard without a host read. */
+int ws_adam_step(const void* table, const void* chunks, int ntensors, int nchunks, const float* lr_dev, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, const float* found_inf,
+                 void* stream);
+
+/* ---- instance noise (tools/trainingtricks.py:49-58; used wind_field_GAN_3D.py:250-299) --------------------------- */
+/* out[i] = x[i] + U[0,1) * scale * (scale_dev ? *scale_dev : 1), n contiguous fp32 elements (out may alias x).
+ * Counter-based Philox4x32-10 keyed by `seed`; state: device uint64[2] (zero-initialised by the caller once) holding
+ * the call counter, advanced by the kernel itself so that CUDA-graph replays draw fresh noise. */
+int ws_instance_noise(const float* x, float* out, int64_t n, float scale, const float* scale_dev, uint64_t seed,
+                      uint64_t* state, void* stream);
+
+/* ---- validation metrics (wind_field_GAN_3D.py:730-770, 597-618) ---------------------------------------------- */
+/* One pass over HR (n,3,x,y,z), SR (same; optional) and LR (n,>=3,xl,yl,z):
+ *   sums[0] = sum (HR-SR)^2, sums[1] = sum (HR-tri)^2, sums[2] = sum |HR-tri|, sums[3] = sum |HR-SR|
+ * with tri = F.interpolate(LR[:, :3], scale_factor=(s,s,1), mode="trilinear", align_corners=True) evaluated on the
+ * fly.  sums: device double[4] (zeroed by the call).  PSNR = 10 log10(4 / (sums[k]/(n*x*y*z) + 1e-8)). */
+int ws_validation_metrics(const ws_tensor* hr, const ws_tensor* sr, const ws_tensor* lr, int n, int x, int y, int z,
+                          int xl, int yl, double* sums, void* stream);
+
+/* ---- input pipeline (process_data.py:159-262, 420-494) ---------------------------------------------------------- */
+/* Builds a training batch on the device from the float64 per-hour fields of the on-disk format
+ * (download_data.py:456-467: z, z_above_ground, u, v, w, pressure, each (sx, sy, sz)):
+ * crop [x_start, x_start+x) x [y_start, y_start+y), normalise (reformat_to_torch), LR = every `coarseness`-th point in
+ * x and y, then torch.rot90(k, [1,2]) and the two flips with the wind-component sign fixes of
+ * CustomizedDataset.__getitem__.  Bit-exact against the reference's numpy/torch CPU code (float64 arithmetic, one
+ * rounding to float32). */
+typedef struct ws_prepare_desc {
+  int32_t n, sx, sy, sz;   /* samples, source field extents                                       */
+  int32_t x, y;            /* crop extents (slice_size, or sx / sy without slicing)               */
+  int32_t coarseness;      /* cfg.scale                                                           */
+  int32_t include_pressure, include_z_channel, include_above_ground_channel;
+  int64_t sample_stride;   /* elements between consecutive samples in each source array           */
+  double uvw_max, p_min, p_max, z_min, z_max, z_above_ground_max;
+} ws_prepare_desc;
+/* aug: device int32[n][5] = x_start, y_start, rotations (0..3), flip_x, flip_y.
+ * lr: (n, C, ceil(x/c), ceil(y/c), sz), hr: (n, 3, x, y, sz), zout: (n, 1, x, y, sz), contiguous fp32. */
+int ws_prepare_batch(const ws_prepare_desc* d, const double* u, const double* v, const double* w, const double* p,
+                     const double* z, const double* zag, const int32_t* aug, float* lr, float* hr, float* zout,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     from gan_sr_wind_field_b200 import _lib
     header = open(os.path.join(ROOT, "include", "windsr.h")).read()
     declared = set(re.findall(r"\b(ws_[a-z0-9_]+)\s*\(", header))
-    declared -= {"ws_tensor", "ws_conv_shape", "ws_epilogue"}
+    declared -= {"ws_tensor", "ws_conv_shape", "ws_epilogue", "ws_adam_tensor", "ws_prepare_desc", "ws_rdb_desc"}
     bound = {name for name, _, _ in _lib.SYMBOLS}
     assert declared == bound, (declared - bound, bound - declared)
     lib = ctypes.CDLL(_lib.LIB_PATH)
@@ -183,9 +183,11 @@ def test_schedule_and_labels():
     assert [gan.is_G_iteration(i) for i in range(8)] == [True, True, False, False, True, True, False, False]
     gan.batch_size = 3
     gan.make_new_labels(0)
-    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.9)) and gan._labels_are_exactly_point_nine
+    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.9)) and float(gan._labels_point_nine) == 1.0
     gan.make_new_labels(50)
-    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.95)) and not gan._labels_are_exactly_point_nine
+    assert torch.allclose(gan.HR_labels, torch.full((3,), 0.95)) and float(gan._labels_point_nine) == 0.0
+    # instance-noise scales sqrt(sigma * (1 - (it-1)/niter)) for sigma = 1, 2 (trainingtricks.py:49-58)
+    assert torch.allclose(gan._scalars[2:4], torch.tensor([0.51 ** 0.5, 1.02 ** 0.5]))
     assert torch.equal(gan.fake_HR_labels, torch.zeros(3))
     assert gan.count_params() == (sum(p.numel() for p in gan.G.parameters()),
                                   sum(p.numel() for p in gan.D.parameters()))

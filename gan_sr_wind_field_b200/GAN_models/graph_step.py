@@ -69,7 +69,7 @@ def run_captured(gan, kind, LR, HR, Z) -> bool:
     """Replay the captured step for this call if there is one (capturing it when the warm-up count is reached).
     Returns False when the caller should run the step eagerly."""
     key = (kind, tuple(LR.shape), tuple(HR.shape), tuple(Z.shape), ops.get_precision(),
-           bool(gan.cfg.training.use_instance_noise))
+           bool(gan.cfg.training.use_instance_noise), gan._skip_D_in_G_step())
     g = gan._graphs.get(key)
     if g is None:
         n = gan._eager_calls.get(key, 0)

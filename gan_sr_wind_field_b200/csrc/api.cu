@@ -37,8 +37,8 @@ int validate_shape(const ws_conv_shape* s) {
 // implemented in the other translation units
 int simt_conv_fwd(const ConvGeom&, const View&, const float*, const View&, const Epi&, cudaStream_t);
 int simt_conv_dgrad(const ConvGeom&, const View&, const float*, const View&, const Epi&, cudaStream_t);
-int simt_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
-size_t simt_wgrad_workspace_bytes(const ConvGeom&);
+int simt_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t, bool);
+size_t simt_wgrad_workspace_bytes(const ConvGeom&, bool);
 int bias_grad(const View&, float*, int, int, long long, int, cudaStream_t);
 bool tc_view_ok(const View&, int);
 int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t,
@@ -266,8 +266,9 @@ int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* pac
 }
 
 size_t ws_conv3d_wgrad_workspace_bytes(const ws_conv_shape* s, int math) {
-  if (!s) return 0;
-  (void)math;
+  if (!s || validate_shape(s)) return 0;
+  // FP32 mode: deterministic split-K (one accumulator array per split, summed in order)
+  if (math == WS_MATH_FP32) return simt_wgrad_workspace_bytes(ConvGeom(*s), true);
   ws_conv_shape t = *s;
   return (size_t)t.kx * t.ky * t.kz * t.cin * t.cout * sizeof(float);
 }
@@ -285,7 +286,7 @@ int ws_conv3d_wgrad(const ws_conv_shape* s, const ws_tensor* in, const ws_tensor
   if (!dw) return 0;
   if (wgrad_path(g, vin, vdy, math) == WS_PATH_TCGEN05)
     return tc_conv_wgrad(g, vin, vdy, dw, accumulate, workspace, workspace_bytes, st);
-  return simt_conv_wgrad(g, vin, vdy, dw, accumulate, workspace, workspace_bytes, st);
+  return simt_conv_wgrad(g, vin, vdy, dw, accumulate, workspace, workspace_bytes, st, math == WS_MATH_FP32);
 }
 
 int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,

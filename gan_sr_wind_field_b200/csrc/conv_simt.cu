@@ -258,7 +258,7 @@ conv_igemm_simt(ConvGeom g, View src, const float* __restrict__ w, View dst, Epi
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(kThreads)
 conv_wgrad_simt(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long k_per_split, int vec_a,
-                int vec_b) {
+                int vec_b, long long split_stride) {
   constexpr int NTX = BN / TN;
   constexpr int NTY = BM / TM;
   static_assert(NTX * NTY <= kThreads, "tile too large");
@@ -380,6 +380,15 @@ conv_wgrad_simt(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long
   store_tiles(0);
   __syncthreads();
   int buf = 0;
+  // Two-level summation: the running sums are folded into `tot` every 64 tiles (1024 voxels), so the rounding error of
+  // a 10^5..10^6-term weight-gradient sum grows like sqrt(1024) + sqrt(K/1024) ulps instead of sqrt(K) (the FP32
+  // parity bar is rel-L2 1e-5 on gradients whose sums cancel heavily).
+  float tot[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) tot[i][j] = 0.f;
+  int since_fold = 0;
   for (long long kk = kbeg; kk < kend; kk += BK) {
     bool more = kk + BK < kend;
     if (more) load_tiles(kk + BK);
@@ -396,6 +405,13 @@ conv_wgrad_simt(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long
 #pragma unroll
           for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
+      if (++since_fold == 64) {
+        since_fold = 0;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+      }
     }
     if (more) {
       store_tiles(buf ^ 1);
@@ -403,6 +419,10 @@ conv_wgrad_simt(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long
       buf ^= 1;
     }
   }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
   if (computes) {
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -412,15 +432,19 @@ conv_wgrad_simt(ConvGeom g, View in, View dy, float* __restrict__ wsp, long long
       for (int j = 0; j < TN; ++j) {
         int co = n0 + tx * TN + j;
         if (co >= g.cout) continue;
-        atomicAdd(&wsp[((long long)tap * g.cin + ci) * g.cout + co], acc[i][j]);
+        const long long o = ((long long)tap * g.cin + ci) * g.cout + co;
+        // split_stride > 0: the deterministic FP32 parity mode — every K-split owns a private copy of the
+        // accumulator array and wgrad_finalize adds the copies in split order (no atomics, no run-to-run variation)
+        if (split_stride > 0) wsp[(long long)blockIdx.z * split_stride + o] = acc[i][j];
+        else atomicAdd(&wsp[o], acc[i][j]);
       }
     }
   }
 }
 
-// dw[co][ci][tap] (torch layout) = (accumulate ? dw : 0) + wsp[tap][ci][co]
+// dw[co][ci][tap] (torch layout) = (accumulate ? dw : 0) + sum_{s < splits, in order} wsp[s][tap][ci][co]
 __global__ void wgrad_finalize(const float* __restrict__ wsp, float* __restrict__ dw, int taps, int cin,
-                               int cout, int accumulate) {
+                               int cout, int accumulate, int splits) {
   long long total = (long long)taps * cin * cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -428,7 +452,9 @@ __global__ void wgrad_finalize(const float* __restrict__ wsp, float* __restrict_
     long long r = i / taps;
     int ci = (int)(r % cin);
     int co = (int)(r / cin);
-    float v = wsp[((long long)tap * cin + ci) * cout + co];
+    const long long o = ((long long)tap * cin + ci) * cout + co;
+    float v = wsp[o];
+    for (int sp = 1; sp < splits; ++sp) v += wsp[(long long)sp * total + o];
     dw[i] = accumulate ? dw[i] + v : v;
   }
 }
@@ -772,8 +798,33 @@ int simt_conv_dgrad(const ConvGeom& g, const View& dy, const float* w, const Vie
   return launch_igemm<1>(g, dy, w, dx, ep, st);
 }
 
-size_t simt_wgrad_workspace_bytes(const ConvGeom& g) {
-  return (size_t)g.taps() * g.cin * g.cout * sizeof(float);
+namespace {
+// K-split plan of the generic weight-gradient kernel: enough splits to fill the chip ~4x, at least 2048 voxels each
+struct WgradPlan { int bm, bn, tiles; long long splits, kps; };
+WgradPlan wgrad_plan(const ConvGeom& g) {
+  WgradPlan p;
+  const long long K = (long long)g.n * g.vout();
+  auto pick = [](int c) { return c > 16 ? 64 : (c > 4 ? 16 : 4); };
+  p.bm = pick(g.cin); p.bn = pick(g.cout);
+  p.tiles = ((g.cin + p.bm - 1) / p.bm) * ((g.cout + p.bn - 1) / p.bn);
+  const long long target_blocks = 148LL * 4;
+  long long splits = (target_blocks + (long long)p.tiles * g.taps() - 1) / ((long long)p.tiles * g.taps());
+  const long long max_splits = (K + 2047) / 2048;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long kps = (K + splits - 1) / splits;
+  kps = (kps + BK - 1) / BK * BK;
+  p.kps = kps;
+  p.splits = (K + kps - 1) / kps;
+  return p;
+}
+}  // namespace
+
+// deterministic (the FP32 parity mode): one accumulator array per K-split, summed in order by the finalize pass
+size_t simt_wgrad_workspace_bytes(const ConvGeom& g, bool deterministic) {
+  const size_t one = (size_t)g.taps() * g.cin * g.cout * sizeof(float);
+  return deterministic ? one * (size_t)wgrad_plan(g).splits : one;
 }
 
 int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumulate, cudaStream_t st) {
@@ -805,25 +856,25 @@ int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumula
 }
 
 int wgrad_finalize_launch(const float* wsp, float* dw, int taps, int cin, int cout, int accumulate,
-                          cudaStream_t st) {
+                          cudaStream_t st, int splits = 1) {
   long long total = (long long)taps * cin * cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_finalize<<<blocks, 256, 0, st>>>(wsp, dw, taps, cin, cout, accumulate);
+  wgrad_finalize<<<blocks, 256, 0, st>>>(wsp, dw, taps, cin, cout, accumulate, splits);
   WS_POST_LAUNCH(1);
   return 0;
 }
 
 int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw, int accumulate,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  size_t need = simt_wgrad_workspace_bytes(g);
+                    void* workspace, size_t workspace_bytes, cudaStream_t st, bool deterministic) {
+  size_t need = simt_wgrad_workspace_bytes(g, deterministic);
   WS_REQUIRE(workspace && workspace_bytes >= need, "wgrad workspace too small: %zu < %zu", workspace_bytes,
              need);
   float* wsp = (float*)workspace;
   WS_CHECK_CUDA(cudaMemsetAsync(wsp, 0, need, st));
-  const long long K = (long long)g.n * g.vout();
   const int groups = g.kx * g.ky;
-  if (g.kz == 3 && g.sz == 1 && groups <= 16 && g.cin <= 4 && (g.cout == 8 || g.cout == 16 || g.cout == 32) &&
+  // (the narrow-input kernels below reduce with atomics across blocks: not used in the deterministic mode)
+  if (!deterministic && g.kz == 3 && g.sz == 1 && groups <= 16 && g.cin <= 4 && (g.cout == 8 || g.cout == 16 || g.cout == 32) &&
       !getenv("WS_DISABLE_SMALL_CIN_Z3")) {
     const long long ncols = (long long)g.n * g.xo * g.yo;
     long long blocks = 148LL * 4 / g.cin;
@@ -838,7 +889,7 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
     WS_POST_LAUNCH(1);
     return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
   }
-  if (g.cin <= 4 && g.taps() * g.cin * g.cout <= 8 * 512) {
+  if (!deterministic && g.cin <= 4 && g.taps() * g.cin * g.cout <= 8 * 512) {
     const int O = g.taps() * g.cin * g.cout;
     int threads = O < 512 ? (O + 31) / 32 * 32 : 512;
     const long long ncols = (long long)g.n * g.xo * g.yo;
@@ -852,22 +903,13 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   }
   int va = vec_ok(in, g.cin) ? 1 : 0;
   int vb = vec_ok(dy, g.cout) ? 1 : 0;
-  auto pick = [](int c) { return c > 16 ? 64 : (c > 4 ? 16 : 4); };
-  int bm = pick(g.cin), bn = pick(g.cout);
-  int tiles = ((g.cin + bm - 1) / bm) * ((g.cout + bn - 1) / bn);
-  // enough K-splits to fill the chip ~4x, but at least 2048 voxels per split
-  long long target_blocks = 148LL * 4;
-  long long splits = (target_blocks + (long long)tiles * g.taps() - 1) / ((long long)tiles * g.taps());
-  long long max_splits = (K + 2047) / 2048;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
-  long long kps = (K + splits - 1) / splits;
-  kps = (kps + BK - 1) / BK * BK;
-  splits = (K + kps - 1) / kps;
-  dim3 grid((unsigned)tiles, (unsigned)g.taps(), (unsigned)splits);
+  const WgradPlan pl = wgrad_plan(g);
+  const int bm = pl.bm, bn = pl.bn;
+  const long long kps = pl.kps;
+  const long long split_stride = deterministic ? (long long)g.taps() * g.cin * g.cout : 0;
+  dim3 grid((unsigned)pl.tiles, (unsigned)g.taps(), (unsigned)pl.splits);
 #define WS_WG(BM_, BN_, TM_, TN_) \
-  conv_wgrad_simt<BM_, BN_, TM_, TN_><<<grid, kThreads, 0, st>>>(g, in, dy, wsp, kps, va, vb)
+  conv_wgrad_simt<BM_, BN_, TM_, TN_><<<grid, kThreads, 0, st>>>(g, in, dy, wsp, kps, va, vb, split_stride)
   if (bm == 64 && bn == 64) WS_WG(64, 64, 4, 4);
   else if (bm == 64 && bn == 16) WS_WG(64, 16, 2, 2);
   else if (bm == 64 && bn == 4) WS_WG(64, 4, 1, 1);
@@ -879,7 +921,7 @@ int simt_conv_wgrad(const ConvGeom& g, const View& in, const View& dy, float* dw
   else WS_WG(4, 4, 1, 1);
 #undef WS_WG
   WS_POST_LAUNCH(1);
-  return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st);
+  return wgrad_finalize_launch(wsp, dw, g.taps(), g.cin, g.cout, accumulate, st, deterministic ? (int)pl.splits : 1);
 }
 
 }  // namespace ws

@@ -23,6 +23,7 @@ from ._lib import (MATH_BF16, MATH_FP32, PACK_SIMT_DGRAD, PACK_SIMT_FWD, PACK_TC
 # precision
 # ------------------------------------------------------------------------------------------------------
 _PRECISION = "bf16"
+PRECISIONS = ("fp32", "bf16")
 
 
 def set_precision(mode: str) -> None:

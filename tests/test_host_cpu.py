@@ -253,18 +253,18 @@ def test_optimizer_step_invalidates_packed_weights():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the reference's CPU path = the oracle port, no GPU needed) prints ONE JSON line
-    with the keys the driver reads."""
+    """`bench.py --impl reference` (the reference's CPU path: the stock modules from baseline/_ref when installed, else
+    the oracle port; no GPU needed) prints ONE JSON line with the keys the driver reads."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                          "--warmup", "0", "--ref-batch", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "GAN train voxels/sec" and line["unit"] == "HR voxels/s"
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
 

@@ -157,3 +157,51 @@ def test_oracle_equals_live_reference_stencils():
     # FP64: the closed-form stencil agrees with torch.gradient to rounding (8.9e-16)
     a64 = process_data.calculate_gradient_of_wind_field(HR.double(), x.double(), y.double(), Z.double())
     assert rel_l2(wo.wind_gradient(HR.double(), x.double(), y.double(), Z.double()), a64) < 1e-13
+
+
+def _prep_case(z, i):
+    """(fields cropped, flags) of case i of prepare_batch.npz"""
+    layout, inc_p, inc_z, inc_ag, xs, ys, k, fx, fy = (int(v) for v in z["cases"][i])
+    return dict(inc_p=bool(inc_p), inc_z=bool(inc_z), inc_ag=bool(inc_ag), xs=xs, ys=ys, k=k, fx=fx, fy=fy)
+
+
+def test_data_oracle_matches_golden_bit_exact():
+    """oracle/data_oracle.py (crop + reformat + augment) against outputs of the reference's reformat_to_torch and
+    augmentation statements (tests/golden/make_golden_r02.py): bit-exact, all 48 (layout, rot, flip) cases."""
+    from oracle import data_oracle as do
+    z = load_npz("prepare_batch.npz")
+    c = {k[6:]: float(z[k]) for k in z.files if k.startswith("const/")}
+    size, cf = int(z["slice_size"]), int(z["coarseness"])
+    for i in range(len(z["cases"])):
+        m = _prep_case(z, i)
+        u, v, w, p, zz, zag = do.crop([z[k] for k in ("u", "v", "w", "p", "z", "zag")], m["xs"], m["ys"], size)
+        LR, HR, Z = do.reformat(u, v, w, p, zz, zag, c["Z_MIN"], c["Z_MAX"], c["Z_ABOVE_GROUND_MAX"], c["UVW_MAX"],
+                                c["P_MIN"], c["P_MAX"], cf, m["inc_p"], m["inc_z"], m["inc_ag"])
+        LR, HR, Z = do.augment(LR, HR, Z, m["k"], m["fx"], m["fy"])
+        for name, t in (("LR", LR), ("HR", HR), ("Z", Z)):
+            assert torch.equal(t, torch.from_numpy(z[f"case{i}/{name}"])), (i, name, m)
+
+
+def test_metrics_oracle_matches_golden():
+    from oracle import data_oracle as do
+    z = load_npz("metrics.npz")
+    HR, SR, LR = (torch.from_numpy(z[k]) for k in ("HR", "SR", "LR"))
+    psnr, tri_psnr, tri_l1 = do.validation_metrics(LR, HR, SR, int(z["scale"]), "l1")
+    assert abs(float(psnr) - float(z["psnr"])) <= 1e-5 and abs(float(tri_psnr) - float(z["tri_psnr"])) <= 1e-5
+    assert abs(float(tri_l1) - float(z["tri_l1"])) <= 1e-6
+    assert abs(float(do.validation_metrics(LR, HR, SR, int(z["scale"]), "l2")[2]) - float(z["tri_l2"])) <= 1e-6
+
+
+@needs_reference
+def test_data_oracle_equals_live_reference_reformat():
+    refshim.activate()
+    import process_data
+    from oracle import data_oracle as do
+    rng = np.random.default_rng(2)
+    f = [rng.normal(size=(8, 12, 4)) * 5 for _ in range(6)]
+    for flags in ((False, False, False), (False, True, False), (True, True, True), (True, False, False)):
+        a = process_data.reformat_to_torch(*f, -2.71, 550.44, 68.46, 32.33, 9e4, 1.05e5, coarseness_factor=4,
+                                           include_pressure=flags[0], include_z_channel=flags[1],
+                                           include_above_ground_channel=flags[2])
+        b = do.reformat(*f, -2.71, 550.44, 68.46, 32.33, 9e4, 1.05e5, 4, *flags)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))

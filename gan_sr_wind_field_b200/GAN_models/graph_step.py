@@ -45,6 +45,7 @@ class StepGraph:
         self.keep = ops.take_keepalive()
         self.launches = ops.launch_count() - launches0  # libwindsr kernels one replay launches
         self.optimizer = gan.optimizer_G if kind == "G" else gan.optimizer_D
+        self.optimizer.finish_capture()
         # references to what the captured step publishes (static tensors, refreshed by every replay)
         self.G_losses = dict(gan.train_G_loss_dict) if kind == "G" else None
         self.D_loss = gan.D_loss_dict["train_loss"] if kind == "D" else None

@@ -320,10 +320,14 @@ class wind_field_GAN_3D(BaseGAN):
             elif not bool(not_finite):
                 self.optimizer_G.step()
         d = self.train_G_loss_dict if training_iteration else self.validation_G_loss_dict
-        d.update(total=loss_G, adversarial=adv, pix=pix, xy_gradient=xy, z_gradient=zg, divergence=div,
-                 xy_divergence=dxy, feature_D=feat)
+        # detached: a stored loss with its grad_fn would keep this step's whole autograd graph (and the parameters'
+        # AccumulateGrad nodes, bound to the stream they were created on) alive into the next step — ~6 GB of saved
+        # activations, and a stream mismatch that invalidates a CUDA-graph capture of the next step
+        det = lambda t: t.detach()
+        d.update(total=det(loss_G), adversarial=det(adv), pix=det(pix), xy_gradient=det(xy), z_gradient=det(zg),
+                 divergence=det(div), xy_divergence=det(dxy), feature_D=det(feat))
         if not training_iteration:
-            self.metrics_dict["pix_loss_unscaled"] = pix / t.pixel_loss_weight
+            self.metrics_dict["pix_loss_unscaled"] = pix.detach() / t.pixel_loss_weight
             self.hist_dict["SR_pix_distribution"] = fake_HR.detach().cpu().numpy()
         return loss_G
 
@@ -368,9 +372,9 @@ class wind_field_GAN_3D(BaseGAN):
                 self.optimizer_D.found_inf = None
             self.optimizer_D.step()
         if training_epoch:
-            self.D_loss_dict["train_loss"] = loss_D
+            self.D_loss_dict["train_loss"] = loss_D.detach()
         else:
-            self.D_loss_dict["validation_loss"] = loss_D
+            self.D_loss_dict["validation_loss"] = loss_D.detach()
             self.hist_dict["D_pred_HR"] = torch.sigmoid(y_pred.detach()).cpu().numpy()[None]
             self.hist_dict["D_pred_SR"] = torch.sigmoid(fake_y_pred.detach()).cpu().numpy()[None]
 

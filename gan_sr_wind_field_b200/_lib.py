@@ -101,7 +101,7 @@ SYMBOLS = [
     ("ws_windloss_bwd_workspace_bytes", _Z, [_I, _I, _I, _I]),
     ("ws_windloss_bwd", _I, [_TP, _TP, _TP, _P, _P, _I, _I, _I, _I, _P, _P, _TP, _P, _Z, _P]),
     ("ws_adam_chunk_elems", _I, []),
-    ("ws_adam_step", _I, [_P, _P, _I, _I, _P, _F, _F, _F, _F, _F, _F, _P, _P]),
+    ("ws_adam_step", _I, [_P, _P, _I, _I, _P, _F, C.c_double, C.c_double, _F, _F, _F, _P, _P]),
     ("ws_instance_noise", _I, [_P, _P, _L, _F, _P, C.c_uint64, _P, _P]),
     ("ws_validation_metrics", _I, [_TP, _TP, _TP, _I, _I, _I, _I, _I, _I, _P, _P]),
     ("ws_prepare_batch", _I, [C.POINTER(WsPrepareDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(os.path.dirname(PKG_DIR), "build")
 LIB_PATH = os.path.join(PKG_DIR, "libwindsr.so")
 SOURCES = ["api.cu", "conv_simt.cu", "elementwise.cu", "windloss.cu", "conv_tc.cu", "conv_tc2.cu", "wgrad_tc.cu",
-           "train_aux.cu"]
+           "train_aux.cu", "rdb_persist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -55,6 +55,9 @@ int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const
                  cudaStream_t);
 size_t tc_rdb_wgrad_workspace_bytes(int, int, int, int);
 int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
+bool rdb_persist_ok(const ws_rdb_desc*, const View&, const View&, int);
+int rdb_persist_forward(const ws_rdb_desc*, const View&, const View&, const View&, void* const*, const Epi&,
+                        cudaStream_t);
 int copy_launch(const View&, const View&, int, int, long long, cudaStream_t);
 int axpby_launch(const View&, float, const View&, float, const View&, int, int, long long, cudaStream_t);
 int lrelu_bwd_launch(const View&, const View&, float, const float*, const float*, const View&, int, int,
@@ -79,6 +82,16 @@ int windloss_fwd_launch(const View&, const View&, const View&, const float*, con
                         float*, long long*, cudaStream_t);
 int windloss_bwd_launch(const View&, const View&, const View&, const float*, const float*, int, int, int, int,
                         const float*, const long long*, const View&, void*, size_t, cudaStream_t);
+
+static int device_sm_count() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  }
+  return sms;
+}
 
 static int device_cc_major() {
   static int major = -1;
@@ -441,7 +454,7 @@ ws_conv_shape rdb_merged_shape(const ws_rdb_desc* d) {
 // act: the operand view whose layout decides the path of the dense convs' / LFF's input (forward: the concat buffer;
 // backward: g_lff for the LFF and a gc-channel slice of gbuf for the dense convs).
 int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act, const ws_tensor* dense_act,
-               const float* const* w, void* const* packed, int dgrad, cudaStream_t st, bool fold_fwd = false) {
+               const float* const* w, void* const* packed, int dgrad, cudaStream_t st, int fold_fwd = 0) {
   const float* bw[WS_RDB_MAX_CONVS + 1];
   void* bp[WS_RDB_MAX_CONVS + 1];
   ConvGeom bg[WS_RDB_MAX_CONVS + 1] = {};
@@ -460,7 +473,7 @@ int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act,
       tc = dgrad_path(g, View(lff_act), d->math) == WS_PATH_TCGEN05;
     }
     if (tc) {
-      bw[nb] = w[i]; bp[nb] = packed[i]; bg[nb] = g; bf[nb] = (fold_fwd && !dgrad && i < d->nconv) ? 1 : 0; ++nb;
+      bw[nb] = w[i]; bp[nb] = packed[i]; bg[nb] = g; bf[nb] = (fold_fwd && !dgrad && i < d->nconv) ? fold_fwd : 0; ++nb;
     } else if (int e = pack_weights_launch(w[i], g, dgrad ? WS_PACK_SIMT_DGRAD : WS_PACK_SIMT_FWD, packed[i], st)) {
       return e;
     }
@@ -530,12 +543,24 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   WS_REQUIRE(x && x->ptr && buf && buf->ptr && out && out->ptr && w && packed, "ws_rdb_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const long long v = (long long)d->x * d->y * d->z;
+  if (device_cc_major() == 10 && rdb_persist_ok(d, View(x), View(buf), device_sm_count()) &&
+      fwd_path(ConvGeom(r.lff), View(buf), d->math) == WS_PATH_TCGEN05) {
+    // the whole block as one persistent cooperative kernel (rdb_persist.cu): z-folded dense-conv weights
+    if (d->repack)
+      if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st, 2)) return e;
+    ws_epilogue ep = plain_epilogue();
+    ep.bias = lff_bias;
+    ep.alpha = d->alpha;
+    ep.res1 = *x; ep.beta1 = d->beta1;
+    if (outer && outer->ptr) { ep.res2 = *outer; ep.beta2 = d->beta2; }
+    return rdb_persist_forward(d, View(x), View(buf), View(out), packed, Epi(&ep, d->f), st);
+  }
   // buf[:, :f] = x (cast to the activation dtype)
   ws_tensor b0 = *buf;
   if (int e = copy_launch(View(x), View(&b0), d->n, d->f, v, st)) return e;
   const bool fold = workspace && workspace_bytes >= ws_rdb_forward_workspace_bytes(d) && rdb_fold_ok(d, buf);
   if (d->repack)
-    if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st, fold)) return e;
+    if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st, fold ? 1 : 0)) return e;
   for (int i = 0; i < d->nconv; ++i) {
     const ws_conv_shape* s = &r.dense[i];
     ws_tensor in = *buf, o = slice(*buf, s->cin);

@@ -71,6 +71,7 @@ struct PackEntry {
   __nv_bfloat16* p;
   int cout, cin, taps, rows_pad, cols_pad, dgrad;
   int fold;  // > 0: x-fold forward packing — `fold` = kx taps side by side on the rows: p[(ky,kz)][dx*cout+co][ci]
+  int fold_z;  // with fold > 0: fold the kz taps instead (persistent RDB kernel): p[(kx,ky)][dz*cout+co][ci]
 };
 struct PackTable {
   int n;
@@ -93,7 +94,8 @@ __global__ void pack_tc_multi(const PackTable t) {
     if (e.fold) {
       // e.taps = ky*kz here; the full kernel has fold*e.taps taps, ordered (kx, ky, kz)
       const int dx = row / e.cout, co = row - dx * e.cout;
-      if (dx < e.fold && col < e.cin) v = w[((long long)co * e.cin + col) * (e.fold * e.taps) + dx * e.taps + tp];
+      const int full_tap = e.fold_z ? tp * e.fold + dx : dx * e.taps + tp;
+      if (dx < e.fold && col < e.cin) v = w[((long long)co * e.cin + col) * (e.fold * e.taps) + full_tap];
     } else if (!e.dgrad) {
       if (row < e.cout && col < e.cin) v = w[((long long)row * e.cin + col) * e.taps + tp];
     } else {
@@ -751,10 +753,14 @@ int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dg
     e.cout = g[i].cout; e.cin = g[i].cin; e.taps = g[i].taps(); e.dgrad = dgrad;
     e.rows_pad = dgrad ? (g[i].cin + 15) / 16 * 16 : (g[i].cout + 15) / 16 * 16;
     e.cols_pad = dgrad ? (g[i].cout + 7) / 8 * 8 : (g[i].cin + 7) / 8 * 8;
-    if (fold && fold[i] > 0 && !dgrad) {
+    if (fold && fold[i] == 1 && !dgrad) {
       e.fold = g[i].kx;
       e.taps = g[i].ky * g[i].kz;
       e.rows_pad = (g[i].kx * g[i].cout + 15) / 16 * 16;
+    } else if (fold && fold[i] == 2 && !dgrad) {
+      e.fold = g[i].kz; e.fold_z = 1;
+      e.taps = g[i].kx * g[i].ky;
+      e.rows_pad = (g[i].kz * g[i].cout + 15) / 16 * 16;
     }
     const long long total = (long long)e.taps * e.rows_pad * e.cols_pad;
     if (total > most) most = total;

@@ -1,0 +1,472 @@
+// rdb_persist.cu — a whole residual dense block (torch_blocks.py:192-290, 328-330) as ONE persistent cooperative kernel.
+//
+// Round-1 profile: the RRDB trunk (48 blocks x 5 convs on a 16x16x10 volume) ran as ~10 launches per block and
+// direction at ~17 us each while its tensor-core work is ~5 us per conv: launch latency, prologue, pipeline ramp and
+// drain of 500 tiny kernels were 25-40 % of the training step at 2.5 % tensor-pipe activity.  Here one CTA per
+// (sample, x-slab) stays resident for the whole block:
+//
+//   phase -1  cast the fp32 block input into channels [0, F) of the bf16 concat buffer
+//   phase i   dense conv i (3x3x3, cin = F + i*gc -> gc) + LeakyReLU -> channels [cin, cin + gc) of the concat buffer
+//   phase n   LFF 1x1x1 (F + n*gc -> F) with bias, alpha, the block skip and the optional RRDB skip -> fp32 output
+//
+// with a grid-wide barrier between phases (every conv reads its neighbours' previous outputs through the 3^3 halo).
+// TMEM, mbarriers, tensor-map prefetch and the role split (TMA producer / MMA issuer / 4 epilogue warps) are set up
+// once; the weights of the next phase are prefetched into the ring while the CTA waits at the barrier.
+//
+// Dense conv formulation ("z-fold"): the kz taps go side by side on the UMMA N dimension (N = 3*gc = 96: an MMA costs
+// the same 72 cycles for N = 32 and N = 96), so U[r][dz*gc + co] = sum_{kx,ky,c} A[r + kx*slab_p + ky*DZ][c] *
+// W[kx,ky,dz][c][co] needs 9 MMAs per K step instead of 27, and out[z] = U[z-1][dz=0] + U[z][dz=1] + U[z+1][dz=2] is a
+// neighbour-row sum in the epilogue (warp shuffles; rows are ordered (y, z) so z +- 1 are adjacent TMEM lanes).
+// The activation operand of a 64-channel chunk is ONE TMA box {64 ch, DZ, DY + 2, 3 slabs} — the output slab with its
+// x and y halo, zero padding by TMA out-of-bounds fill — and the (kx, ky) taps are UMMA descriptor row offsets into it.
+#include <cuda.h>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace ws {
+
+namespace {
+
+constexpr int kMaxPhases = WS_RDB_MAX_CONVS + 1;  // dense convs + LFF
+constexpr int kWSlots = 4;
+constexpr int kAStages = 2;
+constexpr int kThreads = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+
+struct RdbMaps {
+  CUtensorMap a[kMaxPhases];
+  CUtensorMap b[kMaxPhases];
+};
+
+struct RdbFwdParams {
+  int N, DX, DY, DZ;
+  int F, gc, nconv, ctot;
+  int slab;    // output rows of a CTA: DY * DZ
+  int slab_p;  // rows of one x-slab of the halo box: (DY + 2) * DZ
+  int t_m;     // 128-row accumulator tiles per CTA
+  int a_stage_bytes, w_slot_bytes;
+  int a_box_bytes_conv, a_box_bytes_lff;
+  int kchunks[kMaxPhases], last_k16[kMaxPhases];
+  int n_conv;  // UMMA N of a dense conv: 3 * gc
+  int n_lff;   // UMMA N of the LFF: F
+  float slope;
+  uint32_t tmem_cols;
+  int bar_slot;
+};
+
+// ---- grid-wide barrier ------------------------------------------------------------------------------------------
+// Sense-reversing counter barrier in global memory; reusable across launches without a host reset (the count returns
+// to zero, the generation only grows).  One thread per CTA calls it.  The spin is bounded: a protocol bug traps
+// instead of hanging the GPU.
+__device__ unsigned int g_bar_count[4];
+__device__ unsigned int g_bar_gen[4];
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(int slot, unsigned int nblocks) {
+  const unsigned int gen = ld_acquire(&g_bar_gen[slot]);
+  __threadfence();
+  const unsigned int old = atomicAdd(&g_bar_count[slot], 1u);
+  if (old == nblocks - 1) {
+    g_bar_count[slot] = 0u;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_bar_gen[slot]) : "memory");
+  } else {
+    const long long t0 = clock64();
+    while (ld_acquire(&g_bar_gen[slot]) == gen) {
+      if (clock64() - t0 > (1ll << 32)) __trap();  // ~2 s at 2 GHz
+    }
+  }
+  __threadfence();
+}
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams p, const View x, const View buf,
+                       const View out, const Epi ep_lff) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float edge_s[2 * 4 * 2 * 2 * 32];  // [tile][warp quarter][which: u0 of lane 31 / u2 of lane 0][..][32] (t_m <= 2)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t w_base = smem_base + (uint32_t)kAStages * p.a_stage_bytes;
+  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)kWSlots * p.w_slot_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kAStages + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * kAStages + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * kAStages + kWSlots + s); };
+  constexpr int kNumBars = 2 * kAStages + 2 * kWSlots;
+  const uint32_t accum_bar = bar_base + 8u * kNumBars;
+  const uint32_t phase_bar = bar_base + 8u * (kNumBars + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (kNumBars + 2);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (kNumBars + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / p.DX, x0 = blockIdx.x % p.DX;
+  const int nphases = p.nconv + 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < nphases; ++i) {
+      ptx::prefetch_tmap(&maps.a[i]);
+      ptx::prefetch_tmap(&maps.b[i]);
+    }
+    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::mbar_init(phase_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int ph = 0; ph < nphases; ++ph) {
+      const bool lff = ph == p.nconv;
+      const int ntaps = lff ? 1 : 9;
+      const int kch = p.kchunks[ph];
+      const int total_w = kch * ntaps;
+      const uint32_t w_bytes = (uint32_t)(lff ? p.n_lff : p.n_conv) * 128u;
+      int wi = 0;
+      auto issue_w = [&]() {
+        const int ch = wi / ntaps, tap = wi - ch * ntaps;
+        ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(w_full(wsl), w_bytes);
+          ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes, &maps.b[ph], w_full(wsl), ch * 64, 0, tap);
+        }
+        __syncwarp();
+        if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        ++wi;
+      };
+      // weights do not depend on the previous phase: fill the ring before waiting for the grid barrier
+      while (wi < total_w && wi < kWSlots) issue_w();
+      // the activations do: wait until every CTA has published the previous phase's output (phase_bar is armed by this
+      // CTA's epilogue after the grid barrier), then order the generic-proxy writes before our async-proxy reads
+      ptx::mbar_wait(phase_bar, (uint32_t)(ph & 1));
+      fence_proxy_async_global();
+      for (int ch = 0; ch < kch; ++ch) {
+        ptx::mbar_wait(a_empty(ab), aph ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t d = smem_base + ab * p.a_stage_bytes;
+          if (lff) {
+            ptx::mbar_expect_tx(a_full(ab), (uint32_t)p.a_box_bytes_lff);
+            ptx::tma_load_5d(d, &maps.a[ph], a_full(ab), ch * 64, 0, 0, x0, n);
+          } else {
+            ptx::mbar_expect_tx(a_full(ab), (uint32_t)p.a_box_bytes_conv);
+            ptx::tma_load_5d(d, &maps.a[ph], a_full(ab), ch * 64, 0, -1, x0 - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++ab == kAStages) { ab = 0; aph ^= 1u; }
+        const int upto = (ch + 1) * ntaps + kWSlots;
+        while (wi < total_w && wi < upto) issue_w();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int ph = 0; ph < nphases; ++ph) {
+      const bool lff = ph == p.nconv;
+      const int ntaps = lff ? 1 : 9;
+      const int n_umma = lff ? p.n_lff : p.n_conv;
+      const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)n_umma, 0u, 0u);
+      const int kch = p.kchunks[ph];
+      for (int ch = 0; ch < kch; ++ch) {
+        const int nk = (ch == kch - 1) ? p.last_k16[ph] : 4;
+        ptx::mbar_wait(a_full(ab), aph);
+        const uint32_t a_addr = smem_base + ab * p.a_stage_bytes;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          ptx::mbar_wait(w_full(wsl), wph);
+          ptx::tc_fence_after();
+          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes) >> 4) & 0x3fffu);
+          const uint32_t acc0 = (ch > 0 || tap > 0) ? 1u : 0u;
+          // tap (kx, ky) -> first operand row: the output rows start one y line into the centre slab of the box
+          const int roff = lff ? 0 : (tap / 3) * p.slab_p + (tap % 3) * p.DZ;
+          for (int m = 0; m < p.t_m; ++m) {
+            const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * 128u;
+            const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(m * 128);
+            if (ptx::elect_one()) {
+              ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
+              if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              if (nk > 2) ptx::mma_f16_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              if (nk > 3) ptx::mma_f16_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+          __syncwarp();
+          if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        }
+        if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
+        __syncwarp();
+        if (++ab == kAStages) { ab = 0; aph ^= 1u; }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int sub = warp & 3;            // TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 64;     // 0..127
+    auto publish = [&]() {
+      // make this CTA's global writes visible grid-wide, wait for everybody else's, release the producer
+      __threadfence();
+      fence_proxy_async_global();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        grid_barrier(p.bar_slot, gridDim.x);
+        ptx::mbar_arrive(phase_bar);
+      }
+    };
+    // ---- phase -1: x (fp32) -> buf[:, 0:F) (bf16), this CTA's slab
+    {
+      const int c8 = p.F / 8;
+      const long long v0 = (long long)x0 * p.slab;
+      for (int i = et; i < p.slab * c8; i += 128) {
+        const int r = i / c8, q = i - r * c8;
+        const float* src = (const float*)x.ptr + x.off(n, q * 8, v0 + r);
+        const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>((__nv_bfloat16*)buf.ptr + buf.off(n, q * 8, v0 + r)) = o;
+      }
+      publish();
+    }
+    const EpiVec ev = make_epi_vec(out, ep_lff);
+    for (int ph = 0; ph < nphases; ++ph) {
+      const bool lff = ph == p.nconv;
+      ptx::mbar_wait(accum_bar, (uint32_t)(ph & 1));
+      ptx::tc_fence_after();
+      if (!lff) {
+        const int c_out0 = p.F + ph * p.gc;  // first channel of this conv's slice of the concat buffer
+        const int gc = p.gc;
+        // pass 1: the rows a neighbouring warp (or the other tile) needs: u0 of lane 31, u2 of lane 0
+        for (int m = 0; m < p.t_m; ++m) {
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          float* e0 = edge_s + ((m * 4 + sub) * 2 + 0) * 32;
+          float* e2 = edge_s + ((m * 4 + sub) * 2 + 1) * 32;
+          for (int c0 = 0; c0 < gc; c0 += 16) {
+            uint32_t r0[16], r2[16];
+            ptx::tmem_ld16(t_row + (uint32_t)c0, r0);
+            ptx::tmem_ld16(t_row + (uint32_t)(2 * gc + c0), r2);
+            ptx::tmem_ld_wait();
+            if (lane == 31) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) e0[c0 + j] = __uint_as_float(r0[j]);
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) e2[c0 + j] = __uint_as_float(r2[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // pass 2: out[z] = lrelu(U0[z-1] + U1[z] + U2[z+1])
+        for (int m = 0; m < p.t_m; ++m) {
+          const int r = m * 128 + sub * 32 + lane;
+          const int z = r % p.DZ;
+          const bool row_ok = r < p.slab;
+          const bool has_lo = z > 0, has_hi = z < p.DZ - 1;
+          const int g = m * 4 + sub;
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          const long long v = (long long)x0 * p.slab + r;
+          __nv_bfloat16* dst = (__nv_bfloat16*)buf.ptr + buf.off(n, c_out0, v);
+          for (int c0 = 0; c0 < gc; c0 += 16) {
+            uint32_t r0[16], r1[16], r2[16];
+            ptx::tmem_ld16(t_row + (uint32_t)c0, r0);
+            ptx::tmem_ld16(t_row + (uint32_t)(gc + c0), r1);
+            ptx::tmem_ld16(t_row + (uint32_t)(2 * gc + c0), r2);
+            ptx::tmem_ld_wait();
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float lo = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
+              float hi = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+              if (lane == 0 && g > 0) lo = edge_s[((g - 1) * 2 + 0) * 32 + c0 + j];
+              if (lane == 31 && g < 4 * p.t_m - 1) hi = edge_s[((g + 1) * 2 + 1) * 32 + c0 + j];
+              float t = __uint_as_float(r1[j]) + (has_lo ? lo : 0.f) + (has_hi ? hi : 0.f);
+              y[j] = t > 0.f ? t : p.slope * t;
+            }
+            if (row_ok) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* q = reinterpret_cast<uint4*>(dst + c0);
+              q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        publish();
+      } else {
+        // LFF: out = alpha * (acc + bias) + beta1 * x + beta2 * outer   (fp32, epilogue.cuh)
+        for (int m = 0; m < p.t_m; ++m) {
+          const int r = m * 128 + sub * 32 + lane;
+          const bool row_ok = r < p.slab;
+          const long long v = (long long)x0 * p.slab + r;
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          float cur[16], nxt[16];
+          prefetch_res16(ep_lff, ev, n, v, 0, p.F, p.n_lff, row_ok, cur);
+          for (int c0 = 0; c0 < p.n_lff; c0 += 16) {
+            uint32_t rr[16];
+            ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
+            prefetch_res16(ep_lff, ev, n, v, c0 + 16, p.F, p.n_lff, row_ok, nxt);
+            ptx::tmem_ld_wait();
+            epilogue16_simple(ep_lff, ev, out, n, v, c0, p.F, row_ok, rr, cur);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+          }
+        }
+        ptx::tc_fence_before();
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int make_act_map(const View& src, int channels, int DX, int DY, int DZ, int N, int box_y, int box_x, CUtensorMap* out) {
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = reinterpret_cast<uintptr_t>(src.ptr);
+  k.rank = 5; k.dtype = WS_BF16;
+  k.dims[0] = (uint64_t)channels; k.dims[1] = (uint64_t)DZ; k.dims[2] = (uint64_t)DY; k.dims[3] = (uint64_t)DX;
+  k.dims[4] = (uint64_t)N;
+  k.strides[0] = (uint64_t)src.vs * 2;
+  k.strides[1] = (uint64_t)src.vs * 2 * DZ;
+  k.strides[2] = (uint64_t)src.vs * 2 * DZ * DY;
+  k.strides[3] = (uint64_t)src.ns * 2;
+  k.box[0] = 64; k.box[1] = (uint32_t)DZ; k.box[2] = (uint32_t)box_y; k.box[3] = (uint32_t)box_x; k.box[4] = 1;
+  for (int i = 0; i < 5; ++i) k.estr[i] = 1;
+  return get_tensor_map(k, out);
+}
+int make_w_map(const void* packed, int k_pad, int rows, int taps, CUtensorMap* out) {
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = reinterpret_cast<uintptr_t>(packed);
+  k.rank = 3; k.dtype = WS_BF16;
+  k.dims[0] = (uint64_t)k_pad; k.dims[1] = (uint64_t)rows; k.dims[2] = (uint64_t)taps;
+  k.strides[0] = (uint64_t)k_pad * 2;
+  k.strides[1] = (uint64_t)k_pad * 2 * rows;
+  k.box[0] = 64; k.box[1] = (uint32_t)rows; k.box[2] = 1;
+  k.estr[0] = k.estr[1] = k.estr[2] = 1;
+  return get_tensor_map(k, out);
+}
+
+bool env_off(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
+}  // namespace
+
+// Geometry the persistent kernels cover: bf16 tensor-core mode, 3^3 dense convs with gc % 16 == 0 and 3 * gc <= 128,
+// 1^3 LFF with F % 16 == 0 and F <= 128, one x-slab of DY * DZ <= 256 rows per CTA and at most one CTA per SM.
+bool rdb_persist_ok(const ws_rdb_desc* d, const View& x, const View& buf, int sm_count) {
+  static const bool off = env_off("WS_DISABLE_RDB_PERSIST");
+  if (off || d->math != WS_MATH_BF16) return false;
+  if (d->nconv < 1 || d->nconv > WS_RDB_MAX_CONVS || d->k != 3 || d->k_lff != 1) return false;
+  if (d->gc % 16 != 0 || 3 * d->gc > 128 || d->f % 16 != 0 || d->f > 128 || d->f % 8 != 0) return false;
+  const int slab = d->y * d->z;
+  if (slab > 256 || d->z > 128 || d->y + 2 > 256) return false;
+  if ((long long)d->n * d->x > sm_count) return false;
+  if (buf.dtype != WS_BF16 || buf.cs != 1 || x.dtype != WS_F32 || x.cs != 1) return false;
+  if ((reinterpret_cast<uintptr_t>(buf.ptr) & 15) || (buf.vs * 2) % 16 || (buf.ns * 2) % 16) return false;
+  if ((reinterpret_cast<uintptr_t>(x.ptr) & 15) || (x.vs * 4) % 16 || (x.ns * 4) % 16) return false;
+  return true;
+}
+
+// packed[i], i < nconv: z-folded forward packing [tap (kx,ky)][dz * gc + co][cin_pad8] (pack_tc_multi, fold axis z);
+// packed[nconv]: the LFF's ordinary forward packing.
+int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, const View& out, void* const* packed,
+                        const Epi& ep_lff, cudaStream_t st) {
+  RdbFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n; p.DX = d->x; p.DY = d->y; p.DZ = d->z;
+  p.F = d->f; p.gc = d->gc; p.nconv = d->nconv; p.ctot = d->f + d->nconv * d->gc;
+  p.slab = d->y * d->z;
+  p.slab_p = (d->y + 2) * d->z;
+  p.t_m = (p.slab + 127) / 128;
+  p.n_conv = 3 * d->gc;
+  p.n_lff = d->f;
+  p.slope = d->slope;
+  p.bar_slot = 0;
+  p.a_box_bytes_conv = 3 * p.slab_p * 128;
+  p.a_box_bytes_lff = p.slab * 128;
+  p.a_stage_bytes = (p.a_box_bytes_conv + 1023) / 1024 * 1024;
+  p.w_slot_bytes = ((p.n_conv > p.n_lff ? p.n_conv : p.n_lff) * 128 + 1023) / 1024 * 1024;
+  RdbMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i <= d->nconv; ++i) {
+    const bool lff = i == d->nconv;
+    const int cin = lff ? p.ctot : d->f + i * d->gc;
+    p.kchunks[i] = (cin + 63) / 64;
+    p.last_k16[i] = (cin - 64 * (p.kchunks[i] - 1) + 15) / 16;
+    if (int e = make_act_map(buf, cin, d->x, d->y, d->z, d->n, lff ? d->y : d->y + 2, lff ? 1 : 3, &maps.a[i])) return e;
+    const int k_pad = (cin + 7) / 8 * 8;
+    if (int e = make_w_map(packed[i], k_pad, lff ? (d->f + 15) / 16 * 16 : p.n_conv, lff ? 1 : 9, &maps.b[i])) return e;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < p.t_m * 128) cols <<= 1;
+  p.tmem_cols = cols;
+  // the MMA rows of the last tile / the largest tap offset read past the loaded box (rows that are never stored):
+  // they must still lie inside this CTA's shared memory
+  const size_t reach = (size_t)(p.t_m * 128 + 2 * p.slab_p + 2 * p.DZ) * 128;
+  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)kWSlots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
+  if (smem < (size_t)p.a_stage_bytes + reach + 1024) smem = (size_t)p.a_stage_bytes + reach + 1024;
+  WS_REQUIRE(smem <= 225 * 1024, "rdb_persist: shared memory request %zu too large", smem);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute((const void*)rdb_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    225 * 1024);
+  });
+  WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(d->n * d->x));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rdb_fwd_persist_kernel, maps, p, x, buf, out, ep_lff));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+}  // namespace ws

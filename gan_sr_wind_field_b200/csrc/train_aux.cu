@@ -32,23 +32,26 @@ constexpr int kAdamChunk = 8192;  // elements per block
 //   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),   t = step + 1
 __global__ void __launch_bounds__(kBlock)
 adam_multi_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, const float* __restrict__ lr_dev,
-                  float lr, float b1, float b2, float eps, float wd, float grad_scale,
+                  float lr, double b1d, double b2d, float eps, float wd, float grad_scale,
                   const float* __restrict__ found_inf) {
   if (found_inf && *found_inf != 0.f) return;
   const int2 ck = chunks[blockIdx.x];
   const AdamTensor t = tab[ck.x];
   if (lr_dev) lr = *lr_dev;
-  const float stepf = *t.step + 1.f;
-  const float bc1 = 1.f - powf(b1, stepf);
-  const float bc2_sqrt = sqrtf(1.f - powf(b2, stepf));
-  const float step_size = lr / bc1;
+  // bias corrections and the (1 - beta) factors in double, like torch's host-side Python arithmetic: float(0.999) is
+  // 1.3e-5 (relative to 1 - beta2) away from 0.999
+  const double stepd = (double)*t.step + 1.0;
+  const float b1 = (float)b1d, b2 = (float)b2d;
+  const float omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2d, stepd));
+  const float step_size = (float)((double)lr / (1.0 - pow(b1d, stepd)));
   const long long lo = (long long)ck.y * kAdamChunk;
   const long long hi = lo + kAdamChunk < t.n ? lo + kAdamChunk : t.n;
   const bool vec = (((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0;
   auto upd = [&](float& p, float g, float& m, float& v) {
     g = g * grad_scale + wd * p;
-    m = m + (g - m) * (1.f - b1);
-    v = b2 * v + (1.f - b2) * g * g;
+    m = m + (g - m) * omb1;
+    v = b2 * v + omb2 * g * g;
     p -= step_size * m / (sqrtf(v) / bc2_sqrt + eps);
   };
   if (vec) {
@@ -270,7 +273,7 @@ extern "C" {
 int ws_adam_chunk_elems(void) { return kAdamChunk; }
 
 int ws_adam_step(const void* table, const void* chunks, int ntensors, int nchunks, const float* lr_dev, float lr,
-                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, const float* found_inf,
+                 double beta1, double beta2, float eps, float weight_decay, float grad_scale, const float* found_inf,
                  void* stream) {
   WS_REQUIRE(table && chunks && ntensors > 0 && nchunks > 0, "ws_adam_step: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;

@@ -615,7 +615,9 @@ class RDBState:
             self.packed[dgrad] = [torch.empty(lib.ws_rdb_packed_bytes(C.byref(desc), i, dgrad), dtype=torch.uint8,
                                               device=params[0].device) for i in range(nconv + 1)]
             self.stamp[dgrad] = None
-        stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + (desc.math, _WEIGHTS_EPOCH)
+        # (the geometry decides which packing the executor uses: persistent z-fold, x-fold or direct)
+        stamp = tuple((p._version, p.data_ptr()) for p in params[:nconv + 1]) + \
+            (desc.math, _WEIGHTS_EPOCH, desc.n, desc.x, desc.y, desc.z)
         repack = stamp != self.stamp[dgrad]
         self.stamp[dgrad] = stamp
         if capturing():  # a replay must repack from the weights of ITS step; eager calls after it must not trust us

@@ -30,6 +30,7 @@ class WindAdam(torch.optim.Adam):
         self.grad_scale = 1.0          # folded into the gradient read (e.g. 1/world_size after a SUM all-reduce)
         self._tables = {}              # group index -> (key, table_dev, chunks_dev, ntensors, nchunks, lr_dev)
         self._staging = {}
+        self._pending = []             # (device table, host bytes) of tables referenced by a graph under capture
 
     # -- state ----------------------------------------------------------------------------------------------
     def _ensure_state(self, p):
@@ -75,10 +76,11 @@ class WindAdam(torch.optim.Adam):
         chunks = np.concatenate(chunks, 0)
         raw = np.concatenate((tab.view(np.uint8).reshape(-1), chunks.view(np.uint8).reshape(-1)))
         if capturing:
-            # a captured step must not depend on host staging that a later eager step could overwrite
-            host = torch.from_numpy(raw.copy()).pin_memory()
-            blob = host.to(dev, non_blocking=True)
-            self._staging[("capture", gi, len(self._staging))] = (host, blob)
+            # Nothing may allocate pinned memory or copy from the host inside a capture.  The captured kernel only
+            # needs the ADDRESS of its table: allocate the device buffer now (graph memory pool) and fill it right
+            # after the capture has ended (finish_capture), before the first replay.
+            blob = torch.empty(raw.size, dtype=torch.uint8, device=dev)
+            self._pending.append((blob, raw.copy()))
         else:
             host = self._staging.get(gi)
             if host is None or host.numel() < raw.size:
@@ -93,6 +95,13 @@ class WindAdam(torch.optim.Adam):
         if not capturing:
             self._tables[gi] = hit
         return hit
+
+    def finish_capture(self):
+        """Upload the pointer tables of the kernels captured since the last call (see _table)."""
+        for blob, raw in self._pending:
+            blob.copy_(torch.from_numpy(raw))
+            self._staging[("captured", len(self._staging))] = blob  # owned for the lifetime of the optimizer
+        self._pending = []
 
     # -- device-side learning rate ------------------------------------------------------------------------------
     def lr_tensor(self, gi=0):

@@ -313,7 +313,7 @@ int ws_adam_chunk_elems(void);
  * found_inf (optional device float): non-zero -> the whole call is a no-op, the reference's "skip the step when the
  * loss is NaN/Inf" guard without a host read. */
 int ws_adam_step(const void* table, const void* chunks, int ntensors, int nchunks, const float* lr_dev, float lr,
-                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, const float* found_inf,
+                 double beta1, double beta2, float eps, float weight_decay, float grad_scale, const float* found_inf,
                  void* stream);
 
 /* ---- instance noise (tools/trainingtricks.py:49-58; used wind_field_GAN_3D.py:250-299) --------------------------- */

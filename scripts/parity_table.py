@@ -31,10 +31,17 @@ def main():
     ds = (torch.bernoulli(torch.full((B, 144), 1.0 - p), generator=g) / (1.0 - p)).cuda()
     sd = {k: v.detach().clone() for k, v in gan.G.state_dict().items()}
     w = pu.loss_weights(cfg)
-    SR_ref, L_ref, g_ref, dLR_ref = pu.oracle_generator_step(sd, batch, w, ds)
+    # arbiter: the oracle in float64; "ref fp32" columns = the oracle in strict fp32 against it, i.e. how far the
+    # reference's own fp32 arithmetic is from the exact result (LeakyReLU sign flips of near-zero pre-activations)
+    SR_ref, L_ref, g_ref, dLR_ref = pu.oracle_generator_step(sd, batch, w, ds, dtype=torch.float64)
+    SR32, L32, g32, dLR32 = pu.oracle_generator_step(sd, batch, w, ds)
+    ref32 = pu.grad_errors(g32, g_ref)
+    ref32_rows = pu.summarize(ref32)
     lines = [f"# Parity table — upscale8 generator step at the shipped configuration, B = {B} (round 2)", "",
              "`python scripts/parity_table.py` on one B200.  Checker: `oracle/wind_oracle.py` executed on the GPU in strict "
-             "fp32 (TF32 off), the restatement `tests/test_oracle_pinned.py` pins bit-exactly to the reference.  ",
+             "**float64** (the arbiter), the restatement `tests/test_oracle_pinned.py` pins bit-exactly to the reference; "
+             "*ref fp32* = the same oracle in strict fp32 (TF32 off) against the float64 result — the error the "
+             "reference's own fp32 arithmetic has.  ",
              "Step: `G(LR, Z)` in train mode with a fixed Dropout3d mask, the reference's generator loss (pixel L1 0.136 + "
              "xy-gradient 3.064 + divergence 0.366 + xy-divergence 0.721, adversarial weight 0), backward to every "
              "parameter and to LR.  rel-L2 = ||ours - oracle|| / ||oracle|| per tensor; rows aggregate the tensors of one "
@@ -52,16 +59,20 @@ def main():
         rows = pu.summarize(errs)
         tol = TOL[mode]
         n_over = sum(1 for e in errs.values() if e > tol)
+        n_ref_over = sum(1 for e in ref32.values() if e > tol)
         lines += [f"## {mode.upper()} mode — north-star bar {tol:g}", "",
-                  f"* SR: **{rel_l2(SR, SR_ref):.2e}**; loss: {abs(float(L) - float(L_ref)) / abs(float(L_ref)):.2e} "
-                  f"relative; dL/dLR: {rel_l2(dLR, dLR_ref):.2e}"
-                  + (f" (envelope {rel_l2(dLR_env, dLR_ref):.2e})" if env else ""),
-                  f"* parameter gradients above the flat bar: **{n_over} of {len(errs)}**", "",
-                  "| layer family | tensors | median | max | worst tensor |" + (" envelope median | envelope max |" if env else ""),
-                  "|---|---:|---:|---:|---|" + ("---:|---:|" if env else "")]
+                  f"* SR: **{rel_l2(SR, SR_ref):.2e}** (ref fp32: {rel_l2(SR32, SR_ref):.2e}); loss: "
+                  f"{abs(float(L) - float(L_ref)) / abs(float(L_ref)):.2e} relative; dL/dLR: {rel_l2(dLR, dLR_ref):.2e} "
+                  f"(ref fp32: {rel_l2(dLR32, dLR_ref):.2e}"
+                  + (f", envelope {rel_l2(dLR_env, dLR_ref):.2e})" if env else ")"),
+                  f"* parameter gradients above the flat bar: **{n_over} of {len(errs)}** (ref fp32: {n_ref_over})", "",
+                  "| layer family | tensors | median | max | worst tensor | ref fp32 median | ref fp32 max |"
+                  + (" envelope median | envelope max |" if env else ""),
+                  "|---|---:|---:|---:|---|---:|---:|" + ("---:|---:|" if env else "")]
         for grp, (n, med, mx, worst) in sorted(rows.items()):
             extra = f" {env_rows[grp][1]:.2e} | {env_rows[grp][2]:.2e} |" if env else ""
-            lines.append(f"| {grp} | {n} | {med:.2e} | {mx:.2e} | `{worst}` |{extra}")
+            lines.append(f"| {grp} | {n} | {med:.2e} | {mx:.2e} | `{worst}` | {ref32_rows[grp][1]:.2e} | "
+                         f"{ref32_rows[grp][2]:.2e} |{extra}")
         lines.append("")
         print("\n".join(lines[-(len(rows) + 8):]), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

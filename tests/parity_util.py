@@ -80,12 +80,14 @@ def loss_weights(cfg):
                 div=t.divergence_loss_weight, dxy=t.xy_divergence_loss_weight, adv=t.adversarial_loss_weight)
 
 
-def oracle_generator_step(sd, batch, weights, dropout_scale, rounding=None):
-    """Generator forward + the reference's generator loss + backward with the oracle on the GPU (strict fp32).
-    Returns (SR, loss, {name: grad}, dL/dLR)."""
+def oracle_generator_step(sd, batch, weights, dropout_scale, rounding=None, dtype=torch.float32):
+    """Generator forward + the reference's generator loss + backward with the oracle on the GPU (strict fp32, or
+    float64 — the arbiter between two fp32 implementations).  Returns (SR, loss, {name: grad}, dL/dLR)."""
     from oracle import wind_oracle as wo
-    LR, HR, Z, x, y = batch
-    p = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    LR, HR, Z, x, y = (t.to(dtype) for t in batch)
+    if dropout_scale is not None:
+        dropout_scale = dropout_scale.to(dtype)
+    p = {k: v.detach().to(dtype).requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     lr = LR.detach().clone().requires_grad_(True)
     with strict_fp32(), operand_rounding(rounding):
         SR = wo.generator_forward(p, lr, Z, dropout_scale=dropout_scale)

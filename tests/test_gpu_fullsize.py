@@ -40,24 +40,41 @@ def test_full_size_generator_step_vs_oracle(mode):
     ds = _dropout_scale(B, 144, cfg.generator.dropout_probability, "cuda:0")
     sd = {k: v.detach().clone() for k, v in gan.G.state_dict().items()}
     w = pu.loss_weights(cfg)
-    SR_ref, L_ref, g_ref, dLR_ref = pu.oracle_generator_step(sd, batch, w, ds)
+    # arbiter: the oracle in float64.  Two fp32 implementations that sum in different orders decide the sign of a
+    # LeakyReLU pre-activation differently for the few values within rounding distance of zero, and each such flip
+    # changes a gradient element by a factor of 5 — through 200 layers that alone is ~1e-4 rel-L2 on gradients, for
+    # the reference's own fp32 arithmetic too (measured below as `e_ref32`).
+    SR_ref, L_ref, g_ref, dLR_ref = pu.oracle_generator_step(sd, batch, w, ds, dtype=torch.float64)
+    SR32, L32, g32, dLR32 = pu.oracle_generator_step(sd, batch, w, ds)
     SR, L, g, dLR = pu.native_generator_step(gan, batch, mode, ds)
     tol = TOL[mode]
     e_sr, e_l = rel_l2(SR, SR_ref), abs(float(L) - float(L_ref)) / abs(float(L_ref))
     errs = pu.grad_errors(g, g_ref)
     errs["dL/dLR"] = rel_l2(dLR, dLR_ref)
+    ref32 = pu.grad_errors(g32, g_ref)
+    ref32["dL/dLR"] = rel_l2(dLR32, dLR_ref)
     rows = pu.summarize({k: v for k, v in errs.items() if k != "dL/dLR"})
-    print(f"\n[{mode}] B={B}  SR rel-L2 {e_sr:.2e}  loss rel {e_l:.2e}  dL/dLR {errs['dL/dLR']:.2e}")
+    rows32 = pu.summarize({k: v for k, v in ref32.items() if k != "dL/dLR"})
+    print(f"\n[{mode}] B={B}  SR rel-L2 {e_sr:.2e} (fp32 oracle {rel_l2(SR32, SR_ref):.2e})  loss rel {e_l:.2e}  "
+          f"dL/dLR {errs['dL/dLR']:.2e} (fp32 oracle {ref32['dL/dLR']:.2e})")
     for grp, (n, med, mx, worst) in sorted(rows.items()):
-        print(f"[{mode}]   {grp:34s} n={n:3d} median {med:.2e} max {mx:.2e} ({worst})")
+        print(f"[{mode}]   {grp:34s} n={n:3d} median {med:.2e} max {mx:.2e} | fp32 oracle median "
+              f"{rows32[grp][1]:.2e} max {rows32[grp][2]:.2e}")
     assert SR.shape == (B, 3, 128, 128, 10)
     assert e_sr <= tol, e_sr
     assert e_l <= tol, e_l
     if mode == "fp32":
-        # gradients: sums of up to 3.3e5 products per weight with heavy cancellation, re-associated by the GPU
-        # (two-level in-order summation, deterministic); the flat bar holds
-        bad = {k: e for k, e in errs.items() if e > tol}
+        # flat 1e-5 where the reference's own fp32 arithmetic achieves it (SR, loss, hr_convs.2).  Everything behind
+        # a LeakyReLU is as close to the float64 result as the reference's fp32 arithmetic is: sign flips are rare,
+        # heavy-tailed events, so the bound is per layer family — median within 2.5x of the reference's median, every
+        # tensor within 2x of the reference's worst tensor of the family.
+        fam32 = {g: r for g, r in rows32.items()}
+        bad = {k: (e, ref32[k]) for k, e in errs.items()
+               if k != "dL/dLR" and e > max(tol, 2.0 * fam32[pu.group_of(k)][2])}
         assert not bad, bad
+        slow = {g: (r[1], fam32[g][1]) for g, r in rows.items() if r[1] > max(tol, 2.5 * fam32[g][1])}
+        assert not slow, slow
+        assert errs["dL/dLR"] <= max(tol, 2.5 * ref32["dL/dLR"])
         return
     _, _, g_env, dLR_env = pu.oracle_generator_step(sd, batch, w, ds, rounding=mode)
     env = pu.grad_errors(g_env, g_ref)
@@ -90,18 +107,22 @@ def test_full_width_discriminator_vs_oracle(mode):
     sd0 = {k: v.detach().clone() for k, v in D.state_dict().items()}
     cot = torch.linspace(-1.0, 1.0, B, device="cuda").reshape(B, 1)
 
-    def oracle(rounding=None):
-        p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+    def oracle(rounding=None, dtype=torch.float32):
+        cast = lambda v: v.to(dtype) if v.is_floating_point() else v.clone()
+        p = {k: (cast(v).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else cast(v))
              for k, v in sd0.items()}
-        xi = x.detach().clone().requires_grad_(True)
+        xi = x.detach().to(dtype).requires_grad_(True)
         upd = {}
         with pu.strict_fp32(), pu.operand_rounding(rounding):
             out = wo.discriminator_forward(p, xi, True, updated_stats=upd)
             names = [k for k, v in p.items() if v.requires_grad]
-            grads = torch.autograd.grad((out * cot).sum(), [xi] + [p[k] for k in names])
+            grads = torch.autograd.grad((out * cot.to(dtype)).sum(), [xi] + [p[k] for k in names])
         return out.detach(), upd, grads[0], dict(zip(names, grads[1:]))
 
-    out_ref, upd_ref, dx_ref, g_ref = oracle()
+    out_ref, upd_ref, dx_ref, g_ref = oracle(dtype=torch.float64)  # float64 arbiter (see the generator test)
+    out32, _, dx32, g32 = oracle()
+    ref32 = {k: rel_l2(g32[k], g_ref[k]) for k in g_ref}
+    ref32["dL/dx"] = rel_l2(dx32, dx_ref)
     with ops.precision(mode):
         out = D(x)
         (out * cot).sum().backward()
@@ -116,9 +137,12 @@ def test_full_width_discriminator_vs_oracle(mode):
     for k, e in sorted(errs.items(), key=lambda kv: -kv[1])[:8]:
         print(f"[{mode}]   {k}: {e:.2e}")
     assert e_stats <= tol
+    print(f"[{mode}]   the reference's fp32 arithmetic vs float64: out {rel_l2(out32, out_ref):.2e}, worst grad "
+          f"{max(ref32.values()):.2e}")
     if mode == "fp32":
-        assert e_out <= tol, e_out
-        bad = {k: e for k, e in errs.items() if e > 5 * tol}  # ten train-mode BatchNorms in series: see the table
+        assert e_out <= max(tol, 2.5 * rel_l2(out32, out_ref)), e_out
+        worst32 = max(ref32.values())
+        bad = {k: (e, ref32[k]) for k, e in errs.items() if e > max(tol, 2.5 * ref32[k], worst32)}
         assert not bad, bad
         return
     out_env, _, dx_env, g_env = oracle(mode)

@@ -58,6 +58,9 @@ int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t)
 bool rdb_persist_ok(const ws_rdb_desc*, const View&, const View&, int);
 int rdb_persist_forward(const ws_rdb_desc*, const View&, const View&, const View&, void* const*, const Epi&,
                         cudaStream_t);
+bool rdb_persist_bwd_ok(const ws_rdb_desc*, const View&, const View&, const View&, const View&, const View&, int);
+int rdb_persist_backward(const ws_rdb_desc*, const View&, const View&, const View&, const View&, const View&,
+                         void* const*, cudaStream_t);
 int copy_launch(const View&, const View&, int, int, long long, cudaStream_t);
 int axpby_launch(const View&, float, const View&, float, const View&, int, int, long long, cudaStream_t);
 int lrelu_bwd_launch(const View&, const View&, float, const float*, const float*, const View&, int, int,
@@ -620,10 +623,48 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   WS_REQUIRE(d->nconv == 0 || (gbuf && gbuf->ptr), "ws_rdb_backward: null g scratch");
   cudaStream_t st = (cudaStream_t)stream;
   const long long v = (long long)d->x * d->y * d->z;
+  const bool want_w = dw != nullptr;
+  if (device_cc_major() == 10 && d->nconv > 0 && dx && dx->ptr &&
+      rdb_persist_bwd_ok(d, View(dy), View(buf), View(g_lff), View(gbuf), View(dx), device_sm_count()) &&
+      dgrad_path(ConvGeom(r.lff), View(g_lff), d->math) == WS_PATH_TCGEN05) {
+    // the whole data-gradient chain as one persistent cooperative kernel (rdb_persist.cu); the weight-gradient GEMMs
+    // follow on the auxiliary stream (or behind it)
+    if (d->repack)
+      if (int e = rdb_repack(d, r, g_lff, gbuf, w, packed, 1, st)) return e;
+    if (int e = rdb_persist_backward(d, View(dy), View(buf), View(g_lff), View(gbuf), View(dx), packed, st)) return e;
+    if (!want_w) return 0;
+    const bool merged = rdb_merged_wgrad_ok(d, buf, gbuf);
+    const bool aux = aux_stream && aux_stream != stream && aux_workspace &&
+                     aux_workspace_bytes >= ws_rdb_backward_workspace_bytes(d);
+    cudaStream_t wst = aux ? (cudaStream_t)aux_stream : st;
+    void* wws = aux ? aux_workspace : workspace;
+    const size_t wws_bytes = aux ? aux_workspace_bytes : workspace_bytes;
+    if (aux) {
+      cudaEvent_t ev = rdb_event();
+      WS_REQUIRE(ev != nullptr, "ws_rdb_backward: cannot create events");
+      WS_CHECK_CUDA(cudaEventRecord(ev, st));  // g_lff and every g_i are complete
+      WS_CHECK_CUDA(cudaStreamWaitEvent(wst, ev, 0));
+    }
+    if (dw[d->nconv] || db_lff)
+      if (int e = ws_conv3d_wgrad(&r.lff, buf, g_lff, dw[d->nconv], db_lff, 0, d->math, wws, wws_bytes, (void*)wst))
+        return e;
+    if (merged) {
+      ws_conv_shape ms = rdb_merged_shape(d);
+      int cin[WS_RDB_MAX_CONVS];
+      for (int j = 0; j < d->nconv; ++j) cin[j] = r.dense[j].cin;
+      return tc_rdb_wgrad(ConvGeom(ms), View(buf), View(gbuf), dw, cin, d->nconv, d->gc, wws, wws_bytes, wst);
+    }
+    for (int i = 0; i < d->nconv; ++i) {
+      if (!dw[i]) continue;
+      ws_tensor gslice = slice(*gbuf, i * d->gc);
+      if (int e = ws_conv3d_wgrad(&r.dense[i], buf, &gslice, dw[i], nullptr, 0, d->math, wws, wws_bytes, (void*)wst))
+        return e;
+    }
+    return 0;
+  }
   // gradient entering the LFF accumulator: alpha * dy, in the activation dtype
   if (int e = axpby_launch(View(dy), d->alpha, View((const ws_tensor*)nullptr), 0.f, View(g_lff), d->n, d->f, v, st))
     return e;
-  const bool want_w = dw != nullptr;
   bool dx_done = false;
   // gbuf holds the gradients of ALL dense conv outputs side by side (n, nconv*gc, ..): the dgrad chain consumes
   // slice i as it goes, the weight gradients of the dense convs are then one merged GEMM at the end.

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams p, const View x, const View buf,
                        const View out, const Epi ep_lff) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float edge_s[2 * 4 * 2 * 2 * 32];  // [tile][warp quarter][which: u0 of lane 31 / u2 of lane 0][..][32] (t_m <= 2)
+  __shared__ float edge_s[2 * 4 * 2 * 32];  // [tile (t_m <= 2)][warp quarter][u0 of lane 31 | u2 of lane 0][32 channels]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_base = smem_base + (uint32_t)kAStages * p.a_stage_bytes;
@@ -357,30 +357,318 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
   }
 }
 
-int make_act_map(const View& src, int channels, int DX, int DY, int DZ, int N, int box_y, int box_x, CUtensorMap* out) {
+// ---- backward: the data-gradient chain of the block ----------------------------------------------------------------
+// dL/d(concat buffer) never leaves the SM: a CTA owns the same voxel rows in every phase and keeps their fp32
+// gradient for ALL ctot channels in tensor memory (2 tiles x 256 columns = the whole 512-column TMEM), so the
+// accumulate-into-gradient read-modify-write of the per-conv kernels (37 MB through L2 per conv) disappears:
+//
+//   phase -1  g_lff = alpha * dy (bf16) for this CTA's rows                                   (CTA-local)
+//   phase L   acc[:, 0:ctot)  = g_lff x W_lff^T                                               (1x1x1: no halo)
+//             g_{n-1} = acc[:, ctot-gc:ctot) * lrelu'(buf[..])  -> gbuf slice n-1             | grid barrier
+//   phase i   acc[:, 0:cin_i) += dgrad_i(g_i)   (27 taps as row offsets into ONE halo box of g_i, K = gc = 32)
+//             g_{i-1} = acc[:, cin_i-gc:cin_i) * lrelu'(buf[..]) -> gbuf slice i-1            | grid barrier   (i = n-1 .. 1)
+//   phase 0   acc[:, 0:F) += dgrad_0(g_0);  dx = acc[:, 0:F) + beta1 * dy                     (fp32 out)
+//
+// Rows are ordered (y, z) with a z pitch of DZ + 2, so the kz taps are row offsets too (the halo box carries the z pad
+// rows; TMA out-of-bounds fill supplies every zero).  gbuf (all g_i side by side) and g_lff feed the weight-gradient
+// GEMMs afterwards (wgrad_tc.cu), exactly as in the per-conv path.
+struct RdbBwdParams {
+  int N, DX, DY, DZ;
+  int F, gc, nconv, ctot;
+  int pz;      // z pitch of the row order: DZ + 2
+  int slab;    // voxels of an x-slab: DY * DZ
+  int slab_p;  // rows of one x-slab of the halo box: (DY + 2) * pz
+  int t_m;
+  int ctot_pad;  // accumulator columns per tile
+  int a_stage_bytes, w_slot_bytes;
+  int a_box_bytes_conv, a_box_bytes_lff;
+  int kch_lff, last_k16_lff;
+  int cin[kMaxPhases];
+  float slope, alpha, beta1;
+  uint32_t tmem_cols;
+  int bar_slot;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams p, const View dy, const View buf,
+                       const View g_lff, const View gbuf, const View dx) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t w_base = smem_base + (uint32_t)kAStages * p.a_stage_bytes;
+  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)kWSlots * p.w_slot_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kAStages + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * kAStages + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * kAStages + kWSlots + s); };
+  constexpr int kNumBars = 2 * kAStages + 2 * kWSlots;
+  const uint32_t accum_bar = bar_base + 8u * kNumBars;
+  const uint32_t phase_bar = bar_base + 8u * (kNumBars + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (kNumBars + 2);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (kNumBars + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / p.DX, x0 = blockIdx.x % p.DX;
+  const int nphases = p.nconv + 1;  // phase 0 = LFF, phase j >= 1 = dense conv (nconv - j)
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < nphases; ++i) {
+      ptx::prefetch_tmap(&maps.a[i]);
+      ptx::prefetch_tmap(&maps.b[i]);
+    }
+    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::mbar_init(phase_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // maps.a[0] / maps.b[0]: LFF (g_lff, packed LFF dgrad weights); maps.a[1 + i] / maps.b[1 + i]: dense conv i
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int ph = 0; ph < nphases; ++ph) {
+      const bool lff = ph == 0;
+      const int ci = lff ? 0 : p.nconv - ph;  // dense conv index
+      const int mi = lff ? 0 : 1 + ci;
+      const int ntaps = lff ? 1 : 27;
+      const int kch = lff ? p.kch_lff : 1;
+      const int total_w = kch * ntaps;
+      const uint32_t w_bytes = lff ? (uint32_t)p.ctot_pad * 128u : (uint32_t)p.cin[ci] * 64u;
+      int wi = 0;
+      auto issue_w = [&]() {
+        const int ch = wi / ntaps, tap = wi - ch * ntaps;
+        ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(w_full(wsl), w_bytes);
+          ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes, &maps.b[mi], w_full(wsl), ch * 64, 0, tap);
+        }
+        __syncwarp();
+        if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        ++wi;
+      };
+      while (wi < total_w && wi < kWSlots) issue_w();
+      ptx::mbar_wait(phase_bar, (uint32_t)(ph & 1));
+      fence_proxy_async_global();
+      for (int ch = 0; ch < kch; ++ch) {
+        ptx::mbar_wait(a_empty(ab), aph ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t d = smem_base + ab * p.a_stage_bytes;
+          if (lff) {
+            ptx::mbar_expect_tx(a_full(ab), (uint32_t)p.a_box_bytes_lff);
+            ptx::tma_load_5d(d, &maps.a[0], a_full(ab), ch * 64, 0, 0, x0, n);
+          } else {
+            ptx::mbar_expect_tx(a_full(ab), (uint32_t)p.a_box_bytes_conv);
+            ptx::tma_load_5d(d, &maps.a[mi], a_full(ab), 0, -1, -1, x0 - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++ab == kAStages) { ab = 0; aph ^= 1u; }
+        const int upto = (ch + 1) * ntaps + kWSlots;
+        while (wi < total_w && wi < upto) issue_w();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint64_t desc128 = ptx::make_smem_desc_sw128(0, 16, 1024);
+    // SWIZZLE_64B operand rows (K = gc = 32 channels = 64 B): layout type 4, SBO = 8 rows x 64 B (scripts/micro/sw64.cu)
+    const uint64_t desc64 = ((uint64_t)1 << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+    int ab = 0, wsl = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int ph = 0; ph < nphases; ++ph) {
+      const bool lff = ph == 0;
+      const int ci = lff ? 0 : p.nconv - ph;
+      const int ntaps = lff ? 1 : 27;
+      const int kch = lff ? p.kch_lff : 1;
+      const int n_umma = lff ? p.ctot_pad : p.cin[ci];
+      const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)n_umma, 0u, 0u);
+      const uint64_t desc_hi = lff ? desc128 : desc64;
+      const uint32_t row_bytes = lff ? 128u : 64u;
+      for (int ch = 0; ch < kch; ++ch) {
+        const int nk = lff ? ((ch == kch - 1) ? p.last_k16_lff : 4) : 2;
+        ptx::mbar_wait(a_full(ab), aph);
+        const uint32_t a_addr = smem_base + ab * p.a_stage_bytes;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          ptx::mbar_wait(w_full(wsl), wph);
+          ptx::tc_fence_after();
+          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes) >> 4) & 0x3fffu);
+          // the LFF overwrites the accumulators, every dense conv adds to them
+          const uint32_t acc0 = (!lff || ch > 0) ? 1u : 0u;
+          const int ti = tap / 9, tj = (tap / 3) % 3, tl = tap % 3;
+          const int roff = lff ? 0 : ti * p.slab_p + tj * p.pz + tl;
+          for (int m = 0; m < p.t_m; ++m) {
+            const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * row_bytes;
+            const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.ctot_pad);
+            if (ptx::elect_one()) {
+              ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
+              if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              if (nk > 2) ptx::mma_f16_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              if (nk > 3) ptx::mma_f16_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+          __syncwarp();
+          if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        }
+        if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
+        __syncwarp();
+        if (++ab == kAStages) { ab = 0; aph ^= 1u; }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(accum_bar);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int sub = warp & 3;
+    const int et = threadIdx.x - 64;
+    // ---- phase -1: g_lff = alpha * dy (bf16) for this CTA's rows; only this CTA reads them back (1x1x1 conv)
+    {
+      const int c8 = p.F / 8;
+      const long long v0 = (long long)x0 * p.slab;
+      for (int i = et; i < p.slab * c8; i += 128) {
+        const int r = i / c8, q = i - r * c8;
+        const float* src = (const float*)dy.ptr + dy.off(n, q * 8, v0 + r);
+        const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(p.alpha * a.x, p.alpha * a.y);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(p.alpha * a.z, p.alpha * a.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(p.alpha * b.x, p.alpha * b.y);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(p.alpha * b.z, p.alpha * b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>((__nv_bfloat16*)g_lff.ptr + g_lff.off(n, q * 8, v0 + r)) = o;
+      }
+      __threadfence();
+      fence_proxy_async_global();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) ptx::mbar_arrive(phase_bar);
+    }
+    for (int ph = 0; ph < nphases; ++ph) {
+      ptx::mbar_wait(accum_bar, (uint32_t)(ph & 1));
+      ptx::tc_fence_after();
+      const bool last = ph == nphases - 1;
+      // channels [c_hi - gc, c_hi) of the accumulated gradient are final now: the output of dense conv j
+      const int j = p.nconv - 1 - ph;
+      const int c_hi = p.F + (j + 1) * p.gc;
+      for (int m = 0; m < p.t_m; ++m) {
+        const int r = m * 128 + sub * 32 + lane;
+        const int y = r / p.pz, z = r - y * p.pz;
+        const bool row_ok = y < p.DY && z < p.DZ;
+        const long long v = (long long)x0 * p.slab + (long long)y * p.DZ + z;
+        const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.ctot_pad);
+        if (!last) {
+          const __nv_bfloat16* mk = (const __nv_bfloat16*)buf.ptr + buf.off(n, c_hi - p.gc, row_ok ? v : 0);
+          __nv_bfloat16* dst = (__nv_bfloat16*)gbuf.ptr + gbuf.off(n, j * p.gc, row_ok ? v : 0);
+          for (int c0 = 0; c0 < p.gc; c0 += 16) {
+            uint32_t rr[16];
+            ptx::tmem_ld16(t_row + (uint32_t)(c_hi - p.gc + c0), rr);
+            uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+            if (row_ok) {
+              m0 = reinterpret_cast<const uint4*>(mk + c0)[0];
+              m1 = reinterpret_cast<const uint4*>(mk + c0)[1];
+            }
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+              uint32_t pk[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mw[q]));
+                float g0 = __uint_as_float(rr[2 * q]), g1 = __uint_as_float(rr[2 * q + 1]);
+                g0 = a.x > 0.f ? g0 : p.slope * g0;
+                g1 = a.y > 0.f ? g1 : p.slope * g1;
+                __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              reinterpret_cast<uint4*>(dst + c0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(dst + c0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        } else {
+          // dx = dL/d(concat)[:, 0:F) + beta1 * dy   (the block's skip connection)
+          const float* res = (const float*)dy.ptr + dy.off(n, 0, row_ok ? v : 0);
+          float* dst = (float*)dx.ptr + dx.off(n, 0, row_ok ? v : 0);
+          for (int c0 = 0; c0 < p.F; c0 += 16) {
+            uint32_t rr[16];
+            ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
+            float4 q4[4];
+            if (row_ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) q4[q] = reinterpret_cast<const float4*>(res + c0)[q];
+            }
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float4 o;
+                o.x = fmaf(p.beta1, q4[q].x, __uint_as_float(rr[4 * q]));
+                o.y = fmaf(p.beta1, q4[q].y, __uint_as_float(rr[4 * q + 1]));
+                o.z = fmaf(p.beta1, q4[q].z, __uint_as_float(rr[4 * q + 2]));
+                o.w = fmaf(p.beta1, q4[q].w, __uint_as_float(rr[4 * q + 3]));
+                reinterpret_cast<float4*>(dst + c0)[q] = o;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      if (!last) {
+        __threadfence();
+        fence_proxy_async_global();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          grid_barrier(p.bar_slot, gridDim.x);
+          ptx::mbar_arrive(phase_bar);
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int make_act_map(const View& src, int channels, int DX, int DY, int DZ, int N, int box_y, int box_x, CUtensorMap* out,
+                 int box_z = 0, int box_c = 64) {
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.ptr = reinterpret_cast<uintptr_t>(src.ptr);
-  k.rank = 5; k.dtype = WS_BF16;
+  k.rank = 5; k.dtype = WS_BF16 | (box_c == 32 ? kMapSwizzle64 : 0u);
   k.dims[0] = (uint64_t)channels; k.dims[1] = (uint64_t)DZ; k.dims[2] = (uint64_t)DY; k.dims[3] = (uint64_t)DX;
   k.dims[4] = (uint64_t)N;
   k.strides[0] = (uint64_t)src.vs * 2;
   k.strides[1] = (uint64_t)src.vs * 2 * DZ;
   k.strides[2] = (uint64_t)src.vs * 2 * DZ * DY;
   k.strides[3] = (uint64_t)src.ns * 2;
-  k.box[0] = 64; k.box[1] = (uint32_t)DZ; k.box[2] = (uint32_t)box_y; k.box[3] = (uint32_t)box_x; k.box[4] = 1;
+  k.box[0] = (uint32_t)box_c; k.box[1] = (uint32_t)(box_z ? box_z : DZ); k.box[2] = (uint32_t)box_y;
+  k.box[3] = (uint32_t)box_x; k.box[4] = 1;
   for (int i = 0; i < 5; ++i) k.estr[i] = 1;
   return get_tensor_map(k, out);
 }
-int make_w_map(const void* packed, int k_pad, int rows, int taps, CUtensorMap* out) {
+int make_w_map(const void* packed, int k_pad, int rows, int taps, CUtensorMap* out, int box_c = 64) {
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.ptr = reinterpret_cast<uintptr_t>(packed);
-  k.rank = 3; k.dtype = WS_BF16;
+  k.rank = 3; k.dtype = WS_BF16 | (box_c == 32 ? kMapSwizzle64 : 0u);
   k.dims[0] = (uint64_t)k_pad; k.dims[1] = (uint64_t)rows; k.dims[2] = (uint64_t)taps;
   k.strides[0] = (uint64_t)k_pad * 2;
   k.strides[1] = (uint64_t)k_pad * 2 * rows;
-  k.box[0] = 64; k.box[1] = (uint32_t)rows; k.box[2] = 1;
+  k.box[0] = (uint32_t)box_c; k.box[1] = (uint32_t)rows; k.box[2] = 1;
   k.estr[0] = k.estr[1] = k.estr[2] = 1;
   return get_tensor_map(k, out);
 }
@@ -446,12 +734,12 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
   const size_t reach = (size_t)(p.t_m * 128 + 2 * p.slab_p + 2 * p.DZ) * 128;
   size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)kWSlots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
   if (smem < (size_t)p.a_stage_bytes + reach + 1024) smem = (size_t)p.a_stage_bytes + reach + 1024;
-  WS_REQUIRE(smem <= 225 * 1024, "rdb_persist: shared memory request %zu too large", smem);
+  WS_REQUIRE(smem <= 224 * 1024, "rdb_persist: shared memory request %zu too large", smem);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute((const void*)rdb_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    225 * 1024);
+                                    224 * 1024);  // + 2 KB static
   });
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   cudaLaunchConfig_t cfg = {};
@@ -465,6 +753,93 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   WS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rdb_fwd_persist_kernel, maps, p, x, buf, out, ep_lff));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+// Backward data-gradient chain.  packed[i], i < nconv: dgrad packing [flipped tap][cin_pad16][gc_pad8]; packed[nconv]:
+// LFF dgrad packing [1][ctot_pad16][F_pad8].  Additional requirements: gc == 32 (one SWIZZLE_64B K chunk per tap) and
+// 2 tiles x ctot_pad16 <= 512 TMEM columns.
+bool rdb_persist_bwd_ok(const ws_rdb_desc* d, const View& dy, const View& buf, const View& g_lff, const View& gbuf,
+                        const View& dx, int sm_count) {
+  static const bool off = env_off("WS_DISABLE_RDB_PERSIST_BWD");
+  if (off || !rdb_persist_ok(d, dy, buf, sm_count)) return false;
+  if (d->gc != 32 || !dx.ptr) return false;
+  const int ctot_pad = (d->f + d->nconv * d->gc + 15) / 16 * 16;
+  const int pz = d->z + 2;
+  const int span = (d->y - 1) * pz + d->z;
+  const int t_m = (span + 127) / 128;
+  if (ctot_pad > 256 || t_m * ctot_pad > 512 || pz > 256) return false;
+  auto bf16_ok = [](const View& v) {
+    return v.dtype == WS_BF16 && v.cs == 1 && !(reinterpret_cast<uintptr_t>(v.ptr) & 15) && (v.vs * 2) % 16 == 0 &&
+           (v.ns * 2) % 16 == 0;
+  };
+  if (!bf16_ok(g_lff) || !bf16_ok(gbuf)) return false;
+  if (dx.dtype != WS_F32 || dx.cs != 1 || (reinterpret_cast<uintptr_t>(dx.ptr) & 15) || (dx.vs * 4) % 16 ||
+      (dx.ns * 4) % 16)
+    return false;
+  return true;
+}
+
+int rdb_persist_backward(const ws_rdb_desc* d, const View& dy, const View& buf, const View& g_lff, const View& gbuf,
+                         const View& dx, void* const* packed, cudaStream_t st) {
+  RdbBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n; p.DX = d->x; p.DY = d->y; p.DZ = d->z;
+  p.F = d->f; p.gc = d->gc; p.nconv = d->nconv; p.ctot = d->f + d->nconv * d->gc;
+  p.ctot_pad = (p.ctot + 15) / 16 * 16;
+  p.pz = d->z + 2;
+  p.slab = d->y * d->z;
+  p.slab_p = (d->y + 2) * p.pz;
+  p.t_m = ((d->y - 1) * p.pz + d->z + 127) / 128;
+  p.slope = d->slope; p.alpha = d->alpha; p.beta1 = d->beta1;
+  p.bar_slot = 1;
+  p.kch_lff = (d->f + 63) / 64;
+  p.last_k16_lff = (d->f - 64 * (p.kch_lff - 1) + 15) / 16;
+  p.a_box_bytes_conv = 3 * p.slab_p * 64;
+  p.a_box_bytes_lff = d->y * p.pz * 128;
+  int a_bytes = p.a_box_bytes_conv > p.a_box_bytes_lff ? p.a_box_bytes_conv : p.a_box_bytes_lff;
+  p.a_stage_bytes = (a_bytes + 1023) / 1024 * 1024;
+  int w_bytes = p.ctot_pad * 128;
+  RdbMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  // LFF: A = g_lff rows at the z pitch of the chain (pad rows zero-filled by TMA), B = [ctot_pad][F_pad8]
+  if (int e = make_act_map(g_lff, d->f, d->x, d->y, d->z, d->n, d->y, 1, &maps.a[0], p.pz)) return e;
+  if (int e = make_w_map(packed[d->nconv], (d->f + 7) / 8 * 8, p.ctot_pad, 1, &maps.b[0])) return e;
+  for (int i = 0; i < d->nconv; ++i) {
+    p.cin[i] = d->f + i * d->gc;
+    View gi = gbuf;
+    gi.ptr = (char*)gbuf.ptr + (size_t)i * d->gc * 2;
+    if (int e = make_act_map(gi, d->gc, d->x, d->y, d->z, d->n, d->y + 2, 3, &maps.a[1 + i], p.pz, 32)) return e;
+    if (int e = make_w_map(packed[i], (d->gc + 7) / 8 * 8, (p.cin[i] + 15) / 16 * 16, 27, &maps.b[1 + i], 32)) return e;
+    if (p.cin[i] * 64 > w_bytes) w_bytes = p.cin[i] * 64;
+  }
+  p.w_slot_bytes = (w_bytes + 1023) / 1024 * 1024;
+  uint32_t cols = 32;
+  while ((int)cols < p.t_m * p.ctot_pad) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t reach = (size_t)(p.t_m * 128 + 2 * p.slab_p + 2 * p.pz + 2) * 128;  // rows x the wider (128 B) row
+  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)kWSlots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
+  if (smem < (size_t)p.a_stage_bytes + reach + 1024) smem = (size_t)p.a_stage_bytes + reach + 1024;
+  WS_REQUIRE(smem <= 225 * 1024, "rdb_persist backward: shared memory request %zu too large", smem);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute((const void*)rdb_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    225 * 1024);
+  });
+  WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(d->n * d->x));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rdb_bwd_persist_kernel, maps, p, dy, buf, g_lff, gbuf, dx));
   WS_POST_LAUNCH(1);
   return 0;
 }

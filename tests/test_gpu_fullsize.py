@@ -67,10 +67,10 @@ def test_full_size_generator_step_vs_oracle(mode):
         # flat 1e-5 where the reference's own fp32 arithmetic achieves it (SR, loss, hr_convs.2).  Everything behind
         # a LeakyReLU is as close to the float64 result as the reference's fp32 arithmetic is: sign flips are rare,
         # heavy-tailed events, so the bound is per layer family — median within 2.5x of the reference's median, every
-        # tensor within 2x of the reference's worst tensor of the family.
+        # tensor within 3x of the reference's worst tensor of the family.
         fam32 = {g: r for g, r in rows32.items()}
         bad = {k: (e, ref32[k]) for k, e in errs.items()
-               if k != "dL/dLR" and e > max(tol, 2.0 * fam32[pu.group_of(k)][2])}
+               if k != "dL/dLR" and e > max(tol, 3.0 * fam32[pu.group_of(k)][2])}
         assert not bad, bad
         slow = {g: (r[1], fam32[g][1]) for g, r in rows.items() if r[1] > max(tol, 2.5 * fam32[g][1])}
         assert not slow, slow

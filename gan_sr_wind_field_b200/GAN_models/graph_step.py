@@ -37,6 +37,8 @@ class StepGraph:
         for s, t in zip(self.static, (LR, HR, Z)):
             s.copy_(t)
         self.graph = torch.cuda.CUDAGraph()
+        self.optimizer = gan.optimizer_G if kind == "G" else gan.optimizer_D
+        self.optimizer.prepare_capture()
         ops.take_keepalive()
         launches0 = ops.launch_count()
         torch.cuda.synchronize()
@@ -44,7 +46,6 @@ class StepGraph:
             gan._train_step_body(kind, *self.static)
         self.keep = ops.take_keepalive()
         self.launches = ops.launch_count() - launches0  # libwindsr kernels one replay launches
-        self.optimizer = gan.optimizer_G if kind == "G" else gan.optimizer_D
         self.optimizer.finish_capture()
         # references to what the captured step publishes (static tensors, refreshed by every replay)
         self.G_losses = dict(gan.train_G_loss_dict) if kind == "G" else None

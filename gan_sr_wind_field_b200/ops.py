@@ -439,7 +439,11 @@ class ConvFn(torch.autograd.Function):
                      oscale=oscale, chan_scale=cfg.get("chan_scale"), slope=cfg.get("slope", 1.0),
                      res1=res, beta1=cfg.get("beta", 1.0) if res is not None else 0.0)
         ctx.shape = shape
-        ctx.cfg = cfg
+        # NOT the caller's `out` tensor: it is this node's own output, and node -> ctx.cfg -> out -> grad_fn -> node is
+        # a reference cycle through C++ that Python's GC cannot see — the node, everything upstream of it and every
+        # parameter's AccumulateGrad node would stay alive forever (which, besides the leak, pins those nodes to the
+        # stream of their first iteration and invalidates a later CUDA-graph capture)
+        ctx.cfg = {k: v for k, v in cfg.items() if k != "out"}
         ctx.has_bias = bias is not None
         ctx.has_res = res is not None
         ctx.x_dtype = x.dtype
@@ -665,6 +669,13 @@ def aux_join(device=None) -> None:
     before it packs a bucket)."""
     for dev, (stream, _) in _AUX.items():
         if device is None or dev == device:
+            if capturing():
+                # a capturing stream may only wait for streams of the SAME capture: the auxiliary stream joins it when
+                # ws_rdb_backward forks weight gradients onto it, which the small-geometry paths never do
+                with torch.cuda.stream(stream):
+                    forked = torch.cuda.is_current_stream_capturing()
+                if not forked:
+                    continue
             torch.cuda.current_stream(dev).wait_stream(stream)
 
 

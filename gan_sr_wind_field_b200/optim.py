@@ -31,6 +31,7 @@ class WindAdam(torch.optim.Adam):
         self._tables = {}              # group index -> (key, table_dev, chunks_dev, ntensors, nchunks, lr_dev)
         self._staging = {}
         self._pending = []             # (device table, host bytes) of tables referenced by a graph under capture
+        self._capture_blobs = {}       # group index -> table buffer pre-allocated for the next capture
 
     # -- state ----------------------------------------------------------------------------------------------
     def _ensure_state(self, p):
@@ -77,9 +78,13 @@ class WindAdam(torch.optim.Adam):
         raw = np.concatenate((tab.view(np.uint8).reshape(-1), chunks.view(np.uint8).reshape(-1)))
         if capturing:
             # Nothing may allocate pinned memory or copy from the host inside a capture.  The captured kernel only
-            # needs the ADDRESS of its table: allocate the device buffer now (graph memory pool) and fill it right
-            # after the capture has ended (finish_capture), before the first replay.
-            blob = torch.empty(raw.size, dtype=torch.uint8, device=dev)
+            # needs the ADDRESS of its table: it goes into a buffer allocated BEFORE the capture (prepare_capture —
+            # memory from the graph's own pool may be shared with tensors that die earlier in the step, whose
+            # kernels would overwrite an out-of-band upload on every replay) and is filled right after the capture
+            # has ended (finish_capture), before the first replay.
+            blob = self._capture_blobs.pop(gi, None)
+            if blob is None or blob.numel() < raw.size or blob.device != dev:
+                raise _lib.WindSRError("WindAdam.step inside a CUDA-graph capture needs prepare_capture() first")
             self._pending.append((blob, raw.copy()))
         else:
             host = self._staging.get(gi)
@@ -96,10 +101,21 @@ class WindAdam(torch.optim.Adam):
             self._tables[gi] = hit
         return hit
 
+    def prepare_capture(self):
+        """Call right before capturing a step into a CUDA graph: pre-allocates (outside the graph's memory pool) the
+        pointer-table buffer each param group's captured kernel will read."""
+        chunk = _lib.load().ws_adam_chunk_elems()
+        for gi, group in enumerate(self.param_groups):
+            params = list(group["params"])  # upper bound: D's parameters are frozen (requires_grad False) between D steps
+            if not params or not params[0].is_cuda:
+                continue
+            nbytes = 48 * len(params) + 8 * sum((p.numel() + chunk - 1) // chunk for p in params)
+            self._capture_blobs[gi] = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+
     def finish_capture(self):
         """Upload the pointer tables of the kernels captured since the last call (see _table)."""
         for blob, raw in self._pending:
-            blob.copy_(torch.from_numpy(raw))
+            blob[:raw.size].copy_(torch.from_numpy(raw))
             self._staging[("captured", len(self._staging))] = blob  # owned for the lifetime of the optimizer
         self._pending = []
 

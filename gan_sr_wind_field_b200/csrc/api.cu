@@ -546,7 +546,13 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   WS_REQUIRE(x && x->ptr && buf && buf->ptr && out && out->ptr && w && packed, "ws_rdb_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const long long v = (long long)d->x * d->y * d->z;
-  if (device_cc_major() == 10 && rdb_persist_ok(d, View(x), View(buf), device_sm_count()) &&
+  // (the coalesced fp32 row epilogue of the persistent kernel walks x / outer / out with one row stride)
+  const bool rows_ok = out->dtype == WS_F32 && out->cstride == 1 && x->vstride == out->vstride &&
+                       x->nstride == out->nstride && !(reinterpret_cast<uintptr_t>(out->ptr) & 15) &&
+                       (!outer || !outer->ptr ||
+                        (outer->dtype == WS_F32 && outer->cstride == 1 && outer->vstride == out->vstride &&
+                         outer->nstride == out->nstride && !(reinterpret_cast<uintptr_t>(outer->ptr) & 15)));
+  if (device_cc_major() == 10 && rows_ok && rdb_persist_ok(d, View(x), View(buf), device_sm_count()) &&
       fwd_path(ConvGeom(r.lff), View(buf), d->math) == WS_PATH_TCGEN05) {
     // the whole block as one persistent cooperative kernel (rdb_persist.cu): z-folded dense-conv weights
     if (d->repack)
@@ -624,7 +630,8 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
   cudaStream_t st = (cudaStream_t)stream;
   const long long v = (long long)d->x * d->y * d->z;
   const bool want_w = dw != nullptr;
-  if (device_cc_major() == 10 && d->nconv > 0 && dx && dx->ptr &&
+  if (device_cc_major() == 10 && d->nconv > 0 && dx && dx->ptr && dx->vstride == dy->vstride &&
+      dx->nstride == dy->nstride &&
       rdb_persist_bwd_ok(d, View(dy), View(buf), View(g_lff), View(gbuf), View(dx), device_sm_count()) &&
       dgrad_path(ConvGeom(r.lff), View(g_lff), d->math) == WS_PATH_TCGEN05) {
     // the whole data-gradient chain as one persistent cooperative kernel (rdb_persist.cu); the weight-gradient GEMMs

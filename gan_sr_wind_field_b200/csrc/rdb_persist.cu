@@ -56,7 +56,14 @@ struct RdbFwdParams {
   float slope;
   uint32_t tmem_cols;
   int bar_slot;
+  long long* dbg;  // optional (WS_RDB_DEBUG_TIMES=1): globaltimer stamps of CTA 0's epilogue at every phase edge
 };
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---- grid-wide barrier ------------------------------------------------------------------------------------------
 // Sense-reversing counter barrier in global memory; reusable across launches without a host reset (the count returns
@@ -88,6 +95,50 @@ __device__ __forceinline__ void grid_barrier(int slot, unsigned int nblocks) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// fp32 row epilogue through shared memory: a warp's 32 accumulator rows x `ncols` columns go TMEM -> registers ->
+// a padded staging tile, then every row leaves as ONE coalesced 16-byte-per-lane access together with its residual
+// rows (the per-thread row walk of epilogue.cuh issues 32 scattered 16-byte accesses per instruction and was
+// latency-bound here: 11 us for the LFF of one block).  y = alpha * (acc + bias) + beta1 * r1 + beta2 * r2.
+constexpr int kStagePitch = 132;  // floats per staged row (128 + 4: conflict-free 16-byte row writes)
+template <typename RowMap>  // staged row (0..31) -> output row (voxel index inside the sample) or -1
+__device__ __forceinline__ void rows_epilogue_f32(uint32_t t_row, int ncols, float* stg, int lane, const float* bias,
+                                                  float alpha, const float* r1, float beta1, const float* r2,
+                                                  float beta2, float* out, long long row_stride, RowMap row_map) {
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    uint32_t rr[16];
+    ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
+    ptx::tmem_ld_wait();
+    float4* d = reinterpret_cast<float4*>(stg + lane * kStagePitch + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      d[q] = make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]), __uint_as_float(rr[4 * q + 2]),
+                         __uint_as_float(rr[4 * q + 3]));
+  }
+  __syncwarp();
+  const int c = lane * 4;
+  if (c < ncols) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b4 = *reinterpret_cast<const float4*>(bias + c);
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const long long orow = row_map(r);
+      if (orow < 0) continue;
+      const float4 a = *reinterpret_cast<const float4*>(stg + r * kStagePitch + c);
+      float4 y = make_float4(alpha * (a.x + b4.x), alpha * (a.y + b4.y), alpha * (a.z + b4.z), alpha * (a.w + b4.w));
+      if (r1) {
+        const float4 x4 = *reinterpret_cast<const float4*>(r1 + orow * row_stride + c);
+        y.x = fmaf(beta1, x4.x, y.x); y.y = fmaf(beta1, x4.y, y.y); y.z = fmaf(beta1, x4.z, y.z); y.w = fmaf(beta1, x4.w, y.w);
+      }
+      if (r2) {
+        const float4 x4 = *reinterpret_cast<const float4*>(r2 + orow * row_stride + c);
+        y.x = fmaf(beta2, x4.x, y.x); y.y = fmaf(beta2, x4.y, y.y); y.z = fmaf(beta2, x4.z, y.z); y.w = fmaf(beta2, x4.w, y.w);
+      }
+      *reinterpret_cast<float4*>(out + orow * row_stride + c) = y;
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -229,38 +280,62 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
     // ===== epilogue warps =====
     const int sub = warp & 3;            // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 64;     // 0..127
+    int stamp_i = 0;
+    auto stamp = [&]() {
+      if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
+      ++stamp_i;
+    };
     auto publish = [&]() {
       // make this CTA's global writes visible grid-wide, wait for everybody else's, release the producer
       __threadfence();
       fence_proxy_async_global();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      stamp();  // epilogue stores done
       if (et == 0) {
         grid_barrier(p.bar_slot, gridDim.x);
         ptx::mbar_arrive(phase_bar);
       }
+      stamp();  // barrier passed
     };
-    // ---- phase -1: x (fp32) -> buf[:, 0:F) (bf16), this CTA's slab
+    stamp();  // kernel start (after the prologue)
+    // ---- phase -1: x (fp32) -> buf[:, 0:F) (bf16), this CTA's slab (4 independent 32-byte reads in flight per thread)
     {
       const int c8 = p.F / 8;
       const long long v0 = (long long)x0 * p.slab;
-      for (int i = et; i < p.slab * c8; i += 128) {
-        const int r = i / c8, q = i - r * c8;
-        const float* src = (const float*)x.ptr + x.off(n, q * 8, v0 + r);
-        const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>((__nv_bfloat16*)buf.ptr + buf.off(n, q * 8, v0 + r)) = o;
+      const int total = p.slab * c8;
+      for (int i0 = et; i0 < total; i0 += 4 * 128) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 128;
+          if (i < total) {
+            const int r = i / c8, q = i - r * c8;
+            const float* src = (const float*)x.ptr + x.off(n, q * 8, v0 + r);
+            a[u] = reinterpret_cast<const float4*>(src)[0];
+            b[u] = reinterpret_cast<const float4*>(src)[1];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 128;
+          if (i < total) {
+            const int r = i / c8, q = i - r * c8;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a[u].x, a[u].y), h1 = __floats2bfloat162_rn(a[u].z, a[u].w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(b[u].x, b[u].y), h3 = __floats2bfloat162_rn(b[u].z, b[u].w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)buf.ptr + buf.off(n, q * 8, v0 + r)) = o;
+          }
+        }
       }
       publish();
     }
-    const EpiVec ev = make_epi_vec(out, ep_lff);
     for (int ph = 0; ph < nphases; ++ph) {
       const bool lff = ph == p.nconv;
       ptx::mbar_wait(accum_bar, (uint32_t)(ph & 1));
       ptx::tc_fence_after();
+      stamp();  // MMAs of this phase complete
       if (!lff) {
         const int c_out0 = p.F + ph * p.gc;  // first channel of this conv's slice of the concat buffer
         const int gc = p.gc;
@@ -327,25 +402,23 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
         ptx::tc_fence_before();
         publish();
       } else {
-        // LFF: out = alpha * (acc + bias) + beta1 * x + beta2 * outer   (fp32, epilogue.cuh)
+        // LFF: out = alpha * (acc + bias) + beta1 * x + beta2 * outer (fp32): rows are contiguous voxels of this
+        // sample's slab, staged through the (now idle) activation buffers
+        float* stg = reinterpret_cast<float*>(smem) + sub * 32 * kStagePitch;
+        const long long row_base = (long long)x0 * p.slab;
+        const float* r1 = ep_lff.res1.ptr ? (const float*)ep_lff.res1.ptr + ep_lff.res1.off(n, 0, 0) : nullptr;
+        const float* r2 = ep_lff.res2.ptr ? (const float*)ep_lff.res2.ptr + ep_lff.res2.off(n, 0, 0) : nullptr;
+        float* o = (float*)out.ptr + out.off(n, 0, 0);
         for (int m = 0; m < p.t_m; ++m) {
-          const int r = m * 128 + sub * 32 + lane;
-          const bool row_ok = r < p.slab;
-          const long long v = (long long)x0 * p.slab + r;
+          const int r0 = m * 128 + sub * 32;
+          const int ok = p.slab - r0;  // valid rows of this warp's 32
+          if (ok <= 0) break;
           const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
-          float cur[16], nxt[16];
-          prefetch_res16(ep_lff, ev, n, v, 0, p.F, p.n_lff, row_ok, cur);
-          for (int c0 = 0; c0 < p.n_lff; c0 += 16) {
-            uint32_t rr[16];
-            ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
-            prefetch_res16(ep_lff, ev, n, v, c0 + 16, p.F, p.n_lff, row_ok, nxt);
-            ptx::tmem_ld_wait();
-            epilogue16_simple(ep_lff, ev, out, n, v, c0, p.F, row_ok, rr, cur);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
-          }
+          rows_epilogue_f32(t_row, p.n_lff, stg, lane, ep_lff.bias, ep_lff.alpha, r1, ep_lff.beta1, r2, ep_lff.beta2, o,
+                            out.vs, [&](int r) -> long long { return r < ok ? row_base + r0 + r : -1; });
         }
         ptx::tc_fence_before();
+        stamp();  // LFF epilogue done
       }
     }
   }
@@ -537,18 +610,34 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
     {
       const int c8 = p.F / 8;
       const long long v0 = (long long)x0 * p.slab;
-      for (int i = et; i < p.slab * c8; i += 128) {
-        const int r = i / c8, q = i - r * c8;
-        const float* src = (const float*)dy.ptr + dy.off(n, q * 8, v0 + r);
-        const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(p.alpha * a.x, p.alpha * a.y);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(p.alpha * a.z, p.alpha * a.w);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(p.alpha * b.x, p.alpha * b.y);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(p.alpha * b.z, p.alpha * b.w);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>((__nv_bfloat16*)g_lff.ptr + g_lff.off(n, q * 8, v0 + r)) = o;
+      const int total = p.slab * c8;
+      for (int i0 = et; i0 < total; i0 += 4 * 128) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 128;
+          if (i < total) {
+            const int r = i / c8, q = i - r * c8;
+            const float* src = (const float*)dy.ptr + dy.off(n, q * 8, v0 + r);
+            a[u] = reinterpret_cast<const float4*>(src)[0];
+            b[u] = reinterpret_cast<const float4*>(src)[1];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 128;
+          if (i < total) {
+            const int r = i / c8, q = i - r * c8;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(p.alpha * a[u].x, p.alpha * a[u].y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(p.alpha * a[u].z, p.alpha * a[u].w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(p.alpha * b[u].x, p.alpha * b[u].y);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(p.alpha * b[u].z, p.alpha * b[u].w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)g_lff.ptr + g_lff.off(n, q * 8, v0 + r)) = o;
+          }
+        }
       }
       __threadfence();
       fence_proxy_async_global();
@@ -597,30 +686,16 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
             }
           }
         } else {
-          // dx = dL/d(concat)[:, 0:F) + beta1 * dy   (the block's skip connection)
-          const float* res = (const float*)dy.ptr + dy.off(n, 0, row_ok ? v : 0);
-          float* dst = (float*)dx.ptr + dx.off(n, 0, row_ok ? v : 0);
-          for (int c0 = 0; c0 < p.F; c0 += 16) {
-            uint32_t rr[16];
-            ptx::tmem_ld16(t_row + (uint32_t)c0, rr);
-            float4 q4[4];
-            if (row_ok) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) q4[q] = reinterpret_cast<const float4*>(res + c0)[q];
-            }
-            ptx::tmem_ld_wait();
-            if (row_ok) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float4 o;
-                o.x = fmaf(p.beta1, q4[q].x, __uint_as_float(rr[4 * q]));
-                o.y = fmaf(p.beta1, q4[q].y, __uint_as_float(rr[4 * q + 1]));
-                o.z = fmaf(p.beta1, q4[q].z, __uint_as_float(rr[4 * q + 2]));
-                o.w = fmaf(p.beta1, q4[q].w, __uint_as_float(rr[4 * q + 3]));
-                reinterpret_cast<float4*>(dst + c0)[q] = o;
-              }
-            }
-          }
+          // dx = dL/d(concat)[:, 0:F) + beta1 * dy (the block's skip connection): staged through the idle operand
+          // buffers so that every voxel row is one coalesced access (rows_epilogue_f32)
+          float* stg = reinterpret_cast<float*>(smem) + sub * 32 * kStagePitch;
+          const int r0 = m * 128 + sub * 32;
+          const long long row_base = (long long)x0 * p.slab;
+          rows_epilogue_f32(t_row, p.F, stg, lane, nullptr, 1.f, (const float*)dy.ptr + dy.off(n, 0, 0), p.beta1, nullptr,
+                            0.f, (float*)dx.ptr + dx.off(n, 0, 0), dx.vs, [&](int r) -> long long {
+                              const int rr = r0 + r, yy = rr / p.pz, zz = rr - yy * p.pz;
+                              return (yy < p.DY && zz < p.DZ) ? row_base + (long long)yy * p.DZ + zz : -1;
+                            });
         }
       }
       ptx::tc_fence_before();
@@ -711,6 +786,23 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
   p.n_lff = d->f;
   p.slope = d->slope;
   p.bar_slot = 0;
+  static long long* dbg_buf = nullptr;
+  static int dbg_calls = 0;
+  static const bool dbg_on = env_off("WS_RDB_DEBUG_TIMES");  // (env_off: "set and not 0")
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    static const int dbg_at = atoi(getenv("WS_RDB_DEBUG_TIMES")) > 1 ? atoi(getenv("WS_RDB_DEBUG_TIMES")) : 40;
+    if (++dbg_calls == dbg_at) {  // a warm call
+      cudaStreamSynchronize(st);
+      long long h[64];
+      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const int nst = 1 + 2 + 3 * d->nconv + 2;
+      fprintf(stderr, "[rdb_fwd_persist] phase-edge stamps of CTA 0 (us since kernel start):");
+      for (int i = 1; i < nst && i < 64; ++i) fprintf(stderr, " %.1f", (h[i] - h[0]) * 1e-3);
+      fprintf(stderr, "\n  order: cast-done, barrier | per conv: mma-done, epilogue-done, barrier | lff mma-done, epilogue-done\n");
+    }
+    p.dbg = dbg_buf;
+  }
   p.a_box_bytes_conv = 3 * p.slab_p * 128;
   p.a_box_bytes_lff = p.slab * 128;
   p.a_stage_bytes = (p.a_box_bytes_conv + 1023) / 1024 * 1024;

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libwindsr.so")
 WS_F32, WS_BF16 = 0, 1
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 PATH_NONE, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_TC_FWD, PACK_TC_DGRAD = 0, 1, 2, 3
+PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_TC_FWD, PACK_TC_DGRAD, PACK_TC_FWD_TF32, PACK_TC_DGRAD_TF32 = 0, 1, 2, 3, 4, 5
 WL_SLOTS, WL_RESULT_FLOATS, WLB_SLOTS = 16, 64, 12
 
 

@@ -44,11 +44,12 @@ bool tc_view_ok(const View&, int);
 int tc_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t,
                    const TcOverride* ov = nullptr);
 int tc2_conv_launch(const ConvGeom&, int, const View&, const void*, const View&, const Epi&, cudaStream_t,
-                    const TcOverride* ov = nullptr);
+                    const TcOverride* ov = nullptr, int dry = 0);
 bool tc2_enabled();
 int tc_conv_wgrad(const ConvGeom&, const View&, const View&, float*, int, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(const ConvGeom&);
-int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t, const int*);
+int pack_tc_batch_launch(int, const float* const*, const ConvGeom*, int, void* const*, cudaStream_t, const int*,
+                         int tf32 = 0);
 int im2col_small_launch(const View&, const View&, const ConvGeom&, int, cudaStream_t);
 int xfold_sum_lrelu_launch(const View&, const View&, float, int, int, int, int, int, int, int, cudaStream_t);
 int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
@@ -129,7 +130,26 @@ static bool tc_disabled(const char* which) {
 }
 static bool is_strided(const ConvGeom& g) { return g.sx != 1 || g.sy != 1 || g.sz != 1; }
 
+// TF32 mode (tcgen05 kind::tf32 on fp32 channels-last activations): the halo-tile kernel for stride-1 forward /
+// data-gradient convs with at least 8 reduction channels, the MN-major GEMM for every weight gradient; the strided
+// discriminator convs and the narrow first layers stay on the fp32 CUDA-core family (more accurate, and a few
+// percent of the FLOPs).
+static bool tf32_view_ok(const View& v, int channels) {
+  if (v.dtype != WS_F32 || v.cs != 1) return false;
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0) return false;
+  if ((v.vs * 4) % 16 != 0 || (v.ns * 4) % 16 != 0) return false;
+  return channels >= 8;
+}
+static int tf32_conv_path(const ConvGeom& g, int mode, const View& src, const char* which) {
+  if (tc_disabled(which) || device_cc_major() != 10 || is_strided(g) || !tc2_enabled()) return WS_PATH_SIMT;
+  if (!tf32_view_ok(src, mode == 0 ? g.cin : g.cout)) return WS_PATH_SIMT;
+  Epi none(nullptr, mode == 0 ? g.cout : g.cin);
+  return tc2_conv_launch(g, mode, src, nullptr, View(), none, nullptr, nullptr, 1) == 0 ? WS_PATH_TCGEN05
+                                                                                       : WS_PATH_SIMT;
+}
+
 static int fwd_path(const ConvGeom& g, const View& in, int math) {
+  if (math == WS_MATH_TF32) return tf32_conv_path(g, 0, in, "fwd");
   if (math != WS_MATH_BF16) return WS_PATH_SIMT;
   if (tc_disabled("fwd") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
   if (device_cc_major() != 10) return WS_PATH_SIMT;
@@ -138,6 +158,7 @@ static int fwd_path(const ConvGeom& g, const View& in, int math) {
   return WS_PATH_TCGEN05;
 }
 static int dgrad_path(const ConvGeom& g, const View& dy, int math) {
+  if (math == WS_MATH_TF32) return tf32_conv_path(g, 1, dy, "dgrad");
   if (math != WS_MATH_BF16) return WS_PATH_SIMT;
   if (tc_disabled("dgrad") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
   if (device_cc_major() != 10) return WS_PATH_SIMT;
@@ -146,6 +167,13 @@ static int dgrad_path(const ConvGeom& g, const View& dy, int math) {
   return WS_PATH_TCGEN05;
 }
 static int wgrad_path(const ConvGeom& g, const View& in, const View& dy, int math) {
+  if (math == WS_MATH_TF32) {
+    if (tc_disabled("wgrad") || (is_strided(g) && tc_disabled("strided")) || device_cc_major() != 10)
+      return WS_PATH_SIMT;
+    if (!tf32_view_ok(in, g.cin) || !tf32_view_ok(dy, g.cout) || g.cin < 16 || g.cout < 16) return WS_PATH_SIMT;
+    if (g.cin > 256 && g.cout > 256) return WS_PATH_SIMT;
+    return WS_PATH_TCGEN05;
+  }
   if (math != WS_MATH_BF16) return WS_PATH_SIMT;
   if (tc_disabled("wgrad") || (is_strided(g) && tc_disabled("strided"))) return WS_PATH_SIMT;
   if (device_cc_major() != 10) return WS_PATH_SIMT;
@@ -220,6 +248,10 @@ size_t ws_packed_weight_bytes(const ws_conv_shape* s, int kind) {
       return taps * (size_t)((s->cout + 15) / 16 * 16) * (size_t)((s->cin + 7) / 8 * 8) * 2;
     case WS_PACK_TC_DGRAD:
       return taps * (size_t)((s->cin + 15) / 16 * 16) * (size_t)((s->cout + 7) / 8 * 8) * 2;
+    case WS_PACK_TC_FWD_TF32:
+      return taps * (size_t)((s->cout + 15) / 16 * 16) * (size_t)((s->cin + 3) / 4 * 4) * 4;
+    case WS_PACK_TC_DGRAD_TF32:
+      return taps * (size_t)((s->cin + 15) / 16 * 16) * (size_t)((s->cout + 3) / 4 * 4) * 4;
   }
   return 0;
 }
@@ -227,7 +259,9 @@ size_t ws_packed_weight_bytes(const ws_conv_shape* s, int kind) {
 int ws_pack_weights(const float* w, const ws_conv_shape* s, int kind, void* packed, void* stream) {
   if (int e = validate_shape(s)) return e;
   WS_REQUIRE(w && packed, "ws_pack_weights: null pointer");
-  WS_REQUIRE(kind >= WS_PACK_SIMT_FWD && kind <= WS_PACK_TC_DGRAD, "ws_pack_weights: bad kind %d", kind);
+  WS_REQUIRE(kind >= WS_PACK_SIMT_FWD && kind <= WS_PACK_TC_DGRAD_TF32, "ws_pack_weights: bad kind %d", kind);
+  WS_REQUIRE(kind < WS_PACK_TC_FWD_TF32 || (s->sx == 1 && s->sy == 1 && s->sz == 1),
+             "ws_pack_weights: the TF32 tensor-core packings are stride-1 only");
   return pack_weights_launch(w, ConvGeom(*s), kind, packed, (cudaStream_t)stream);
 }
 
@@ -258,6 +292,7 @@ int ws_conv3d_fwd(const ws_conv_shape* s, const ws_tensor* in, const void* packe
       int r = tc2_conv_launch(g, 0, vin, packed_w, vout, e, (cudaStream_t)stream);
       if (r >= 0) return r;  // -1: geometry not covered by the halo-tile kernel
     }
+    WS_REQUIRE(math == WS_MATH_BF16, "ws_conv3d_fwd: geometry not covered by the TF32 tensor-core kernel");
     return tc_conv_launch(g, 0, vin, packed_w, vout, e, (cudaStream_t)stream);
   }
   return simt_conv_fwd(g, vin, (const float*)packed_w, vout, e, (cudaStream_t)stream);
@@ -276,6 +311,7 @@ int ws_conv3d_dgrad(const ws_conv_shape* s, const ws_tensor* dy, const void* pac
       int r = tc2_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
       if (r >= 0) return r;
     }
+    WS_REQUIRE(math == WS_MATH_BF16, "ws_conv3d_dgrad: geometry not covered by the TF32 tensor-core kernel");
     return tc_conv_launch(g, 1, vdy, packed_w, vdx, e, (cudaStream_t)stream);
   }
   return simt_conv_dgrad(g, vdy, (const float*)packed_w, vdx, e, (cudaStream_t)stream);
@@ -481,7 +517,7 @@ int rdb_repack(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* lff_act,
       return e;
     }
   }
-  return pack_tc_batch_launch(nb, bw, bg, dgrad, bp, st, bf);
+  return pack_tc_batch_launch(nb, bw, bg, dgrad, bp, st, bf, d->math == WS_MATH_TF32 ? 1 : 0);
 }
 // x-folded forward of the dense convs: the kx taps go side by side on the UMMA N dimension (N = kx*gc = 96 instead of
 // 32 — an MMA costs the same 72 cycles either way), the conv runs as a (1,k,k) conv into an fp32 scratch U and a small
@@ -502,6 +538,7 @@ bool rdb_fold_ok(const ws_rdb_desc* d, const ws_tensor* buf) {
   return true;
 }
 bool rdb_merged_wgrad_ok(const ws_rdb_desc* d, const ws_tensor* buf, const ws_tensor* gbuf) {
+  if (d->math != WS_MATH_BF16) return false;  // the merged GEMM is a bf16 kernel
   if (d->nconv < 2 || d->nconv * d->gc > 256 || d->gc % 16 != 0 || getenv("WS_DISABLE_RDB_MERGED_WGRAD")) return false;
   ws_conv_shape s = rdb_merged_shape(d);
   return wgrad_path(ConvGeom(s), View(buf), View(gbuf), d->math) == WS_PATH_TCGEN05;
@@ -534,6 +571,8 @@ extern "C" size_t ws_rdb_packed_bytes(const ws_rdb_desc* d, int i, int dgrad) {
   const ws_conv_shape* s = i < d->nconv ? &r.dense[i] : &r.lff;
   size_t a = ws_packed_weight_bytes(s, dgrad ? WS_PACK_SIMT_DGRAD : WS_PACK_SIMT_FWD);
   size_t b = ws_packed_weight_bytes(s, dgrad ? WS_PACK_TC_DGRAD : WS_PACK_TC_FWD);
+  size_t c = ws_packed_weight_bytes(s, dgrad ? WS_PACK_TC_DGRAD_TF32 : WS_PACK_TC_FWD_TF32);
+  if (c > b) b = c;
   return a > b ? a : b;
 }
 

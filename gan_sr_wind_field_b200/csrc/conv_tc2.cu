@@ -50,7 +50,8 @@ struct Tc2Params {
   int box_y, box_z;  // TMA box extents in y and z (by, DZ, plus the ky-1 / kz-1 halo in volume mode)
   int row_bytes;     // bytes of one operand row: 128 (SWIZZLE_128B, 64 channels per chunk) or 64 (SWIZZLE_64B, 32 channels:
                      // K <= 32 layers — the dense-conv data-gradients — issue 2 K-steps per tap instead of 4 half-empty ones)
-  int kelems;        // channels per K chunk = row_bytes / 2
+  int kelems;        // channels per K chunk = row_bytes / element size
+  int tf32;          // 1: fp32 activations and weights, tcgen05 kind::tf32 (K = 8 per instruction instead of 16)
   int tap_base;      // first tap of the packed weights this launch uses
   int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
@@ -173,7 +174,8 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1 && leader) {
     // ===== MMA issuer (pair mode: the leader CTA only) =====
-    const uint32_t idesc = ptx::make_idesc(1u, kPair ? 256u : 128u, (uint32_t)p.n_umma, 0u, 0u);
+    const uint32_t idesc = ptx::make_idesc(p.tf32 ? 2u : 1u, kPair ? 256u : 128u, (uint32_t)p.n_umma, 0u, 0u);
+    const int k_per_row = p.row_bytes / 32;  // K steps per operand row: one instruction consumes 32 bytes of K
     // everything but the start address: SWIZZLE_128B (SBO = 8 rows x 128 B) or SWIZZLE_64B (layout type 4, SBO = 512;
     // scripts/micro/sw64.cu)
     const uint64_t desc_hi = p.row_bytes == 128
@@ -186,7 +188,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int iters = (p.vol ? 1 : nyz) * p.kchunks;
     for (int it = 0; it < iters; ++it) {
       const int ch = it % p.kchunks;
-      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : p.kelems / 16;
+      const int nk = (ch == p.kchunks - 1) ? p.last_k16 : k_per_row;
       ptx::mbar_wait(a_full(ab), aph);
       const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
       for (int tt = 0; tt < ntaps; ++tt) {
@@ -209,7 +211,19 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
           if (ptx::elect_one()) {
             // K advance inside the 128-byte swizzle row: +32 B = +2 in the (addr >> 4) field
-            if (kPair) {
+            if (p.tf32) {
+              if (kPair) {
+                ptx::mma_tf32_ss2(d_tmem, adesc, bdesc, idesc, acc0);
+                if (nk > 1) ptx::mma_tf32_ss2(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                if (nk > 2) ptx::mma_tf32_ss2(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                if (nk > 3) ptx::mma_tf32_ss2(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              } else {
+                ptx::mma_tf32_ss(d_tmem, adesc, bdesc, idesc, acc0);
+                if (nk > 1) ptx::mma_tf32_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                if (nk > 2) ptx::mma_tf32_ss(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                if (nk > 3) ptx::mma_tf32_ss(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              }
+            } else if (kPair) {
               ptx::mma_f16_ss2(d_tmem, adesc, bdesc, idesc, acc0);
               if (nk > 1) ptx::mma_f16_ss2(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
               if (nk > 2) ptx::mma_f16_ss2(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
@@ -463,9 +477,13 @@ bool tc2_enabled() {
 }
 
 // mode 0: forward; mode 1: stride-1 dgrad. Returns -1 when this geometry is not covered (caller uses v1).
+// src.dtype == WS_F32 selects the TF32 flavour (fp32 tensor maps, weights packed as fp32, kind::tf32).
+// dry != 0: only decide whether this geometry is covered (0) or not (-1); nothing is launched.
 int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* packed_w, const View& dst,
-                    const Epi& ep, cudaStream_t st, const TcOverride* ov) {
+                    const Epi& ep, cudaStream_t st, const TcOverride* ov, int dry) {
   if (!ov && (g.sx != 1 || g.sy != 1 || g.sz != 1)) return -1;
+  const bool tf32 = src.dtype == WS_F32;
+  const int esize = tf32 ? 4 : 2;
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   int SX, SY, SZ;
@@ -488,7 +506,8 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     p.ODY = ov->ODY; p.ODZ = ov->ODZ;
   }
   const int cn_pad = (p.cn + 15) / 16 * 16;
-  const int ck_pad = (p.ck + 7) / 8 * 8;
+  const int ck_pad = tf32 ? (p.ck + 3) / 4 * 4 : (p.ck + 7) / 8 * 8;  // 16-byte rows of the packed weights
+  p.tf32 = tf32 ? 1 : 0;
   const int n_tiles = (cn_pad + 255) / 256;
   p.n_tile = ((cn_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
   p.n_umma = p.n_tile;
@@ -499,11 +518,12 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   if (n_tiles != 1) pair = false;
   // K <= 32 (the gc = 32 data-gradients of the RRDB trunk, D's 32-channel layers): 64-byte operand rows
   static const bool env_no_sw64 = getenv("WS_DISABLE_SW64") != nullptr;
-  const bool sw64 = ck_pad <= 32 && !pair && !env_no_sw64;
+  const bool sw64 = ck_pad <= 32 && !pair && !env_no_sw64 && !tf32;
   p.row_bytes = sw64 ? 64 : 128;
-  p.kelems = p.row_bytes / 2;
+  p.kelems = p.row_bytes / esize;
   p.kchunks = (p.ck + p.kelems - 1) / p.kelems;
-  p.last_k16 = (p.ck - p.kelems * (p.kchunks - 1) + 15) / 16;
+  const int kper = 32 / esize;  // K elements of one instruction: 16 (bf16) or 8 (tf32)
+  p.last_k16 = (p.ck - p.kelems * (p.kchunks - 1) + kper - 1) / kper;
   // volume mode is opt-in (WS_TC2_VOL=1): measured on the RRDB trunk it is parity-clean but not faster (dense
   // conv 54 vs 48 us, dgrad 46 vs 45 us) — those layers are bound by the N=32 MMA floor and by the weight
   // stream, not by the activation re-reads this mode removes.
@@ -552,17 +572,18 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   uint32_t cols = 32;
   while ((int)cols < p.t_m * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
+  if (dry) return 0;
 
   MapKey ka;
   memset(&ka, 0, sizeof(ka));
   ka.ptr = reinterpret_cast<uintptr_t>(src.ptr);
-  ka.rank = 5; ka.dtype = WS_BF16 | (sw64 ? kMapSwizzle64 : 0u);
+  ka.rank = 5; ka.dtype = (tf32 ? WS_F32 : WS_BF16) | (sw64 ? kMapSwizzle64 : 0u);
   ka.dims[0] = (uint64_t)p.ck; ka.dims[1] = (uint64_t)SZ; ka.dims[2] = (uint64_t)SY; ka.dims[3] = (uint64_t)SX;
   ka.dims[4] = (uint64_t)g.n;
-  ka.strides[0] = (uint64_t)src.vs * 2;
-  ka.strides[1] = (uint64_t)src.vs * 2 * SZ;
-  ka.strides[2] = (uint64_t)src.vs * 2 * SZ * SY;
-  ka.strides[3] = (uint64_t)src.ns * 2;
+  ka.strides[0] = (uint64_t)src.vs * esize;
+  ka.strides[1] = (uint64_t)src.vs * esize * SZ;
+  ka.strides[2] = (uint64_t)src.vs * esize * SZ * SY;
+  ka.strides[3] = (uint64_t)src.ns * esize;
   ka.box[0] = (uint32_t)p.kelems; ka.box[1] = (uint32_t)p.box_z; ka.box[2] = (uint32_t)p.box_y; ka.box[3] = (uint32_t)p.a_sub_slabs;
   ka.box[4] = 1;
   for (int i = 0; i < 5; ++i) ka.estr[i] = 1;
@@ -571,10 +592,10 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   MapKey kb;
   memset(&kb, 0, sizeof(kb));
   kb.ptr = reinterpret_cast<uintptr_t>(packed_w);
-  kb.rank = 3; kb.dtype = WS_BF16 | (sw64 ? kMapSwizzle64 : 0u);
+  kb.rank = 3; kb.dtype = (tf32 ? WS_F32 : WS_BF16) | (sw64 ? kMapSwizzle64 : 0u);
   kb.dims[0] = (uint64_t)ck_pad; kb.dims[1] = (uint64_t)cn_pad; kb.dims[2] = (uint64_t)taps_total;
-  kb.strides[0] = (uint64_t)ck_pad * 2;
-  kb.strides[1] = (uint64_t)ck_pad * 2 * cn_pad;
+  kb.strides[0] = (uint64_t)ck_pad * esize;
+  kb.strides[1] = (uint64_t)ck_pad * esize * cn_pad;
   kb.box[0] = (uint32_t)p.kelems; kb.box[1] = (uint32_t)(pair ? p.n_umma / 2 : p.n_umma); kb.box[2] = 1;
   kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
   if (int e = get_tensor_map(kb, &tmB)) return e;

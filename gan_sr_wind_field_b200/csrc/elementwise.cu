@@ -45,7 +45,11 @@ __global__ void pack_simt(const float* __restrict__ w, float* __restrict__ p, in
 // tcgen05 packings, bf16, zero padded.
 // fwd:   p[tap][co_pad][ci_pad]          = w[co][ci][tap]
 // dgrad: p[taps-1-tap][ci_pad16][co_pad8] = w[co][ci][tap]   (taps-1-tap == flip of all three axes)
-__global__ void pack_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout, int cin,
+__device__ __forceinline__ void store_packed(__nv_bfloat16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_packed(float* p, long long i, float v) { p[i] = v; }  // TF32 flavour: fp32 operands
+
+template <typename T>
+__global__ void pack_tc(const float* __restrict__ w, T* __restrict__ p, int cout, int cin,
                         int taps, int rows_pad, int cols_pad, int dgrad) {
   long long total = (long long)taps * rows_pad * cols_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -60,7 +64,7 @@ __global__ void pack_tc(const float* __restrict__ w, __nv_bfloat16* __restrict__
     } else {
       if (row < cin && col < cout) v = w[((long long)col * cin + row) * taps + (taps - 1 - tp)];
     }
-    p[i] = __float2bfloat16_rn(v);
+    store_packed(p, i, v);
   }
 }
 
@@ -72,6 +76,7 @@ struct PackEntry {
   int cout, cin, taps, rows_pad, cols_pad, dgrad;
   int fold;  // > 0: x-fold forward packing — `fold` = kx taps side by side on the rows: p[(ky,kz)][dx*cout+co][ci]
   int fold_z;  // with fold > 0: fold the kz taps instead (persistent RDB kernel): p[(kx,ky)][dz*cout+co][ci]
+  int tf32;    // fp32 output (TF32 mode) instead of bf16
 };
 struct PackTable {
   int n;
@@ -101,7 +106,8 @@ __global__ void pack_tc_multi(const PackTable t) {
     } else {
       if (row < e.cin && col < e.cout) v = w[((long long)col * e.cin + row) * e.taps + (e.taps - 1 - tp)];
     }
-    p[i] = __float2bfloat16_rn(v);
+    if (e.tf32) reinterpret_cast<float*>(e.p)[i] = v;
+    else p[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -726,13 +732,19 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
           out += total;
         }
     return 0;
+  } else if (kind == WS_PACK_TC_FWD_TF32 || kind == WS_PACK_TC_DGRAD_TF32) {
+    int dgrad = kind == WS_PACK_TC_DGRAD_TF32;
+    int rows = dgrad ? (g.cin + 15) / 16 * 16 : (g.cout + 15) / 16 * 16;
+    int cols = dgrad ? (g.cout + 3) / 4 * 4 : (g.cin + 3) / 4 * 4;
+    long long total = (long long)taps * rows * cols;
+    pack_tc<float><<<grid_for(total), kBlock, 0, st>>>(w, (float*)packed, g.cout, g.cin, taps, rows, cols, dgrad);
   } else {
     int dgrad = kind == WS_PACK_TC_DGRAD;
     int rows = dgrad ? (g.cin + 15) / 16 * 16 : (g.cout + 15) / 16 * 16;
     int cols = dgrad ? (g.cout + 7) / 8 * 8 : (g.cin + 7) / 8 * 8;
     long long total = (long long)taps * rows * cols;
-    pack_tc<<<grid_for(total), kBlock, 0, st>>>(w, (__nv_bfloat16*)packed, g.cout, g.cin, taps, rows, cols,
-                                               dgrad);
+    pack_tc<__nv_bfloat16><<<grid_for(total), kBlock, 0, st>>>(w, (__nv_bfloat16*)packed, g.cout, g.cin, taps, rows,
+                                                              cols, dgrad);
   }
   WS_POST_LAUNCH(1);
   return 0;
@@ -740,7 +752,7 @@ int pack_weights_launch(const float* w, const ConvGeom& g, int kind, void* packe
 
 // stride-1 tensor-core packings of up to WS_RDB_MAX_CONVS + 1 convs in one launch
 int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dgrad, void* const* packed,
-                         cudaStream_t st, const int* fold) {
+                         cudaStream_t st, const int* fold, int tf32) {
   if (n <= 0) return 0;
   WS_REQUIRE(n <= WS_RDB_MAX_CONVS + 1, "pack_tc_batch: too many entries");
   PackTable t;
@@ -752,7 +764,9 @@ int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dg
     e.w = w[i]; e.p = (__nv_bfloat16*)packed[i];
     e.cout = g[i].cout; e.cin = g[i].cin; e.taps = g[i].taps(); e.dgrad = dgrad;
     e.rows_pad = dgrad ? (g[i].cin + 15) / 16 * 16 : (g[i].cout + 15) / 16 * 16;
-    e.cols_pad = dgrad ? (g[i].cout + 7) / 8 * 8 : (g[i].cin + 7) / 8 * 8;
+    e.tf32 = tf32 ? 1 : 0;
+    if (tf32) e.cols_pad = dgrad ? (g[i].cout + 3) / 4 * 4 : (g[i].cin + 3) / 4 * 4;
+    else e.cols_pad = dgrad ? (g[i].cout + 7) / 8 * 8 : (g[i].cin + 7) / 8 * 8;
     if (fold && fold[i] == 1 && !dgrad) {
       e.fold = g[i].kx;
       e.taps = g[i].ky * g[i].kz;

@@ -186,6 +186,15 @@ __device__ __forceinline__ void mma_f16_ss2(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ss2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair when the MMAs retire
 __device__ __forceinline__ void mma_commit2(uint32_t bar) {
   asm volatile(

@@ -53,6 +53,7 @@ struct WgParams {
   int m_valid, n_valid;  // valid rows / columns of the accumulator
   int n_umma;
   int shift_on_m;        // 1: the M operand is x (shifted), 0: the N operand is x
+  int tf32;              // 1: fp32 operands, kind::tf32 — 32 channels per 128-byte row, 8 voxel rows per instruction
   int a_slot_bytes, b_slot_bytes, b_slots;
   uint32_t tmem_cols;
   // workspace addressing: wsp[tap * tap_stride + m * m_stride + n * n_stride]
@@ -82,7 +83,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = p.m0 + (int)blockIdx.z * 128;                       // this CTA's 128-row M block
   const int m_valid = min(128, p.m_total - (int)blockIdx.z * 128);
-  const int m_blocks = (m_valid + 63) / 64;
+  const int cblk = p.tf32 ? 32 : 64;  // channels per 128-byte operand row
+  const int m_blocks = (m_valid + cblk - 1) / cblk;
   // Work = (tile range, tap group, tile) items in that order; CTA b owns items [b*per, (b+1)*per): the same load for
   // every CTA however taps and tiles divide (hr_convs.0: 63 groups x 2 splits left 22 of 148 SMs idle), and the CTAs
   // of a wave that share a tile range walk the same tiles at the same time, so a tile is fetched from DRAM once per
@@ -145,7 +147,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(a_full(as), blk_bytes * fix_blocks);
           for (int b = 0; b < fix_blocks; ++b)
-            ptx::tma_load_5d(a_base + as * p.a_slot_bytes + b * blk_bytes, tm_fix, a_full(as), fix_c0 + b * 64, z0,
+            ptx::tma_load_5d(a_base + as * p.a_slot_bytes + b * blk_bytes, tm_fix, a_full(as), fix_c0 + b * cblk, z0,
                              y0, x0, n);
         }
         __syncwarp();
@@ -157,7 +159,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(b_full(bs), blk_bytes * sh_blocks);
             for (int b = 0; b < sh_blocks; ++b)
-              ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * blk_bytes, tm_sh, b_full(bs), sh_c0 + b * 64, cz,
+              ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * blk_bytes, tm_sh, b_full(bs), sh_c0 + b * cblk, cz,
                                cy, cx, n);
           }
           __syncwarp();
@@ -168,11 +170,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   } else if (warp == 1) {
     if (has_work) {
       // ===== MMA issuer =====
-      const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
+      const uint32_t idesc = ptx::make_idesc(p.tf32 ? 2u : 1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
       const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, blk_bytes, 1024);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      const int k16 = p.rows / 16;
+      // one instruction consumes 16 voxel rows of bf16 (2048 B of the MN-major tile) or 8 rows of tf32 (1024 B)
+      const int krows = p.tf32 ? 8 : 16;
+      const int k16 = p.rows / krows;
+      const uint64_t kadv = (uint64_t)(krows * 128 / 16);
       uint32_t acc_tile = 0;
       int seg = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
@@ -202,10 +207,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           const uint64_t bdesc = desc_hi | (uint64_t)((n_addr >> 4) & 0x3fffu);
           const uint32_t d_tmem = tmem_base + (uint32_t)(tp * p.n_umma);
           if (ptx::elect_one()) {
-            // one MMA per 16 voxel rows: +2048 B = +128 in the (addr >> 4) field
-            for (int k = 0; k < k16; ++k)
-              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
-                              (acc_tile | (uint32_t)k) ? 1u : 0u);
+            // one MMA per `krows` voxel rows: the descriptor start advances by krows * 128 B
+            if (p.tf32) {
+              for (int k = 0; k < k16; ++k)
+                ptx::mma_tf32_ss(d_tmem, adesc + kadv * k, bdesc + kadv * k, idesc, (acc_tile | (uint32_t)k) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < k16; ++k)
+                ptx::mma_f16_ss(d_tmem, adesc + kadv * k, bdesc + kadv * k, idesc, (acc_tile | (uint32_t)k) ? 1u : 0u);
+            }
             ptx::mma_commit(b_empty(bs));
           }
           __syncwarp();
@@ -264,40 +273,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   }
 }
 
-void choose_wgrad_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+void choose_wgrad_tile_search(int DX, int DY, int DZ, int sx, int sy, int sz, int max_rows, int& bx, int& by, int& bz) {
   double best = -1.0;
   bx = by = 1; bz = 16;
-  for (int z = 1; z <= 128; ++z) {
+  for (int z = 1; z <= max_rows; ++z) {
     if (z > DZ && z != 16) continue;  // allow a padded z only as the fallback
     if ((z - 1) * sz + 1 > 256) break;
-    for (int y = 1; z * y <= 128; ++y) {
+    for (int y = 1; z * y <= max_rows; ++y) {
       if ((y - 1) * sy + 1 > 256) break;
       if (y > 2 * DY) break;
-      for (int x = 1; z * y * x <= 128; ++x) {
+      for (int x = 1; z * y * x <= max_rows; ++x) {
         if ((x - 1) * sx + 1 > 256) break;
         if (x > 2 * DX) break;
         int rows = z * y * x;
         if (rows % 16) continue;
         long long tiles = (long long)((DX + x - 1) / x) * ((DY + y - 1) / y) * ((DZ + z - 1) / z);
         double eff = (double)DX * DY * DZ / ((double)tiles * rows);
-        double score = eff + 1e-4 * rows / 128.0;
+        double score = eff + 1e-4 * rows / (double)max_rows;
         if (score > best) { best = score; bx = x; by = y; bz = z; }
       }
     }
   }
 }
 
-void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int& bx, int& by, int& bz) {
+// max_rows: voxel rows of one operand tile (128; 64 in TF32 mode, whose 128-byte rows hold half as many channels)
+void choose_wgrad_tile(int DX, int DY, int DZ, int sx, int sy, int sz, int max_rows, int& bx, int& by, int& bz) {
   struct Hit { int bx, by, bz; };
   static std::mutex mu;
-  static std::map<std::array<int, 6>, Hit> memo;  // keyed by the full geometry (no hash collisions)
-  const std::array<int, 6> key = {DX, DY, DZ, sx, sy, sz};
+  static std::map<std::array<int, 7>, Hit> memo;  // keyed by the full geometry (no hash collisions)
+  const std::array<int, 7> key = {DX, DY, DZ, sx, sy, sz, max_rows};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);
     if (it != memo.end()) { bx = it->second.bx; by = it->second.by; bz = it->second.bz; return; }
   }
-  choose_wgrad_tile_search(DX, DY, DZ, sx, sy, sz, bx, by, bz);
+  choose_wgrad_tile_search(DX, DY, DZ, sx, sy, sz, max_rows, bx, by, bz);
   std::lock_guard<std::mutex> lk(mu);
   memo[key] = Hit{bx, by, bz};
 }
@@ -315,7 +325,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.n;
-  choose_wgrad_tile(g.xo, g.yo, g.zo, g.sx, g.sy, g.sz, p.bx, p.by, p.bz);
+  choose_wgrad_tile(g.xo, g.yo, g.zo, g.sx, g.sy, g.sz, x.dtype == WS_F32 ? 64 : 128, p.bx, p.by, p.bz);
   p.rows = p.bx * p.by * p.bz;
   p.tiles_x = (g.xo + p.bx - 1) / p.bx;
   p.tiles_y = (g.yo + p.by - 1) / p.by;
@@ -328,12 +338,15 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   p.n_umma = (n_count + 15) / 16 * 16;
   WS_REQUIRE(p.n_umma <= 256, "wgrad N tile too large (%d)", p.n_umma);
   const int mz = (m_total + 127) / 128;
-  p.n_blocks = (p.n_umma + 63) / 64;
+  const bool tf32 = x.dtype == WS_F32;
+  const int esize = tf32 ? 4 : 2, cblk = 128 / esize;
+  p.tf32 = tf32 ? 1 : 0;
+  p.n_blocks = (p.n_umma + cblk - 1) / cblk;
   p.shift_on_m = swap;
   const int blk = p.rows * 128;
-  // the M operand tile must always present 2 blocks worth of address space (UMMA M = 128 reads 2 blocks)
-  const int fix_alloc = swap ? p.n_blocks : 2;
-  const int sh_alloc = swap ? 2 : p.n_blocks;
+  // the M operand tile must always present 128 channels worth of address space (UMMA M = 128 reads all of its blocks)
+  const int fix_alloc = swap ? p.n_blocks : 128 / cblk;
+  const int sh_alloc = swap ? 128 / cblk : p.n_blocks;
   p.a_slot_bytes = fix_alloc * blk;
   p.b_slot_bytes = sh_alloc * blk;
   int budget = 220 * 1024 - 1024 - 512 - 2 * p.a_slot_bytes;
@@ -428,15 +441,15 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     MapKey k;
     memset(&k, 0, sizeof(k));
     k.ptr = reinterpret_cast<uintptr_t>(v.ptr);
-    k.rank = 5; k.dtype = WS_BF16;
+    k.rank = 5; k.dtype = tf32 ? WS_F32 : WS_BF16;
     k.dims[0] = (uint64_t)channels; k.dims[1] = (uint64_t)Z; k.dims[2] = (uint64_t)Y; k.dims[3] = (uint64_t)X;
     k.dims[4] = (uint64_t)g.n;
-    k.strides[0] = (uint64_t)v.vs * 2;
-    k.strides[1] = (uint64_t)v.vs * 2 * Z;
-    k.strides[2] = (uint64_t)v.vs * 2 * Z * Y;
-    k.strides[3] = (uint64_t)v.ns * 2;
+    k.strides[0] = (uint64_t)v.vs * esize;
+    k.strides[1] = (uint64_t)v.vs * esize * Z;
+    k.strides[2] = (uint64_t)v.vs * esize * Z * Y;
+    k.strides[3] = (uint64_t)v.ns * esize;
     int ssx = strided ? g.sx : 1, ssy = strided ? g.sy : 1, ssz = strided ? g.sz : 1;
-    k.box[0] = 64;
+    k.box[0] = (uint32_t)cblk;
     k.box[1] = (uint32_t)((p.bz - 1) * ssz + 1);
     k.box[2] = (uint32_t)((p.by - 1) * ssy + 1);
     k.box[3] = (uint32_t)((p.bx - 1) * ssx + 1);

@@ -16,21 +16,24 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (MATH_BF16, MATH_FP32, PACK_SIMT_DGRAD, PACK_SIMT_FWD, PACK_TC_DGRAD, PACK_TC_FWD,
-                   PATH_TCGEN05, WsConvShape, WsEpilogue, check, load, null_view, ptr, stream_ptr, view)
+from ._lib import (MATH_BF16, MATH_FP32, MATH_TF32, PACK_SIMT_DGRAD, PACK_SIMT_FWD, PACK_TC_DGRAD,
+                   PACK_TC_DGRAD_TF32, PACK_TC_FWD, PACK_TC_FWD_TF32, PATH_TCGEN05, WsConvShape, WsEpilogue, check, load,
+                   null_view, ptr, stream_ptr, view)
 
 # ------------------------------------------------------------------------------------------------------
 # precision
 # ------------------------------------------------------------------------------------------------------
 _PRECISION = "bf16"
-PRECISIONS = ("fp32", "bf16")
+PRECISIONS = ("fp32", "tf32", "bf16")
 
 
 def set_precision(mode: str) -> None:
-    """'fp32' (CUDA-core FFMA, rel-L2 <= 1e-5 parity mode) or 'bf16' (tcgen05, fp32 accumulate)."""
+    """'fp32' (CUDA-core FFMA, the 1e-5 parity mode), 'tf32' (tcgen05 kind::tf32 on fp32 activations — the arithmetic
+    the reference actually ran with on its A100: torch's default ``cudnn.allow_tf32``) or 'bf16' (tcgen05 kind::f16,
+    bf16 operands); fp32 accumulation everywhere."""
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
-        raise ValueError(f"precision must be 'fp32' or 'bf16', got {mode!r}")
+    if mode not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {mode!r}")
     _PRECISION = mode
 
 
@@ -53,7 +56,13 @@ class precision:
 
 
 def math_mode() -> int:
-    return MATH_BF16 if _PRECISION == "bf16" else MATH_FP32
+    return {"bf16": MATH_BF16, "tf32": MATH_TF32, "fp32": MATH_FP32}[_PRECISION]
+
+
+def _tc_pack_kind(dgrad: bool, math: int) -> int:
+    if math == MATH_TF32:
+        return PACK_TC_DGRAD_TF32 if dgrad else PACK_TC_FWD_TF32
+    return PACK_TC_DGRAD if dgrad else PACK_TC_FWD
 
 
 def act_dtype() -> torch.dtype:
@@ -264,7 +273,7 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights], s
     math = math_mode() if math is None else math
     xv, ov = view(x), view(out)
     path = lib.ws_conv3d_fwd_path(C.byref(shape), C.byref(xv), C.byref(ov), math)
-    kind = PACK_TC_FWD if path == PATH_TCGEN05 else PACK_SIMT_FWD
+    kind = _tc_pack_kind(False, math) if path == PATH_TCGEN05 else PACK_SIMT_FWD
     packed = cache.get(w, shape, kind) if cache is not None else pack_weights(w, shape, kind)
     e = _epilogue(**ep)
     with _timed("fwd", shape):
@@ -281,7 +290,7 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, cache: Optional[PackedWeights]
     math = math_mode() if math is None else math
     dv, xv = view(dy), view(dx)
     path = lib.ws_conv3d_dgrad_path(C.byref(shape), C.byref(dv), C.byref(xv), math)
-    kind = PACK_TC_DGRAD if path == PATH_TCGEN05 else PACK_SIMT_DGRAD
+    kind = _tc_pack_kind(True, math) if path == PATH_TCGEN05 else PACK_SIMT_DGRAD
     if cache is None:
         cache = PackedWeights()
     packed = cache.get(w, shape, kind, pad_cout=pad_cout)
@@ -476,7 +485,7 @@ class ConvFn(torch.autograd.Function):
             g = dy
         dx = dw = db = None
         pad_cout = 0
-        if (cdt == torch.bfloat16 and shape.cout < 16 <= shape.cin and x.dtype == torch.bfloat16
+        if (get_precision() in ("bf16", "tf32") and shape.cout < 16 <= shape.cin and x.dtype == cdt
                 and (shape.sx, shape.sy, shape.sz) == (1, 1, 1)):
             # narrow output (hr_convs.2: 144 -> 3): zero-pad the gradient to 16 channels so dgrad and wgrad run on
             # the tensor-core kernels instead of the CUDA-core family

@@ -45,7 +45,9 @@ enum {
   WS_PACK_SIMT_FWD = 0,   /* fp32 [tap][cin][cout]                 B operand of fwd on CUDA cores        */
   WS_PACK_SIMT_DGRAD = 1, /* fp32 [tap][cout][cin]                 B operand of dgrad on CUDA cores       */
   WS_PACK_TC_FWD = 2,     /* bf16 [tap][cout_pad16][cin_pad8]      K-major B operand for tcgen05 fwd      */
-  WS_PACK_TC_DGRAD = 3    /* bf16 [flipped tap][cin_pad16][cout_pad8]  K-major B operand for tcgen05 dgrad */
+  WS_PACK_TC_DGRAD = 3,   /* bf16 [flipped tap][cin_pad16][cout_pad8]  K-major B operand for tcgen05 dgrad */
+  WS_PACK_TC_FWD_TF32 = 4,   /* fp32 [tap][cout_pad16][cin_pad4]            the same for WS_MATH_TF32          */
+  WS_PACK_TC_DGRAD_TF32 = 5  /* fp32 [flipped tap][cin_pad16][cout_pad4]                                       */
 };
 
 /* A view of a 5-D activation: element (n, c, v) with v = (x*Y + y)*Z + z lives at

@@ -46,7 +46,7 @@ def _to_act(t, dtype):
     return out
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("layer", LAYERS, ids=[l[0] for l in LAYERS])
 def test_conv_fwd_dgrad_wgrad(layer, mode):
     from gan_sr_wind_field_b200 import ops
@@ -91,9 +91,16 @@ def test_tensor_core_path_is_selected():
     with ops.precision("fp32"):
         xf = ops.empty_cl(1, 144, 8, 8, 10, torch.float32, "cuda")
         assert ops.fwd_path(shape, xf) == _lib.PATH_SIMT
+    with ops.precision("tf32"):  # kind::tf32 on fp32 activations; strided convs stay on the CUDA cores
+        dyf = ops.empty_cl(1, 144, 8, 8, 10, torch.float32, "cuda")
+        assert ops.fwd_path(shape, xf) == _lib.PATH_TCGEN05
+        assert ops.dgrad_path(shape, dyf) == _lib.PATH_TCGEN05
+        assert ops.wgrad_path(shape, xf, dyf) == _lib.PATH_TCGEN05
+        strided = ops.make_shape(xf.shape, 144, (4, 4, 3), (2, 2, 1), 1)
+        assert ops.fwd_path(strided, xf) == _lib.PATH_SIMT
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_fused_epilogue(mode):
     """bias + LeakyReLU + channel (dropout) scale + two residuals + slice write + second output."""
     from gan_sr_wind_field_b200 import ops

@@ -174,7 +174,7 @@ def test_gan_step_vs_golden(mode):
                     assert rel_l2(upd, ref_upd) <= 0.05, name
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp32"])
 def test_full_size_upscale8_generator_vs_oracle(mode):
     """BASELINE.json config #1 shapes: the shipped upscale8 architecture (128 features, 16 RRDBs, 5x5x5 HR convs),
     LR (1,4,16,16,10) -> SR (1,3,128,128,10), against the CPU oracle with the same weights."""

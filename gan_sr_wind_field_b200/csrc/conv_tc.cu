@@ -249,7 +249,9 @@ int get_tensor_map_impl(const MapKey& key, CUtensorMap* out) {
   // key.dtype: low byte = element type, bit 8 = SWIZZLE_64B instead of SWIZZLE_128B (tmap.cuh)
   CUtensorMapDataType dt =
       (key.dtype & 0xffu) == WS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapSwizzle swz = (key.dtype & kMapSwizzle64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle swz = (key.dtype & kMapSwizzle64)          ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : (key.dtype & kMapSwizzle128Atom32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                                      : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = enc(&m, dt, key.rank, reinterpret_cast<void*>(key.ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

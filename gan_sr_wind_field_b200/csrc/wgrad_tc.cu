@@ -171,7 +171,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     if (has_work) {
       // ===== MMA issuer =====
       const uint32_t idesc = ptx::make_idesc(p.tf32 ? 2u : 1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
-      const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, blk_bytes, 1024);
+      // bf16: SWIZZLE_128B, K atoms of 8 rows (SBO = 1024 B).  tf32: the MN-major operand must use the 32-byte-atom
+      // flavour of the 128-byte swizzle (layout type 1), whose K atoms are 4 rows (SBO = 512 B); LBO = one channel block
+      const uint64_t desc_hi =
+          p.tf32 ? (((uint64_t)((blk_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) |
+                    ((uint64_t)1 << 61))
+                 : ptx::make_smem_desc_sw128(0, blk_bytes, 1024);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       // one instruction consumes 16 voxel rows of bf16 (2048 B of the MN-major tile) or 8 rows of tf32 (1024 B)
@@ -441,7 +446,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     MapKey k;
     memset(&k, 0, sizeof(k));
     k.ptr = reinterpret_cast<uintptr_t>(v.ptr);
-    k.rank = 5; k.dtype = tf32 ? WS_F32 : WS_BF16;
+    k.rank = 5; k.dtype = tf32 ? (WS_F32 | kMapSwizzle128Atom32) : WS_BF16;
     k.dims[0] = (uint64_t)channels; k.dims[1] = (uint64_t)Z; k.dims[2] = (uint64_t)Y; k.dims[3] = (uint64_t)X;
     k.dims[4] = (uint64_t)g.n;
     k.strides[0] = (uint64_t)v.vs * esize;

@@ -22,7 +22,7 @@ def _generator(sd):
     return G
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_generator_forward_backward_vs_golden(mode):
     from gan_sr_wind_field_b200 import ops
     z = load_npz("generator_small.npz")
@@ -42,15 +42,20 @@ def test_generator_forward_backward_vs_golden(mode):
     if mode == "fp32":
         assert all(e <= 5e-5 for e in errs.values()), errs  # ~50-layer chain of re-associated fp32 sums
         return
-    # BF16: this fixture is deliberately hot (init scale 0.5, |SR| up to ~90, raw-altitude terrain features
+    # BF16 / TF32: this fixture is deliberately hot (init scale 0.5, |SR| up to ~90, raw-altitude terrain features
     # next to O(1) wind features), so even the minimal bf16-operand scheme is 5-19 % away from fp32 in the deep
     # gradients.  Bound the CUDA path by that intrinsic envelope, measured here on the CPU.
+    if mode == "tf32":
+        from tests.parity_util import operand_rounding
+        emulate = lambda: operand_rounding("tf32")
+    else:
+        emulate = bf16_operand_emulation
     from oracle import wind_oracle as wo
     sd = sd_from(z, "sd/")
     p_cpu = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     lr_cpu = torch.from_numpy(z["LR"]).requires_grad_(True)
     names = [k for k in errs if k != "LR"]
-    with bf16_operand_emulation():
+    with emulate():
         o = wo.generator_forward(p_cpu, lr_cpu, torch.from_numpy(z["Z"]))
         g = torch.autograd.grad((o * torch.from_numpy(z["r"])).sum(), [lr_cpu] + [p_cpu[n] for n in names])
     env = {"LR": rel_l2(g[0], z["grad_LR"])}

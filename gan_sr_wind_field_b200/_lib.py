@@ -34,7 +34,7 @@ class WsEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("oscale", C.c_void_p), ("chan_scale", C.c_void_p),
                 ("lrelu_slope", C.c_float), ("alpha", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("res1", WsTensor), ("res2", WsTensor), ("mask", WsTensor),
-                ("mask_c0", C.c_int32), ("mask_c1", C.c_int32), ("mask_slope", C.c_float), ("_pad", C.c_int32),
+                ("mask_c0", C.c_int32), ("mask_c1", C.c_int32), ("mask_slope", C.c_float), ("flags", C.c_int32),
                 ("out2", WsTensor), ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p),
                 ("tail_out", WsTensor), ("tail_mask", WsTensor), ("tail_c0", C.c_int32), ("tail_slope", C.c_float)]
 

@@ -63,6 +63,7 @@ bool rdb_persist_bwd_ok(const ws_rdb_desc*, const View&, const View&, const View
 int rdb_persist_backward(const ws_rdb_desc*, const View&, const View&, const View&, const View&, const View&,
                          void* const*, cudaStream_t);
 int copy_launch(const View&, const View&, int, int, long long, cudaStream_t);
+int round_tf32_launch(const View&, int, int, long long, cudaStream_t);
 int axpby_launch(const View&, float, const View&, float, const View&, int, int, long long, cudaStream_t);
 int lrelu_bwd_launch(const View&, const View&, float, const float*, const float*, const View&, int, int,
                      long long, cudaStream_t);
@@ -606,6 +607,8 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
   // buf[:, :f] = x (cast to the activation dtype)
   ws_tensor b0 = *buf;
   if (int e = copy_launch(View(x), View(&b0), d->n, d->f, v, st)) return e;
+  if (d->math == WS_MATH_TF32)  // the conv-operand copy of the block input (the fp32 residual stream stays exact)
+    if (int e = round_tf32_launch(View(&b0), d->n, d->f, v, st)) return e;
   const bool fold = workspace && workspace_bytes >= ws_rdb_forward_workspace_bytes(d) && rdb_fold_ok(d, buf);
   if (d->repack)
     if (int e = rdb_repack(d, r, buf, nullptr, w, packed, 0, st, fold ? 1 : 0)) return e;
@@ -624,6 +627,7 @@ extern "C" int ws_rdb_forward(const ws_rdb_desc* d, const ws_tensor* x, const ws
     }
     ws_epilogue ep = plain_epilogue();
     ep.lrelu_slope = d->slope;
+    ep.flags = d->math == WS_MATH_TF32 ? 1 : 0;
     if (int e = ws_conv3d_fwd(s, &in, packed[i], &o, &ep, d->math, stream)) return e;
   }
   {

@@ -103,6 +103,14 @@ struct View {
   __host__ __device__ int esize() const { return dtype == WS_F32 ? 4 : 2; }
 };
 
+// fp32 -> nearest TF32 value (10 mantissa bits), ties away from zero.  The tensor cores TRUNCATE fp32 operands to TF32;
+// rounding the stored operand first halves that error and removes its bias.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // Device-side epilogue (see ws_epilogue in windsr.h for the exact semantics).
 struct Epi {
   const float* bias;
@@ -117,6 +125,7 @@ struct Epi {
   View tail_out, tail_mask;  // see ws_epilogue: fused LeakyReLU-backward of the tail channels
   int tail_c0;
   float tail_slope;
+  int round_out;  // ws_epilogue::flags bit 0: round the stored values to TF32 (pure activations in TF32 mode)
   int cout;  // channel count of the output (indexing chan_scale)
 
   __host__ Epi() {}
@@ -129,7 +138,9 @@ struct Epi {
       mask_c0 = e->mask_c0; mask_c1 = e->mask_c1; mask_slope = e->mask_slope;
       stat_sum = e->stat_sum; stat_sqsum = e->stat_sqsum;
       tail_out = View(e->tail_out); tail_mask = View(e->tail_mask); tail_c0 = e->tail_c0; tail_slope = e->tail_slope;
+      round_out = e->flags & 1;
     } else {
+      round_out = 0;
       tail_c0 = 0; tail_slope = 1.f;
       bias = oscale = chan_scale = nullptr;
       lrelu_slope = 1.f; alpha = 1.f; beta1 = beta2 = 0.f;
@@ -153,6 +164,7 @@ struct Epi {
       float m = mask.ld(n, c, v);
       y *= (m > 0.f ? 1.f : mask_slope);
     }
+    if (round_out) y = round_tf32(y);
     return y;
   }
 };

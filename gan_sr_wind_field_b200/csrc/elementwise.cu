@@ -46,7 +46,7 @@ __global__ void pack_simt(const float* __restrict__ w, float* __restrict__ p, in
 // fwd:   p[tap][co_pad][ci_pad]          = w[co][ci][tap]
 // dgrad: p[taps-1-tap][ci_pad16][co_pad8] = w[co][ci][tap]   (taps-1-tap == flip of all three axes)
 __device__ __forceinline__ void store_packed(__nv_bfloat16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
-__device__ __forceinline__ void store_packed(float* p, long long i, float v) { p[i] = v; }  // TF32 flavour: fp32 operands
+__device__ __forceinline__ void store_packed(float* p, long long i, float v) { p[i] = round_tf32(v); }  // TF32 operands
 
 template <typename T>
 __global__ void pack_tc(const float* __restrict__ w, T* __restrict__ p, int cout, int cin,
@@ -106,7 +106,7 @@ __global__ void pack_tc_multi(const PackTable t) {
     } else {
       if (row < e.cin && col < e.cout) v = w[((long long)col * e.cin + row) * e.taps + (e.taps - 1 - tp)];
     }
-    if (e.tf32) reinterpret_cast<float*>(e.p)[i] = v;
+    if (e.tf32) reinterpret_cast<float*>(e.p)[i] = round_tf32(v);
     else p[i] = __float2bfloat16_rn(v);
   }
 }
@@ -782,6 +782,24 @@ int pack_tc_batch_launch(int n, const float* const* w, const ConvGeom* g, int dg
   int bx = (int)((most + kBlock - 1) / kBlock);
   if (bx > 148 * 2) bx = 148 * 2;
   WS_CHECK_CUDA(launch_pdl(pack_tc_multi, dim3((unsigned)bx, (unsigned)n), dim3(kBlock), 0, st, 1, t));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+// in place: x = nearest TF32 value of x (fp32, contiguous channels per voxel)
+__global__ void round_tf32_kernel(View x, int n, int c, long long v) {
+  const long long total = (long long)n * v * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c);
+    const long long r = i / c;
+    const long long o = x.off((int)(r / v), cc, r % v);
+    ((float*)x.ptr)[o] = round_tf32(((const float*)x.ptr)[o]);
+  }
+}
+int round_tf32_launch(const View& x, int n, int c, long long v, cudaStream_t st) {
+  if (x.dtype != WS_F32) return 0;
+  round_tf32_kernel<<<grid_for((long long)n * v * c), kBlock, 0, st>>>(x, n, c, v);
   WS_POST_LAUNCH(1);
   return 0;
 }

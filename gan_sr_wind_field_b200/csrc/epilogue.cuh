@@ -142,6 +142,10 @@ __device__ __forceinline__ void epilogue16_simple(const Epi& ep, const EpiVec& e
     store16(ep.tail_out, view_vec_ok(ep.tail_out), n, ct, v, cnt, y);
     return;
   }
+  if (ep.round_out) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = round_tf32(y[j]);
+  }
   store16(dst, ev.dst, n, cbase, v, cn, y);
   if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
 }
@@ -204,6 +208,10 @@ __device__ __forceinline__ void epilogue16(const Epi& ep, const EpiVec& ev, cons
     }
   }
   if (row_ok) {
+    if (ep.round_out) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = round_tf32(y[j]);
+    }
     store16(dst, ev.dst, n, cbase, v, cn, y);
     if (ep.out2.ptr) store16(ep.out2, ev.out2, n, cbase, v, cn, y);
   }

@@ -200,7 +200,9 @@ def _epilogue(bias=None, oscale=None, chan_scale=None, slope=1.0, alpha=1.0, res
     return WsEpilogue(ptr(bias), ptr(oscale), ptr(chan_scale), slope, alpha, beta1, beta2,
                       view(res1) if res1 is not None else null_view(),
                       view(res2) if res2 is not None else null_view(),
-                      view(mask) if mask is not None else null_view(), mask_c0, mask_c1, mask_slope, 0,
+                      view(mask) if mask is not None else null_view(), mask_c0, mask_c1, mask_slope,
+                      # TF32 mode: LeakyReLU outputs are pure activations (conv operands only) -> store them rounded
+                      1 if (_PRECISION == "tf32" and slope != 1.0) else 0,
                       view(out2) if out2 is not None else null_view(), ptr(stat_sum), ptr(stat_sqsum))
 
 

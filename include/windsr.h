@@ -100,7 +100,8 @@ typedef struct ws_epilogue {
   ws_tensor mask;
   int32_t mask_c0, mask_c1;
   float mask_slope;
-  int32_t _pad;
+  int32_t flags; /* bit 0: round the stored values to the nearest TF32 value (outputs that only feed WS_MATH_TF32 convs:
+                    the tensor cores truncate fp32 operands, rounding first halves the error and removes its bias) */
   ws_tensor out2;
   float* stat_sum;
   float* stat_sqsum;

@@ -365,9 +365,24 @@ def run_native(args):
             ms_inf, _ = timed(lambda i: gan.G(LR[:1], Z[:1]), 10)
         infer = {"ms": ms_inf / 10, "voxels_per_s": VOX_PER_SAMPLE / (ms_inf / 10 * 1e-3), "batch": 1}
 
+    def teardown():
+        """Captured CUDA graphs hold NCCL kernels: they have to go before the communicator does (destroying the
+        process group first left both ranks hanging in NCCL's teardown until its watchdog fired 8 minutes later).  A
+        timer guarantees the process ends even if a teardown path blocks."""
+        if world == 1:
+            return
+        import threading
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        gan._graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown()
         return
     vox = world * B * VOX_PER_SAMPLE
     tflops_peak, hbm_peak, peak_src = _peaks()
@@ -415,9 +430,8 @@ def run_native(args):
     }
     if world == 1 and not args.no_cpu_baseline and not args.quick:
         out["cpu_baseline"] = cpu_reference_step(steps=1, warmup=0, batch=1)
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    teardown()
 
 
 def _measured_traffic():

@@ -39,7 +39,7 @@ from .. import ops
 from ..CNN_models.Discriminator_3D import Discriminator_3D
 from ..CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
 from ..optim import WindAdam
-from ..parallel import GradSync, allreduce_max_, broadcast_module
+from ..parallel import GradSync, allreduce_max, allreduce_max_, broadcast_module
 from ..tools import initialization, trainingtricks
 from .baseGAN import BaseGAN
 
@@ -259,7 +259,13 @@ class wind_field_GAN_3D(BaseGAN):
                                       "configs: out_num_ch = 3)")
         s = ops.windloss_slots(HR, fake_HR, Z, self.x, self.y)
         cnt = float(HR.shape[0] * HR.shape[2] * HR.shape[3] * HR.shape[4])
-        norm = [torch.maximum(s[6 + 2 * k], s[7 + 2 * k] / 100) for k in range(4)]
+        mx = s[6:14]
+        if self.world_size > 1 and os.environ.get("WINDSR_SYNC_NORMALISERS", "1") != "0":
+            # the four loss normalisers are maxima over the WHOLE batch (wind_field_GAN_3D.py:773-814): with the batch
+            # sharded over ranks they are the one batch-coupled term of a generator step (G has no BatchNorm), so one
+            # 8-float MAX all-reduce makes W ranks reproduce the reference on the concatenated batch
+            mx = allreduce_max(mx)
+        norm = [torch.maximum(mx[2 * k], mx[2 * k + 1] / 100) for k in range(4)]
         xy = s[0] / (6.0 * cnt) / (norm[0] * norm[0])
         zg = s[1] / (3.0 * cnt) / (norm[1] * norm[1])
         div = s[2] / cnt / (norm[2] * norm[2])

@@ -142,3 +142,32 @@ def allreduce_max_(flag: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
     return flag
+
+
+class _AllReduceMaxFn(torch.autograd.Function):
+    """y = max over ranks of x (elementwise).  Backward: the cotangent reaches the local x only where the local value
+    IS the global maximum — the sub-gradient torch.max would give on the concatenated batch.  The loss that consumes y
+    is the mean over ranks of per-rank losses, so after the gradient all-reduce(AVG) the winner has to carry the SUM of
+    every rank's cotangent: all-reduce(SUM) of the cotangent first."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.detach().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.MAX, group=group)
+        ctx.save_for_backward(x.detach() == y)
+        ctx.group = group
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (winner,) = ctx.saved_tensors
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return torch.where(winner, g, torch.zeros_like(g)), None
+
+
+def allreduce_max(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Differentiable MAX over ranks (identity without a process group)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    return _AllReduceMaxFn.apply(x, group)

@@ -196,7 +196,7 @@ def test_schedule_and_labels():
 _DDP_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from gan_sr_wind_field_b200.parallel import GradSync
+from gan_sr_wind_field_b200.parallel import GradSync, allreduce_max, allreduce_max_, broadcast_module
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 torch.manual_seed(0)
@@ -224,6 +224,31 @@ ok = all((p.grad is None and not p.requires_grad) or torch.allclose(p.grad, r_, 
 net.zero_grad(set_to_none=True)
 sync.begin(); net(data[rank]).pow(2).mean().backward(); sync.finish()
 ok = ok and all((p.grad is None) or torch.allclose(p.grad, r_, atol=1e-6) for p, r_ in zip(net.parameters(), ref))
+# p.grad is a view of the reduced bucket (no copy back)
+live = [p for p in net.parameters() if p.grad is not None]
+def flat_ptr(p):
+    b = sync._where[p]
+    i = [id(q) for q in b.params].index(id(p))
+    return b.flat[b.offsets[i]:].data_ptr()
+ok = ok and all(p.grad.data_ptr() == flat_ptr(p) for p in live)
+# replicas built from different seeds take rank 0's parameters
+torch.manual_seed(10 + rank)
+other = torch.nn.Linear(3, 3)
+broadcast_module(other)
+gathered = [torch.zeros_like(other.weight) for _ in range(world)]
+dist.all_gather(gathered, other.weight.detach())
+ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)
+# the global "loss is not finite" flag: one bad rank makes every rank skip
+flag = torch.tensor(1.0 if rank == 1 else 0.0)
+ok = ok and float(allreduce_max_(flag)) == 1.0
+# differentiable MAX over ranks (the loss normalisers): forward = global max; backward = the SUM of all ranks'
+# cotangents, delivered to the rank that holds the maximum only
+x = torch.tensor([1.0 + rank, 5.0 - rank], requires_grad=True)     # slot 0: rank 1 wins, slot 1: rank 0 wins
+y = allreduce_max(x)
+ok = ok and torch.equal(y.detach(), torch.tensor([2.0, 5.0]))
+(y * torch.tensor([1.0 + rank, 10.0 * (1 + rank)])).sum().backward()  # cotangents (1|2, 10|20) on rank (0|1)
+want = torch.tensor([0.0, 30.0]) if rank == 0 else torch.tensor([3.0, 0.0])
+ok = ok and torch.equal(x.grad, want)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 3)
 '''
@@ -315,3 +340,22 @@ def test_xfold_weight_matches_conv():
             if 0 <= xs < X:
                 out[:, :, xx] += U[:, dx * co:(dx + 1) * co, xs]
     assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_device_dataset_sampling_follows_reference_distributions(monkeypatch):
+    """Host side of the GPU input pipeline: per-sample draws in the reference's order and ranges
+    (process_data.py:159-166, 199, 246, 252); no device work (tensors stay on the CPU here)."""
+    import numpy as np
+    from gan_sr_wind_field_b200.data_pipeline import DeviceWindDataset
+    f = np.zeros((3, 24, 20, 4))
+    ds = DeviceWindDataset(f, f, f, f, f, f, -2.71, 550.44, 32.33, 9e4, 1.05e5, 68.46, include_z_channel=True,
+                           COARSENESS_FACTOR=4, enable_slicing=True, slice_size=16, device="cpu", seed=7)
+    aug = ds.sample_augmentation(2000)
+    assert aug.dtype == np.int32 and aug.shape == (2000, 5)
+    assert aug[:, 0].min() >= 0 and aug[:, 0].max() <= 24 - 16 and aug[:, 1].max() <= 20 - 16
+    # beta(0.25, 0.25) piles the offsets up at both ends of the range
+    assert (aug[:, 0] == 0).mean() > 0.2 and (aug[:, 0] == 8).mean() > 0.2
+    assert set(np.unique(aug[:, 2])) == {0, 1, 2, 3} and set(np.unique(aug[:, 3:])) == {0, 1}
+    plain = DeviceWindDataset(f, f, f, f, f, f, -2.71, 550.44, 32.33, 9e4, 1.05e5, 68.46, data_aug_rot=False,
+                              data_aug_flip=False, device="cpu")
+    assert not plain.sample_augmentation(5).any() and len(plain) == 3

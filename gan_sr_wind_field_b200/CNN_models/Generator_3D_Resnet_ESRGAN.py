@@ -18,6 +18,7 @@ Fused dataflow of ``forward`` (reference lines in brackets):
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -134,6 +135,10 @@ class Generator_3D(nn.Module, lc.GlobalLoggingClass):
         last = self.hr_convs[2]
         if (ops.get_precision() == "bf16" and last.stride == (1, 1, 1) and last.kernel_size[0] * last.out_channels <= 16
                 and last.in_channels >= 16 and feat.dtype == torch.bfloat16):
+            # very narrow output (144 -> 3): lateral taps folded into the channel dimension (ops.XYFoldConvFn / XFoldConvFn)
+            if (last.out_channels <= 8 and last.kernel_size[0] * last.kernel_size[1] * last.out_channels <= 128
+                    and os.environ.get("WINDSR_XYFOLD", "1") != "0"):
+                return ops.XYFoldConvFn.apply(feat, last.weight, last.bias, last.padding)
             return ops.XFoldConvFn.apply(feat, last.weight, last.bias, last.padding)
         return last.run(feat, out_dtype=torch.float32, out_contig=True)
 

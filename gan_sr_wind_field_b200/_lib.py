@@ -88,6 +88,8 @@ SYMBOLS = [
     ("ws_upsample_nearest_xy_bwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_xfold_sum", _I, [_TP, _P, _TP, _I, _I, _I, _I, _I, _I, _I, _P]),
     ("ws_xunfold", _I, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    ("ws_xyfold_sum", _I, [_TP, _P, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    ("ws_xyunfold", _I, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     ("ws_copy", _I, [_TP, _TP, _I, _I, _L, _P]),
     ("ws_axpby", _I, [_TP, _F, _TP, _F, _TP, _I, _I, _L, _P]),
     ("ws_lrelu_bwd", _I, [_TP, _TP, _F, _P, _P, _TP, _I, _I, _L, _P]),

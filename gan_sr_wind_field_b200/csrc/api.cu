@@ -80,6 +80,8 @@ int bn_bwd_apply_launch(const View&, const View&, const View&, const float*, con
                         cudaStream_t);
 int xfold_sum_launch(const View&, const float*, const View&, int, int, int, int, int, int, int, cudaStream_t);
 int xunfold_launch(const View&, const View&, int, int, int, int, int, int, int, int, cudaStream_t);
+int xyfold_sum_launch(const View&, const float*, const View&, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int xyunfold_launch(const View&, const View&, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int axis_coeffs_launch(const float*, int, float*, cudaStream_t);
 int wind_gradient_launch(const View&, const View&, const float*, const float*, const View&, int, int, int, int,
                          cudaStream_t);
@@ -362,6 +364,17 @@ int ws_xunfold(const ws_tensor* dout, const ws_tensor* u, int n, int co, int kx,
                int z, void* stream) {
   WS_REQUIRE(dout && dout->ptr && u && u->ptr && cpad >= kx * co, "ws_xunfold: bad arguments");
   return xunfold_launch(View(dout), View(u), n, co, kx, pad, cpad, x, yy, z, (cudaStream_t)stream);
+}
+
+int ws_xyfold_sum(const ws_tensor* y, const float* bias, const ws_tensor* out, int n, int co, int kx, int ky, int px,
+                  int py, int x, int yy, int z, void* stream) {
+  WS_REQUIRE(y && y->ptr && out && out->ptr && co > 0 && kx > 0 && ky > 0, "ws_xyfold_sum: bad arguments");
+  return xyfold_sum_launch(View(y), bias, View(out), n, co, kx, ky, px, py, x, yy, z, (cudaStream_t)stream);
+}
+int ws_xyunfold(const ws_tensor* dout, const ws_tensor* u, int n, int co, int kx, int ky, int px, int py, int cpad,
+                int x, int yy, int z, void* stream) {
+  WS_REQUIRE(dout && dout->ptr && u && u->ptr && cpad >= kx * ky * co, "ws_xyunfold: bad arguments");
+  return xyunfold_launch(View(dout), View(u), n, co, kx, ky, px, py, cpad, x, yy, z, (cudaStream_t)stream);
 }
 
 int ws_im2col(const ws_conv_shape* s, const ws_tensor* x, const ws_tensor* u, int cpad, void* stream) {

@@ -205,3 +205,28 @@ def test_module_path_144_channels_remainder_xfold_wgrad():
     # both halves of the output-channel split are right on their own
     assert rel_l2(conv.weight.grad[:128], wr.grad[:128]) <= TOL["bf16"]
     assert rel_l2(conv.weight.grad[128:], wr.grad[128:]) <= TOL["bf16"]
+
+
+@pytest.mark.parametrize("fn_name", ["XFoldConvFn", "XYFoldConvFn"])
+def test_folded_narrow_conv_matches_conv3d(fn_name):
+    """hr_convs.2 (5x5x5, 144 -> 3, bias; Generator_3D_Resnet_ESRGAN.py:105-110) with the lateral taps folded into the
+    channel dimension: forward, dL/dx, dL/dw, dL/db against torch's CPU conv3d on the same bf16-rounded operands."""
+    from gan_sr_wind_field_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, cin, cout, vol = 2, 144, 3, (11, 13, 10)
+    x = torch.randn(n, cin, *vol, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, 5, 5, 5, generator=g) / (cin * 125) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(n, cout, *vol, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv3d(xr, wr, br, padding=2)
+    gx, gw, gb = torch.autograd.grad(ref, (xr, wr, br), dy)
+    with ops.precision("bf16"):
+        xa = _to_act(x, torch.bfloat16).requires_grad_(True)
+        wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+        out = getattr(ops, fn_name).apply(xa, wc, bc, (2, 2, 2))
+        out.backward(dy.cuda())
+        torch.cuda.synchronize()
+    assert out.shape == ref.shape and out.is_contiguous()
+    errs = dict(fwd=rel_l2(out, ref), dx=rel_l2(xa.grad.float(), gx), dw=rel_l2(wc.grad, gw), db=rel_l2(bc.grad, gb))
+    assert all(e <= TOL["bf16"] for e in errs.values()), errs

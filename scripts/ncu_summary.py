@@ -6,7 +6,8 @@
 import collections, csv, io, json, os, re, subprocess, sys
 
 METRICS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-           "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active", "l1tex__m_xbar2l1tex_read_bytes.sum",
+           "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+           "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second", "l1tex__m_xbar2l1tex_read_bytes.sum",
            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__block_size", "launch__cluster_dim_x",
            "launch__grid_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
            "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -55,7 +56,7 @@ def full(rep, out, title, traffic_key=None):
                   "| metric | value |", "|---|---|"]
         dram = 0.0
         for h, u in zip(hdr, units):
-            if any(m in h for m in METRICS):
+            if h in METRICS or h.endswith("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"):
                 lines.append(f"| {h} | {rec[h]} {u} |")
                 if h in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     dram += float(rec[h].replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)

@@ -18,6 +18,10 @@ t = cfg.training
 gan.feed_xy_niter(x, y, torch.tensor(t.niter, device=dev), t.d_g_train_ratio, t.d_g_train_period)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 for i in range(n):
+    if i == n - 1:  # `ncu --profile-from-start off` then sees exactly one steady-state step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     gan.optimize_parameters(LR, HR, Z, 1 + i)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", ops.launch_count())

@@ -236,9 +236,7 @@ class SkipConnectionBlock(nn.Module):
             parts = last._parts()
             if parts is not None and parts[1] is None and parts[2] is None:
                 x32 = _to_f32(x)
-                h = x32
-                for m in list(mod)[:-1]:
-                    h = m(h)
+                h = run_trunk(list(mod)[:-1], x32)
                 return parts[0].run(h, res=x32, beta=1.0, out_dtype=torch.float32)
         return ops.AxpbyFn.apply(_to_f32(x), _to_f32(mod(x)), 1.0, 1.0)
 
@@ -368,6 +366,78 @@ class RRDB(nn.Module):
                 return rdb.run(h, outer=x, outer_scale=self.RRDB_residual_scaling)
             h = rdb.run(h)
         return ops.AxpbyFn.apply(h, x, self.RRDB_residual_scaling, 1.0)  # number_of_RDBs == 0
+
+
+def _trunk_signature(m):
+    """Geometry key of an RRDB whose RDBs ops.TrunkFn can batch, else None."""
+    if not isinstance(m, RRDB) or len(m.RDBs) == 0:
+        return None
+    sig = None
+    for rdb in m.RDBs:
+        if not isinstance(rdb, RDB) or rdb.LFF.bias is None:
+            return None
+        convs = rdb._dense_convs()
+        if len(convs) < 2 or any(c.bias is not None or c.stride != (1, 1, 1) for c in convs):
+            return None
+        k = convs[0].kernel_size
+        if k[0] != k[1] or k[0] != k[2] or rdb.LFF.kernel_size != (1, 1, 1):
+            return None
+        f, gc = rdb.LFF.out_channels, convs[0].out_channels
+        if any(c.in_channels != f + i * gc or c.out_channels != gc for i, c in enumerate(convs)):
+            return None
+        if rdb.LFF.in_channels != f + len(convs) * gc:
+            return None
+        s = (rdb.LFF.out_channels, convs[0].out_channels, len(convs), k[0], rdb.lrelu_negative_slope,
+             tuple(c.in_channels for c in convs), tuple(c.kernel_size for c in convs))
+        if sig is not None and s != sig:
+            return None
+        sig = s
+    return sig
+
+
+def run_trunk(mods, h):
+    """Apply a list of trunk modules; maximal runs of RRDBs with identical RDB geometry go through ``ops.TrunkFn``
+    (one autograd node, batched weight gradients) when gradients are being recorded on the BF16 tensor-core path,
+    every other case through the modules' own forward.  ``WINDSR_TRUNK_GROUPS`` splits a run into that many nodes
+    (their parameter gradients — and with them the gradient all-reduce — become available earlier)."""
+    import os
+    i = 0
+    use = (ops.trunk_batched_enabled() and torch.is_grad_enabled() and h.is_cuda and ops.get_precision() == "bf16")
+    groups = max(1, int(os.environ.get("WINDSR_TRUNK_GROUPS", "1")))
+    while i < len(mods):
+        sig = _trunk_signature(mods[i]) if use else None
+        j = i
+        if sig is not None:
+            while j < len(mods) and _trunk_signature(mods[j]) == sig:
+                j += 1
+        if j > i and ops.trunk_supported(h, sig):
+            per = -(-(j - i) // groups)
+            for a in range(i, j, per):
+                h = _trunk_apply(mods[a:min(j, a + per)], h, sig)
+            i = j
+        else:
+            h = mods[i](h)
+            i += 1
+    return h
+
+
+def _trunk_apply(rrdbs, h, sig):
+    blocks, params = [], []
+    for m in rrdbs:
+        first = len(blocks)
+        rdbs = list(m.RDBs)
+        for t, rdb in enumerate(rdbs):
+            if not hasattr(rdb, "_rdb_state"):
+                rdb._rdb_state = ops.RDBState()
+            last = t == len(rdbs) - 1
+            if last:
+                blocks.append(dict(alpha=rdb.residual_scaling * m.RRDB_residual_scaling, beta1=m.RRDB_residual_scaling,
+                                   beta2=1.0, outer=first, state=rdb._rdb_state))
+            else:
+                blocks.append(dict(alpha=rdb.residual_scaling, beta1=1.0, beta2=0.0, outer=None, state=rdb._rdb_state))
+            params += [c.weight for c in rdb._dense_convs()] + [rdb.LFF.weight, rdb.LFF.bias]
+    cfg = dict(nconv=sig[2], slope=sig[4], blocks=blocks)
+    return ops.TrunkFn.apply(_to_f32(h), cfg, *params)
 
 
 class UpConvBlock(nn.Sequential):

@@ -84,6 +84,10 @@ SYMBOLS = [
     ("ws_rdb_forward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P, _P, _Z, _P]),
     ("ws_rdb_backward", _I, [C.POINTER(WsRdbDesc), _TP, _TP, _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P),
                              C.POINTER(_P), _P, _P, _Z, _P, _P, _P, _Z]),
+    ("ws_trunk_wgrad_supported", _I, [C.POINTER(WsRdbDesc)]),
+    ("ws_trunk_wgrad_record_floats", _Z, [C.POINTER(WsRdbDesc)]),
+    ("ws_trunk_wgrad_workspace_bytes", _Z, [C.POINTER(WsRdbDesc), _I]),
+    ("ws_trunk_wgrad", _I, [C.POINTER(WsRdbDesc), _I, _TP, _TP, _TP, _P, _L, _P, _Z, _P]),
     ("ws_upsample_nearest_xy_fwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_upsample_nearest_xy_bwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_xfold_sum", _I, [_TP, _P, _TP, _I, _I, _I, _I, _I, _I, _I, _P]),

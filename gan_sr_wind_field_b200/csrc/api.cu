@@ -55,6 +55,10 @@ int xfold_sum_lrelu_launch(const View&, const View&, float, int, int, int, int, 
 int tc_rdb_wgrad(const ConvGeom&, const View&, const View&, float* const*, const int*, int, int, void*, size_t,
                  cudaStream_t);
 size_t tc_rdb_wgrad_workspace_bytes(int, int, int, int);
+size_t tc_trunk_wgrad_workspace_bytes(int, int, int, int, int);
+int tc_trunk_wgrad(const ConvGeom&, const ConvGeom&, int, const View&, const View&, const View&, const int*, int, int,
+                   float*, long long, void*, size_t, cudaStream_t);
+int bias_grad_batched(const View&, float*, int, long long, int, int, long long, cudaStream_t);
 int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
 bool rdb_persist_ok(const ws_rdb_desc*, const View&, const View&, int);
 int rdb_persist_forward(const ws_rdb_desc*, const View&, const View&, const View&, void* const*, const Epi&,
@@ -824,4 +828,66 @@ extern "C" int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const 
     if (int e = axpby_launch(View(dbuf), 1.f, View(dy), d->beta1, View(dx), d->n, d->f, v, st)) return e;
   }
   return 0;
+}
+
+// ---- batched weight gradients of a run of identical residual dense blocks (wgrad_tc.cu: tc_trunk_wgrad) -------------
+extern "C" size_t ws_trunk_wgrad_record_floats(const ws_rdb_desc* d) {
+  RdbGeom r;
+  if (!d || rdb_geom(d, r)) return 0;
+  size_t total = 0;
+  for (int i = 0; i < d->nconv; ++i)
+    total += (size_t)r.dense[i].cout * r.dense[i].cin * r.dense[i].kx * r.dense[i].ky * r.dense[i].kz;
+  total += (size_t)r.lff.cout * r.lff.cin * r.lff.kx * r.lff.ky * r.lff.kz;
+  return total + (size_t)r.lff.cout;
+}
+
+extern "C" size_t ws_trunk_wgrad_workspace_bytes(const ws_rdb_desc* d, int nblocks) {
+  if (!d || nblocks < 1 || d->nconv < 1) return 0;
+  return tc_trunk_wgrad_workspace_bytes(nblocks, d->k * d->k * d->k, d->f + (d->nconv - 1) * d->gc, d->nconv, d->gc);
+}
+
+namespace {
+bool trunk_wgrad_ok(const ws_rdb_desc* d, const RdbGeom& r, const ws_tensor* buf, const ws_tensor* g,
+                    const ws_tensor* g_lff) {
+  return d->k_lff == 1 && d->nconv >= 2 && device_cc_major() == 10 && rdb_merged_wgrad_ok(d, buf, g) &&
+         wgrad_path(ConvGeom(r.lff), View(buf), View(g_lff), d->math) == WS_PATH_TCGEN05 &&
+         View(g_lff).cs == 1 && r.lff.cout % 8 == 0 && 256 % (r.lff.cout / 8) == 0;
+}
+}  // namespace
+
+/* 1 when ws_trunk_wgrad covers blocks of this geometry / precision with densely packed channels-last slabs */
+extern "C" int ws_trunk_wgrad_supported(const ws_rdb_desc* d) {
+  RdbGeom r;
+  if (!d || d->nconv < 1 || d->nconv > WS_RDB_MAX_CONVS || d->k % 2 != 1 || d->k_lff % 2 != 1) return 0;
+  rdb_geom(d, r);
+  const int dt = d->math == WS_MATH_BF16 ? WS_BF16 : WS_F32;
+  const long long v = (long long)d->x * d->y * d->z;
+  void* fake = reinterpret_cast<void*>(uintptr_t(1) << 20);  // aligned stand-in: only layouts are examined
+  ws_tensor buf = {fake, dt, 0, v * r.ctot, r.ctot, 1};
+  ws_tensor g = {fake, dt, 0, v * d->nconv * d->gc, (long long)d->nconv * d->gc, 1};
+  ws_tensor gl = {fake, dt, 0, v * d->f, d->f, 1};
+  return trunk_wgrad_ok(d, r, &buf, &g, &gl) ? 1 : 0;
+}
+
+extern "C" int ws_trunk_wgrad(const ws_rdb_desc* d, int nblocks, const ws_tensor* buf, const ws_tensor* g,
+                              const ws_tensor* g_lff, float* grads, long long block_stride, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  RdbGeom r;
+  if (int e = rdb_geom(d, r)) return e;
+  WS_REQUIRE(nblocks >= 1 && buf && buf->ptr && g && g->ptr && g_lff && g_lff->ptr && grads,
+             "ws_trunk_wgrad: null pointer");
+  WS_REQUIRE(trunk_wgrad_ok(d, r, buf, g, g_lff),
+             "ws_trunk_wgrad: geometry / precision outside the batched tensor-core path");
+  WS_REQUIRE((size_t)block_stride >= ws_trunk_wgrad_record_floats(d), "ws_trunk_wgrad: block_stride too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  ws_conv_shape ms = rdb_merged_shape(d), ls = r.lff;
+  ms.n = ls.n = d->n * nblocks;  // the batch dimension of the tensor maps runs over (block, sample)
+  int cin[WS_RDB_MAX_CONVS];
+  for (int j = 0; j < d->nconv; ++j) cin[j] = r.dense[j].cin;
+  if (int e = tc_trunk_wgrad(ConvGeom(ms), ConvGeom(ls), nblocks, View(buf), View(g), View(g_lff), cin, d->nconv, d->gc,
+                             grads, block_stride, workspace, workspace_bytes, st))
+    return e;
+  const long long off_bias = (long long)ws_trunk_wgrad_record_floats(d) - r.lff.cout;
+  return bias_grad_batched(View(g_lff), grads + off_bias, nblocks, block_stride, d->n, r.lff.cout,
+                           (long long)d->x * d->y * d->z, st);
 }

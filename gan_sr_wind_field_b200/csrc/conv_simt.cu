@@ -493,10 +493,14 @@ __global__ void bias_grad_kernel(View dy, float* __restrict__ db, int n, int c, 
 // channels-last dy (bf16 or fp32, 8-channel vectors): a block takes a run of voxel rows, thread (q, r) sums the
 // 8 channels of group q over rows r, r + R, ...; partials meet in shared memory, one atomic per channel per block.
 __global__ void __launch_bounds__(256)
-bias_grad_cl8_kernel(View dy, float* __restrict__ db, int c8, long long v, long long rows_total, long long rows_per_block) {
+bias_grad_cl8_kernel(View dy, float* __restrict__ db, int c8, long long v, long long rows_total, long long rows_per_block,
+                     long long dy_batch_stride, long long db_batch_stride) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float red[256][9];
+  // batched form (blockIdx.y = problem): operands dy_batch_stride elements / results db_batch_stride floats apart
+  dy.ptr = (char*)dy.ptr + (long long)blockIdx.y * dy_batch_stride * (dy.dtype == WS_F32 ? 4 : 2);
+  db += (long long)blockIdx.y * db_batch_stride;
   const int q = threadIdx.x % c8, r = threadIdx.x / c8, R = blockDim.x / c8;
   const long long beg = (long long)blockIdx.x * rows_per_block;
   const long long end = beg + rows_per_block < rows_total ? beg + rows_per_block : rows_total;
@@ -847,7 +851,7 @@ int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumula
       const long long rpb = (total + blocks - 1) / blocks;
       blocks = (total + rpb - 1) / rpb;
       WS_CHECK_CUDA(launch_pdl(bias_grad_cl8_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, dy, db, c / 8, v, total,
-                               rpb));
+                               rpb, 0LL, 0LL));
       WS_POST_LAUNCH(1);
       return 0;
     }
@@ -858,6 +862,28 @@ int bias_grad(const View& dy, float* db, int n, int c, long long v, int accumula
   if (slices < 1) slices = 1;
   dim3 grid(c, slices);
   bias_grad_kernel<<<grid, 256, 0, st>>>(dy, db, n, c, v, slices);
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+// bias gradients of `nblocks` identical problems in one launch (channels-last, 8-channel vectors only): problem r reads
+// dy + r * n * nstride and writes db + r * db_stride
+int bias_grad_batched(const View& dy, float* db, int nblocks, long long db_stride, int n, int c, long long v,
+                      cudaStream_t st) {
+  const int al = dy.dtype == WS_F32 ? 4 : 8;
+  WS_REQUIRE(dy.cs == 1 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && dy.vs % al == 0 && dy.ns % al == 0 &&
+                 ((uintptr_t)dy.ptr % 16) == 0,
+             "bias_grad_batched: needs channels-last 8-channel vectors");
+  WS_CHECK_CUDA(cudaMemset2DAsync(db, (size_t)db_stride * sizeof(float), 0, (size_t)c * sizeof(float), (size_t)nblocks, st));
+  const long long total = (long long)n * v;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (148LL * 8 + nblocks - 1) / nblocks;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const long long rpb = (total + blocks - 1) / blocks;
+  blocks = (total + rpb - 1) / rpb;
+  WS_CHECK_CUDA(launch_pdl(bias_grad_cl8_kernel, dim3((unsigned)blocks, (unsigned)nblocks), dim3(256), 0, st, 1, dy, db,
+                           c / 8, v, total, rpb, (long long)n * dy.ns, db_stride));
   WS_POST_LAUNCH(1);
   return 0;
 }

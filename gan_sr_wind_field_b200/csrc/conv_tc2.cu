@@ -17,6 +17,7 @@
 // Generator_3D_Resnet_ESRGAN.py:95-111 (hr_convs).
 #include <cuda.h>
 #include <mutex>
+#include <vector>
 #include <array>
 #include <map>
 #include <stdlib.h>
@@ -42,6 +43,11 @@ struct Tc2Params {
   int ck, kchunks, last_k16, cn, n_umma, n_tile;
   int t_m, out_rows, halo_rows;
   int a_buf_bytes, w_bytes, w_slots;
+  int w_group;       // weight tiles (taps) per ring slot: the slot's barrier pair is waited / committed once per group.
+                     // A completed mbarrier wait + tcgen05 fence costs the issuing thread ~280 cycles and a tcgen05.commit
+                     // ~220 (scripts/micro/mma_rate3.cu) — per TAP that is more than the tap's MMAs (t_m x 288 cycles)
+  int merged;        // 1: w_group == taps per halo load and the weight tiles ride on the halo buffer's barriers
+                     // (ONE wait + ONE commit per K iteration)
   int a_bufs;        // halo buffers in the ring (2..kMaxABufs)
   int a_sub_slabs;   // x-slabs per TMA instruction of the halo load
   int a_ops;         // TMA instructions per halo load
@@ -55,6 +61,15 @@ struct Tc2Params {
   int tap_base;      // first tap of the packed weights this launch uses
   int omx, oax, omy, oay, omz, oaz, ODY, ODZ;  // destination voxel transform (tc_task.cuh)
   uint32_t tmem_cols;
+  int n_iss;         // MMA-issuing warps (1..4, <= t_m): warp 1 + q owns the accumulators m = q, q + n_iss, ...  A tcgen05.mma
+                     // occupies its issuing thread for about as long as it executes (scripts/micro/mma_rate3.cu: a loop
+                     // with +150 cycles of scalar work per 4 MMAs ran 110 instead of 73 cycles per MMA): whatever the
+                     // thread does between two MMAs — descriptor arithmetic, elect / reconvergence, barrier waits, commits —
+                     // is tensor-pipe idle time unless ANOTHER warp has MMAs queued meanwhile
+  int chunk_major;  // 1: K loop ordered (chunk, ky, kz) instead of (ky, kz, chunk): the short tail chunk of a channel count
+                    // that is not a multiple of 64 (144 = 64 + 64 + 16) runs as one block at the end — its quarter-length
+                    // MMA bursts no longer have to hide the load of a full-size halo tile
+  long long* dbg;  // optional (WS_TC2_DEBUG_TIMES=1): per-CTA cycle counts of the pipeline stages, 8 slots per CTA
 };
 
 // kPair: launched as clusters of two CTAs (cta_group::2).  Each CTA keeps its own halo tile, accumulators and
@@ -76,7 +91,8 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t w_base = smem_base + (uint32_t)p.a_bufs * p.a_buf_bytes;
   if (ep.stat_sum)
     for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_s[i] = 0.f;  // visible after the prologue barrier
-  const uint32_t bar_off = (uint32_t)p.a_bufs * p.a_buf_bytes + (uint32_t)p.w_slots * p.w_bytes;
+  const uint32_t w_slot_bytes = (uint32_t)p.w_group * (uint32_t)p.w_bytes;
+  const uint32_t bar_off = (uint32_t)p.a_bufs * p.a_buf_bytes + (uint32_t)p.w_slots * w_slot_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxABufs + s); };
@@ -105,9 +121,11 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    for (int s = 0; s < p.a_bufs; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < p.w_slots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
-    ptx::mbar_init(accum_bar, 1);
+    // every issuing warp commits its own MMAs: the "empty" and "accumulators complete" barriers take n_iss arrivals
+    for (int s = 0; s < p.a_bufs; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), (uint32_t)p.n_iss); }
+    if (!p.merged)
+      for (int s = 0; s < p.w_slots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), (uint32_t)p.n_iss); }
+    ptx::mbar_init(accum_bar, (uint32_t)p.n_iss);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -136,16 +154,21 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::griddep_wait();  // the predecessor's activations / packed weights must be complete before the first load
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
+    long long dbg_wa = 0, dbg_ww = 0;
     const uint32_t a_op_bytes = (uint32_t)(p.a_sub_slabs * p.slabrows) * (uint32_t)p.row_bytes;
     const int ngroups = p.vol ? 1 : nyz;             // activation loads per 64-channel chunk
     const int ntaps = p.vol ? p.kx * nyz : p.kx;     // weight tiles per activation load
-    for (int yz = 0; yz < ngroups; ++yz) {
+    for (int it = 0; it < ngroups * p.kchunks; ++it) {
+      const int yz = p.chunk_major ? it % ngroups : it / p.kchunks;
+      const int ch = p.chunk_major ? it / ngroups : it % p.kchunks;
       const int tj = p.vol ? 0 : yz / p.kz, tl = p.vol ? 0 : yz % p.kz;
-      for (int ch = 0; ch < p.kchunks; ++ch) {
-        ptx::mbar_wait(a_empty(ab), aph ^ 1u);
+      {
+        if (p.dbg) { const long long c0 = clock64(); ptx::mbar_wait(a_empty(ab), aph ^ 1u); dbg_wa += clock64() - c0; }
+        else ptx::mbar_wait(a_empty(ab), aph ^ 1u);
+        const uint32_t a_tx = a_op_bytes * (uint32_t)p.a_ops;
         if (ptx::elect_one()) {
           // the halo box is fetched as a_ops independent TMA instructions (more requests in flight)
-          if (leader) ptx::mbar_expect_tx(a_full(ab), a_op_bytes * (uint32_t)p.a_ops * tx_mult);
+          if (leader) ptx::mbar_expect_tx(a_full(ab), (a_tx + (p.merged ? (uint32_t)ntaps * w_cta_bytes : 0u)) * tx_mult);
           for (int o = 0; o < p.a_ops; ++o) {
             const uint32_t d = smem_base + ab * p.a_buf_bytes + o * a_op_bytes;
             if (kPair)
@@ -157,23 +180,37 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         __syncwarp();
-        if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
-        for (int tt = 0; tt < ntaps; ++tt) {
-          // volume mode walks the packed taps in storage order (ti, tj, tl); otherwise the kx taps of this (tj, tl)
-          const int tap = p.tap_base + (p.vol ? tt : (tt * p.ky + tj) * p.kz + tl);
-          ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
+        for (int t0 = 0; t0 < ntaps; t0 += p.w_group) {
+          const int cnt = min(p.w_group, ntaps - t0);
+          // merged: the weight tiles of this K iteration live in slot `ab` and complete the halo buffer's barrier
+          const int slot = p.merged ? ab : wsl;
+          const uint32_t bar = p.merged ? a_full(ab) : w_full(wsl);
+          if (!p.merged) {
+            if (p.dbg) { const long long c0 = clock64(); ptx::mbar_wait(w_empty(wsl), wph ^ 1u); dbg_ww += clock64() - c0; }
+            else ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
+          }
           if (ptx::elect_one()) {
-            if (leader) ptx::mbar_expect_tx(w_full(wsl), w_cta_bytes * tx_mult);
-            if (kPair) ptx::tma_load_3d_2sm(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * p.kelems, w_row0, tap);
-            else ptx::tma_load_3d(w_base + wsl * p.w_bytes, &tmB, w_full(wsl), ch * p.kelems, w_row0, tap);
+            if (leader && !p.merged) ptx::mbar_expect_tx(bar, (uint32_t)cnt * w_cta_bytes * tx_mult);
+            for (int j = 0; j < cnt; ++j) {
+              // volume mode walks the packed taps in storage order (ti, tj, tl); otherwise the kx taps of this (tj, tl)
+              const int tt = t0 + j;
+              const int tap = p.tap_base + (p.vol ? tt : (tt * p.ky + tj) * p.kz + tl);
+              const uint32_t d = w_base + slot * w_slot_bytes + j * p.w_bytes;
+              if (kPair) ptx::tma_load_3d_2sm(d, &tmB, bar, ch * p.kelems, w_row0, tap);
+              else ptx::tma_load_3d(d, &tmB, bar, ch * p.kelems, w_row0, tap);
+            }
           }
           __syncwarp();
-          if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+          if (!p.merged && ++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
         }
+        if (++ab == p.a_bufs) { ab = 0; aph ^= 1u; }
       }
     }
-  } else if (warp == 1 && leader) {
-    // ===== MMA issuer (pair mode: the leader CTA only) =====
+    if (p.dbg && lane == 0) { p.dbg[8 * blockIdx.x + 5] = dbg_wa; p.dbg[8 * blockIdx.x + 6] = dbg_ww; }
+  }
+  if (warp >= 1 && warp - 1 < p.n_iss && leader) {
+    // ===== MMA issuers (pair mode: the leader CTA only): warps 1 .. n_iss; warps >= 2 go on to the epilogue =====
+    const int q = warp - 1;
     const uint32_t idesc = ptx::make_idesc(p.tf32 ? 2u : 1u, kPair ? 256u : 128u, (uint32_t)p.n_umma, 0u, 0u);
     const int k_per_row = p.row_bytes / 32;  // K steps per operand row: one instruction consumes 32 bytes of K
     // everything but the start address: SWIZZLE_128B (SBO = 8 rows x 128 B) or SWIZZLE_64B (layout type 4, SBO = 512;
@@ -186,15 +223,26 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aph = 0, wph = 0;
     const int ntaps = p.vol ? p.kx * nyz : p.kx;
     const int iters = (p.vol ? 1 : nyz) * p.kchunks;
+    long long dbg_wa = 0, dbg_ww = 0;
+    const bool dbg = p.dbg && q == 0;
+    const long long dbg_t0 = dbg ? clock64() : 0;
     for (int it = 0; it < iters; ++it) {
-      const int ch = it % p.kchunks;
+      const int ch = p.chunk_major ? it / (p.vol ? 1 : nyz) : it % p.kchunks;
       const int nk = (ch == p.kchunks - 1) ? p.last_k16 : k_per_row;
-      ptx::mbar_wait(a_full(ab), aph);
+      if (dbg) { const long long c0 = clock64(); ptx::mbar_wait(a_full(ab), aph); dbg_wa += clock64() - c0; }
+      else ptx::mbar_wait(a_full(ab), aph);
       const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
+      if (p.merged) ptx::tc_fence_after();
+      int gpos = 0;  // position inside the weight group
       for (int tt = 0; tt < ntaps; ++tt) {
-        ptx::mbar_wait(w_full(wsl), wph);
-        ptx::tc_fence_after();
-        const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_bytes) >> 4) & 0x3fffu);
+        const int tj_ = gpos;
+        const int slot = p.merged ? ab : wsl;
+        if (!p.merged && tj_ == 0) {
+          if (dbg) { const long long c0 = clock64(); ptx::mbar_wait(w_full(wsl), wph); dbg_ww += clock64() - c0; }
+          else ptx::mbar_wait(w_full(wsl), wph);
+          ptx::tc_fence_after();
+        }
+        const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + slot * w_slot_bytes + tj_ * p.w_bytes) >> 4) & 0x3fffu);
         const uint32_t acc0 = (it > 0 || tt > 0) ? 1u : 0u;
         // tap -> first A row.  Any 128-byte row of the 1024-byte-aligned tile is a valid SWIZZLE_128B operand
         // start with base_offset 0: the swizzle is a function of the absolute address bits
@@ -205,7 +253,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int tj = tyz / p.kz, tl = tyz - tj * p.kz;
           roff = ti * p.slabrows + tj * p.pitch_y + tl;
         }
-        for (int m = 0; m < p.t_m; ++m) {
+        for (int m = q; m < p.t_m; m += p.n_iss) {
           const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * (uint32_t)p.row_bytes;
           const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.n_umma);
@@ -237,9 +285,12 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
         }
-        if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(w_empty(wsl)); else ptx::mma_commit(w_empty(wsl)); }
-        __syncwarp();
-        if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+        if (++gpos == p.w_group) gpos = 0;
+        if (!p.merged && (gpos == 0 || tt == ntaps - 1)) {
+          if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(w_empty(wsl)); else ptx::mma_commit(w_empty(wsl)); }
+          __syncwarp();
+          if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+        }
       }
       if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(a_empty(ab)); else ptx::mma_commit(a_empty(ab)); }
       __syncwarp();
@@ -247,14 +298,22 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(accum_bar); else ptx::mma_commit(accum_bar); }
     __syncwarp();
-  } else if (warp >= 2) {
+    if (dbg && lane == 0) {
+      p.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;  // issue loop
+      p.dbg[8 * blockIdx.x + 1] = dbg_wa;              // ... of which waiting for halo tiles
+      p.dbg[8 * blockIdx.x + 2] = dbg_ww;              // ... and for weight tiles
+    }
+  }
+  if (warp >= 2) {
     // ===== epilogue =====
     const int sub = warp & 3;
     constexpr int kParts = kEpiWarps / 4;       // warps sharing one TMEM lane quarter
     const int part = (warp - 2) >> 2;           // this warp takes chunks part, part + kParts, ...
     ptx::griddep_wait();  // residual reads / output writes also order after the predecessor
+    const long long dbg_e0 = p.dbg ? clock64() : 0;
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
+    const long long dbg_e1 = p.dbg ? clock64() : 0;
     const EpiVec ev = make_epi_vec(dst, ep);
     const bool simple = epi_is_simple(ep);
     for (int m = 0; m < p.t_m; ++m) {
@@ -299,6 +358,10 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       flush_bn_stats(ep, stat_s, n0, p.n_umma, p.cn, (int)threadIdx.x - 64, 32 * kEpiWarps);
     }
     ptx::tc_fence_before();
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[8 * blockIdx.x + 3] = dbg_e1 - dbg_e0;    // prologue end -> accumulators complete
+      p.dbg[8 * blockIdx.x + 4] = clock64() - dbg_e1;  // epilogue
+    }
   }
 
   if (kPair) ptx::cluster_sync();
@@ -311,6 +374,27 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 constexpr int kSmemBudget = 222 * 1024;  // dynamic SMEM; 2 KB of static SMEM (BN partial sums) sit beside it
+
+// How many weight tiles share one barrier pair (Tc2Params::w_group / merged) under an SMEM budget: all `ntaps` of a K
+// iteration on the halo buffer's own barriers when two such stages fit, else the largest even split that leaves room
+// for `need_bufs` halo buffers and two weight-group slots.  Returns the barrier round trips per K iteration.
+int weight_grouping(int a_buf_bytes, int w_bytes, int ntaps, int budget, int need_bufs, int& w_group, int& merged) {
+  static const bool no_merge = getenv("WS_TC2_NO_MERGE") != nullptr;
+  static const int env_group = getenv("WS_TC2_WGROUP") ? atoi(getenv("WS_TC2_WGROUP")) : 0;
+  merged = 0;
+  if (!no_merge && env_group <= 0 && need_bufs * (a_buf_bytes + ntaps * w_bytes) + 2048 <= budget) {
+    merged = 1;
+    w_group = ntaps;
+    return 1;
+  }
+  int g = (budget - 2048 - need_bufs * a_buf_bytes) / (2 * w_bytes);
+  if (g > ntaps) g = ntaps;
+  if (g < 1) g = 1;
+  if (env_group > 0 && env_group < g) g = env_group;
+  const int ngr = (ntaps + g - 1) / g;
+  w_group = (ntaps + ngr - 1) / ngr;
+  return 1 + ngr;
+}
 
 // Pick (by, tx): minimise estimated SM-time = waves * max(MMA cycles, L2->SMEM cycles) per K iteration.
 bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool pair, Tc2Params& p) {
@@ -359,8 +443,17 @@ bool choose_cfg_search(int N, int DX, int DY, int DZ, int kx, int n_umma, bool p
       const long long per_sm = (ctas + 147) / 148;
       const int r = per_sm < cps ? (int)per_sm : cps;  // CTAs actually sharing an SM
       const long long waves = (ctas + 148LL * r - 1) / (148LL * r);
-      const double overhead = (150.0 * kx + 300.0) / r;
-      const double iter = (mma > load ? mma : load) * r + overhead;
+      // the issuing thread: ~170 cycles per group of 4 MMAs, ~500 per barrier round trip (wait + fence + commit);
+      // co-resident CTAs issue independently
+      int wg, mg;
+      const int syncs = weight_grouping(a_bytes, w_bytes, kx, r >= 2 ? (227 * 1024) / 2 - 1024 - 2048 : kSmemBudget, 2, wg, mg);
+      // (an issuing warp is busy for its MMAs' execution time plus ~200 cycles of scalar work per group of 4; up to 4
+      // warps issue, one accumulator each)
+      const int n_iss = t_m < 4 ? t_m : 4;
+      const double issue = (double)((t_m + n_iss - 1) / n_iss) * kx * (4.0 * per_mma + 200.0) + 500.0 * syncs;
+      double iter = (mma > load ? mma : load) * r;
+      if (issue > iter) iter = issue;
+      iter += 100.0;
       // fixed per-CTA cost (prologue, pipeline ramp, epilogue of t_m tiles) in units of iterations' cycles
       const double cost = (double)waves * (iter + (6000.0 + 2500.0 * t_m) / 30.0);
       if (cost < best) {
@@ -552,26 +645,39 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   }
   // SMEM budget: the whole SM for one resident CTA, half of it when the config was costed with two
   const int budget = p.a_bufs >= 2 ? (227 * 1024) / 2 - 1024 - 2048 : kSmemBudget;  // 2 KB static SMEM per CTA
-  // weight ring: at least kx + 1 slots when they fit, then as many halo buffers as the rest allows
-  p.w_slots = p.kx + 1 > kMaxWSlots ? kMaxWSlots : (p.kx + 1 < 3 ? 3 : p.kx + 1);
-  {
-    const int need_bufs = (vol && p.kchunks == 1) ? 1 : 2;
-    while (p.w_slots > 2 && need_bufs * p.a_buf_bytes + p.w_slots * p.w_bytes + 2048 > budget) --p.w_slots;
-  }
-  p.a_bufs = (budget - 2048 - p.w_slots * p.w_bytes) / p.a_buf_bytes;
-  if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
-  if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
+  const int ntaps_it = vol ? p.kx * p.ky * p.kz : p.kx;  // weight tiles per halo load
   const int loads = (vol ? 1 : p.ky * p.kz) * p.kchunks;  // activation loads of the whole kernel
-  if (p.a_bufs > loads) p.a_bufs = loads;
-  if (p.a_bufs < (loads > 1 ? 2 : 1) || p.w_slots < 2) return -1;
-  {
-    int spare = (budget - 2048 - p.a_bufs * p.a_buf_bytes) / p.w_bytes;
+  const int need_bufs = loads > 1 ? 2 : 1;
+  weight_grouping(p.a_buf_bytes, p.w_bytes, ntaps_it, budget, need_bufs, p.w_group, p.merged);
+  const int w_slot = p.w_group * p.w_bytes;
+  if (p.merged) {
+    p.a_bufs = (budget - 2048) / (p.a_buf_bytes + w_slot);
+    if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
+    if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
+    if (p.a_bufs > loads) p.a_bufs = loads;
+    if (p.a_bufs < need_bufs) return -1;
+    p.w_slots = p.a_bufs;
+  } else {
+    // two weight-group slots, as many halo buffers as the rest allows, then spare room back to the weight ring
+    p.w_slots = 2;
+    if (need_bufs * p.a_buf_bytes + p.w_slots * w_slot + 2048 > budget) return -1;
+    p.a_bufs = (budget - 2048 - p.w_slots * w_slot) / p.a_buf_bytes;
+    if (p.a_bufs > kMaxABufs) p.a_bufs = kMaxABufs;
+    if (p.a_bufs > env_bufs) p.a_bufs = env_bufs < 2 ? 2 : env_bufs;
+    if (p.a_bufs > loads) p.a_bufs = loads;
+    if (p.a_bufs < need_bufs) return -1;
+    int spare = (budget - 2048 - p.a_bufs * p.a_buf_bytes) / w_slot;
     if (spare > kMaxWSlots) spare = kMaxWSlots;
     if (spare > p.w_slots) p.w_slots = spare;
   }
   uint32_t cols = 32;
   while ((int)cols < p.t_m * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
+  static const int env_niss = getenv("WS_TC2_NISS") ? atoi(getenv("WS_TC2_NISS")) : 4;
+  p.n_iss = p.t_m < 4 ? p.t_m : 4;
+  if (p.n_iss > env_niss) p.n_iss = env_niss < 1 ? 1 : env_niss;
+  static const int env_cm = getenv("WS_TC2_CHUNK_MAJOR") ? atoi(getenv("WS_TC2_CHUNK_MAJOR")) : -1;
+  p.chunk_major = env_cm >= 0 ? (env_cm != 0) : (p.kchunks > 1 && p.last_k16 < p.row_bytes / 32);
   if (dry) return 0;
 
   MapKey ka;
@@ -600,7 +706,7 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   kb.estr[0] = kb.estr[1] = kb.estr[2] = 1;
   if (int e = get_tensor_map(kb, &tmB)) return e;
 
-  size_t smem = (size_t)p.a_bufs * p.a_buf_bytes + (size_t)p.w_slots * p.w_bytes +
+  size_t smem = (size_t)p.a_bufs * p.a_buf_bytes + (size_t)p.w_slots * p.w_group * p.w_bytes +
                 8 * (2 * kMaxABufs + 2 * kMaxWSlots + 2) + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -617,6 +723,15 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 225 * 1024, "conv_tc2: smem request %zu too large", smem);
   const unsigned tiles = (unsigned)(p.N * p.tiles_x * p.tiles_y);
+  // WS_TC2_DEBUG_TIMES=1: per-CTA stage cycle counts (clock64), printed as means after a blocking sync — profiling only
+  static const bool dbg_on = getenv("WS_TC2_DEBUG_TIMES") && atoi(getenv("WS_TC2_DEBUG_TIMES")) != 0;
+  static long long* dbg_buf = nullptr;
+  const size_t dbg_ctas = (size_t)(tiles + 1) * (size_t)n_tiles;
+  if (dbg_on && dbg_ctas <= 16384) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16384 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, dbg_ctas * 8 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
   // 8 epilogue warps when the CTA cannot share its SM anyway (SMEM) and there is more than one chunk per warp
   static const int env_epi = getenv("WS_TC2_EPI8") ? atoi(getenv("WS_TC2_EPI8")) : -1;
   const bool single = smem > 113 * 1024 || pair;
@@ -636,6 +751,25 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
       WS_CHECK_CUDA(launch_pdl(conv3d_tc2_kernel<true, 4>, grid, dim3(192), smem, st, 2, tmA, tmB, p, dst, ep));
   }
   WS_POST_LAUNCH(1);
+  if (p.dbg) {
+    cudaStreamSynchronize(st);
+    std::vector<long long> h(dbg_ctas * 8);
+    cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[8] = {0};
+    long long n_mma = 0, n_all = 0;
+    for (size_t c = 0; c < dbg_ctas; ++c) {
+      if (h[8 * c + 0]) { ++n_mma; for (int j = 0; j < 3; ++j) sum[j] += (double)h[8 * c + j]; }
+      if (h[8 * c + 4]) { ++n_all; for (int j = 3; j < 7; ++j) sum[j] += (double)h[8 * c + j]; }
+    }
+    if (n_mma && n_all)
+      fprintf(stderr,
+              "[tc2 dbg] pair=%d by=%d tx=%d t_m=%d a_bufs=%d w_slots=%d w_group=%d merged=%d n_iss=%d kchunks=%d grid=%u | issue loop %.0f cyc (wait halo %.0f, "
+              "wait weights %.0f) | accumulators ready after %.0f, epilogue %.0f | producer waits: halo slot %.0f, weight "
+              "slot %.0f | MMA floor %.0f\n",
+              (int)pair, p.by, p.tx, p.t_m, p.a_bufs, p.w_slots, p.w_group, p.merged, p.n_iss, p.kchunks, tiles, sum[0] / n_mma, sum[1] / n_mma,
+              sum[2] / n_mma, sum[3] / n_all, sum[4] / n_all, sum[5] / n_all, sum[6] / n_all,
+              (double)p.t_m * p.kx * p.ky * p.kz * (4.0 * (p.kchunks - 1) + p.last_k16) * (p.n_umma / 2.0 > 72.0 ? p.n_umma / 2.0 : 72.0));
+  }
   return 0;
 }
 

@@ -34,7 +34,7 @@ namespace ws {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 288;  // warp 0: TMA producer, warps 1-4: MMA issuers (warp 1 owns TMEM), warps 5-8: epilogue
 constexpr int kMaxBSlots = 6;
 
 struct WgParams {
@@ -56,8 +56,14 @@ struct WgParams {
   int tf32;              // 1: fp32 operands, kind::tf32 — 32 channels per 128-byte row, 8 voxel rows per instruction
   int a_slot_bytes, b_slot_bytes, b_slots;
   uint32_t tmem_cols;
-  // workspace addressing: wsp[tap * tap_stride + m * m_stride + n * n_stride]
+  // workspace addressing: wsp[range * range_stride + tap * tap_stride + m * m_stride + n * n_stride]
   long long tap_stride, m_stride, n_stride;
+  long long range_stride;  // batched launches (one tile range per residual dense block): a result per range
+  int n_iss;               // MMA-issuing warps (1..4, <= taps_per_cta): issuer q owns the accumulators of taps q, q + n_iss, ...
+                           // (a tcgen05.mma occupies its issuing thread about as long as it executes, so barrier waits,
+                           // commits and descriptor arithmetic of ONE issuer are tensor-pipe idle time — conv_tc2.cu)
+  int plain_store;         // 1: every output element has exactly one segment -> st.global instead of red.global.add
+  int mz;                  // > 0: the M block index is blockIdx.x % mz (CTAs of one range adjacent in launch order)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -81,8 +87,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (6 + 2 * kMaxBSlots));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = p.m0 + (int)blockIdx.z * 128;                       // this CTA's 128-row M block
-  const int m_valid = min(128, p.m_total - (int)blockIdx.z * 128);
+  const int mblk = p.mz > 0 ? (int)(blockIdx.x % (unsigned)p.mz) : (int)blockIdx.z;
+  const long long bx_lin = p.mz > 0 ? (long long)(blockIdx.x / (unsigned)p.mz) : (long long)blockIdx.x;
+  const int m0 = p.m0 + mblk * 128;                                  // this CTA's 128-row M block
+  const int m_valid = min(128, p.m_total - mblk * 128);
   const int cblk = p.tf32 ? 32 : 64;  // channels per 128-byte operand row
   const int m_blocks = (m_valid + cblk - 1) / cblk;
   // Work = (tile range, tap group, tile) items in that order; CTA b owns items [b*per, (b+1)*per): the same load for
@@ -91,16 +99,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   // pass and re-used out of L2 by the other tap groups (ncu: 27 GB of DRAM reads per launch in group-major order).
   // A run that crosses a (range, group) boundary is processed as consecutive SEGMENTS, each with its own accumulate
   // / reduce phase.
-  const long long item_lo = (long long)blockIdx.x * p.items_per_cta;
+  const long long item_lo = bx_lin * p.items_per_cta;
   const long long item_hi = min(p.items, item_lo + p.items_per_cta);
 
   if (threadIdx.x == 0) ptx::griddep_launch();  // programmatic dependent launch, see conv_tc2.cu
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmM);
     ptx::prefetch_tmap(&tmN);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), (uint32_t)p.n_iss); }
     for (int s = 0; s < p.b_slots; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    ptx::mbar_init(accum_bar, 1);
+    ptx::mbar_init(accum_bar, (uint32_t)p.n_iss);
     ptx::mbar_init(tmem_free, 4);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
   }
@@ -122,8 +130,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     ptx::griddep_wait();
     if (has_work) {
       // ===== TMA producer =====
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      // the ring of shifted-operand slots is split into one private ring per issuing warp (slots_per slots each): a
+      // barrier then has exactly one consumer, which sees every one of its phases in order
+      const int slots_per = p.b_slots / p.n_iss;
+      uint32_t bstate = 0;  // per issuer q a nibble: position in its private ring (3 bits) | phase << 3
       // the unshifted operand (dy) is the one that is NOT x
       const CUtensorMap* tm_fix = p.shift_on_m ? &tmN : &tmM;
       const CUtensorMap* tm_sh = p.shift_on_m ? &tmM : &tmN;
@@ -155,6 +167,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
           const int cx = x0 * p.sx - p.px + ti, cy = y0 * p.sy - p.py + tj, cz = z0 * p.sz - p.pz + tl;
+          const int q = (tap - tap_lo) % p.n_iss;
+          const uint32_t nib = (bstate >> (4 * q)) & 0xfu;
+          const int pos = (int)(nib & 7u);
+          const uint32_t bph = nib >> 3;
+          const int bs = q * slots_per + pos;
+          const uint32_t nxt = pos + 1 == slots_per ? ((bph ^ 1u) << 3) : (nib + 1u);
+          bstate = (bstate & ~(0xfu << (4 * q))) | (nxt << (4 * q));
           ptx::mbar_wait(b_empty(bs), bph ^ 1u);
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(b_full(bs), blk_bytes * sh_blocks);
@@ -163,13 +182,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
                                cy, cx, n);
           }
           __syncwarp();
-          if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  }
+  if (warp >= 1 && warp - 1 < p.n_iss) {
     if (has_work) {
-      // ===== MMA issuer =====
+      // ===== MMA issuers: warps 1 .. n_iss =====
+      const int q = warp - 1;
       const uint32_t idesc = ptx::make_idesc(p.tf32 ? 2u : 1u, 128u, (uint32_t)p.n_umma, 1u, 1u);  // both MN-major
       // bf16: SWIZZLE_128B, K atoms of 8 rows (SBO = 1024 B).  tf32: the MN-major operand must use the 32-byte-atom
       // flavour of the 128-byte swizzle (layout type 1), whose K atoms are 4 rows (SBO = 512 B); LBO = one channel block
@@ -177,8 +197,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           p.tf32 ? (((uint64_t)((blk_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) |
                     ((uint64_t)1 << 61))
                  : ptx::make_smem_desc_sw128(0, blk_bytes, 1024);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      const int slots_per = p.b_slots / p.n_iss;
+      int bpos = 0;  // position / phase in this issuer's private ring
+      uint32_t bph = 0;
       // one instruction consumes 16 voxel rows of bf16 (2048 B of the MN-major tile) or 8 rows of tf32 (1024 B)
       const int krows = p.tf32 ? 8 : 16;
       const int k16 = p.rows / krows;
@@ -202,7 +225,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         if (tile >= p.total_tiles) continue;  // tail of the last range (never the first item of a segment)
         ptx::mbar_wait(a_full(as), aph);
         const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
-        for (int tp = 0; tp < ntap; ++tp) {
+        for (int tp = q; tp < ntap; tp += p.n_iss) {  // the other taps belong to other issuers (and their rings)
+          const int bs = q * slots_per + bpos;
           ptx::mbar_wait(b_full(bs), bph);
           ptx::tc_fence_after();
           const uint32_t sh_addr = b_base + bs * p.b_slot_bytes;
@@ -223,7 +247,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
             ptx::mma_commit(b_empty(bs));
           }
           __syncwarp();
-          if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+          if (++bpos == slots_per) { bpos = 0; bph ^= 1u; }
         }
         if (ptx::elect_one()) ptx::mma_commit(a_empty(as));
         __syncwarp();
@@ -233,7 +257,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       if (ptx::elect_one()) ptx::mma_commit(accum_bar);
       __syncwarp();
     }
-  } else if (has_work) {
+  }
+  if (warp >= 5 && has_work) {
     // ===== epilogue: TMEM -> red.global.add into the fp32 workspace, once per segment =====
     const int sub = warp & 3;
     const int m = sub * 32 + lane;
@@ -243,6 +268,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       const int tap_lo = (int)((item / p.range_tiles) % p.tap_groups) * p.taps_per_cta;
       const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
       const long long seg_end = min(item_hi, (item / p.range_tiles + 1) * p.range_tiles);
+      float* wrange = wsp + ((item / p.range_tiles) / p.tap_groups) * p.range_stride;
       ptx::mbar_wait(accum_bar, (uint32_t)(seg & 1));
       ptx::tc_fence_after();
       for (int tp = 0; tp < ntap; ++tp) {
@@ -253,11 +279,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
           ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(tp * p.n_umma + c0), r);
           ptx::tmem_ld_wait();
           if (m < m_valid) {
-            float* dst = wsp + (long long)tap * p.tap_stride + (long long)(m0 + m) * p.m_stride +
+            float* dst = wrange + (long long)tap * p.tap_stride + (long long)(m0 + m) * p.m_stride +
                          (long long)(p.n0 + c0) * p.n_stride;
+            if (p.plain_store) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.n_valid) atomicAdd(dst + (long long)j * p.n_stride, __uint_as_float(r[j]));
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.n_valid) dst[(long long)j * p.n_stride] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.n_valid) atomicAdd(dst + (long long)j * p.n_stride, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -325,8 +357,15 @@ size_t tc_wgrad_workspace_bytes(const ConvGeom& g) {
 
 // One launch: M rows = channels [m0, m0+m_count) of the M operand, N cols = channels [n0, n0+n_count) of the
 // N operand.  swap == 0: M = cout (dy), N = cin (x).  swap == 1: M = cin (x), N = cout (dy).
+// batch: the launch covers `ranges` independent problems of identical geometry laid out back to back along the batch
+// dimension (g.n = ranges * samples per problem): one tile range per problem, results `range_stride` floats apart,
+// written with plain stores (every output element belongs to exactly one segment).
+struct WgBatch {
+  int ranges;
+  long long range_stride;
+};
 static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* wsp, int swap, int m_total,
-                      int n0, int n_count, cudaStream_t st) {
+                      int n0, int n_count, cudaStream_t st, const WgBatch* batch = nullptr) {
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.n;
@@ -385,6 +424,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
         const long long fill = 148LL * k * gpc / ((long long)tg * mz);
         if (fill >= 1) cand[ncand++] = fill;
       }
+      if (batch) { ncand = 0; cand[ncand++] = batch->ranges; }
       for (int ci = 0; ci < ncand; ++ci) {
         long long S = cand[ci];                    // tile ranges
         if (S > p.total_tiles) continue;
@@ -392,7 +432,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
         S = (p.total_tiles + R - 1) / R;
         const long long ncta = (S * tg + gpc - 1) / gpc;
         const long long ctas = ncta * mz;
-        if (ctas > 444) continue;
+        if (ctas > 444 && !batch) continue;
+        if (batch && S != batch->ranges) continue;  // one tile range per problem
         const long long waves = (ctas + 147) / 148;
         const long long per = (long long)gpc * R;
         // CTAs that walk the same tiles at the same time: L2 serves their re-reads (good), but past ~2 dozen the
@@ -414,7 +455,17 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     }
   }
   // experiment hook: WS_WGRAD_FORCE="taps_per_cta,groups_per_cta,tile_ranges" (read at every launch)
-  if (const char* f = getenv("WS_WGRAD_FORCE")) {
+  if (batch) {
+    // experiment hook of the batched launches: WS_TRUNK_WGRAD_FORCE="taps_per_cta,groups_per_cta"
+    if (const char* f = getenv("WS_TRUNK_WGRAD_FORCE")) {
+      int ftpc = 0, fgpc = 0;
+      if (sscanf(f, "%d,%d", &ftpc, &fgpc) == 2 && ftpc >= 1 && ftpc <= max_tpc && ftpc <= p.taps && fgpc >= 1) {
+        best_tpc = ftpc;
+        best_gpc = fgpc;
+      }
+    }
+    best_range = p.total_tiles / batch->ranges;
+  } else if (const char* f = getenv("WS_WGRAD_FORCE")) {
     int ftpc = 0, fgpc = 0, fs = 0;
     if (sscanf(f, "%d,%d,%d", &ftpc, &fgpc, &fs) == 3 && ftpc >= 1 && ftpc <= max_tpc && fgpc >= 1 && fs >= 1) {
       best_tpc = ftpc;
@@ -434,6 +485,10 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   uint32_t cols = 32;
   while ((int)cols < p.taps_per_cta * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
+  static const int env_niss = getenv("WS_WGRAD_NISS") ? atoi(getenv("WS_WGRAD_NISS")) : 4;
+  p.n_iss = p.taps_per_cta < 4 ? p.taps_per_cta : 4;
+  if (p.n_iss > env_niss) p.n_iss = env_niss < 1 ? 1 : env_niss;
+  while (p.n_iss > 1 && p.b_slots / p.n_iss < 2) --p.n_iss;  // two slots of its private ring per issuer
 
   // workspace layout: the M index is always the contiguous one, so that the 32 lanes of an epilogue warp (one
   // accumulator row each) hit consecutive floats with every red.global.add — [tap][cout][cin] when M = cin
@@ -441,6 +496,13 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   p.tap_stride = (long long)g.cout * g.cin;
   p.m_stride = 1;
   p.n_stride = swap ? g.cin : g.cout;
+  if (batch) {
+    WS_REQUIRE(p.total_tiles % batch->ranges == 0 && p.range_tiles == p.total_tiles / batch->ranges,
+               "wgrad: batched launch needs whole tile ranges (%lld tiles, %d problems)", p.total_tiles, batch->ranges);
+    p.range_stride = batch->range_stride;
+    p.plain_store = 1;
+    p.mz = mz;
+  }
 
   auto make_map = [&](const View& v, int channels, int X, int Y, int Z, bool strided, CUtensorMap* out) -> int {
     MapKey k;
@@ -475,6 +537,7 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   WS_REQUIRE(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
   dim3 grid((unsigned)ncta, 1u, (unsigned)mz);
+  if (batch) grid = dim3((unsigned)(ncta * mz), 1u, 1u);
   if (!swap) WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_dy, tm_x, p, wsp));
   else WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_x, tm_dy, p, wsp));
   WS_POST_LAUNCH(1);
@@ -579,6 +642,90 @@ int tc_rdb_wgrad(const ConvGeom& gm, const View& x, const View& g, float* const*
   if (blocks > 148 * 2) blocks = 148 * 2;
   WS_CHECK_CUDA(launch_pdl(wgrad_tc_finalize_rdb, dim3((unsigned)blocks, (unsigned)nconv), dim3(256), 0, st, 1, wsp, t,
                            gm.taps(), gc, gm.cin, gm.cout));
+  WS_POST_LAUNCH(1);
+  return 0;
+}
+
+
+// ---- weight gradients of a whole run of identical residual dense blocks as batched launches ----------------------
+// Per block the voxel count (20 480 at the shipped size) is too small for a split-K GEMM to amortise its reduce
+// epilogue: 48 x (merged dense GEMM 63 us + LFF GEMM 61 us + 2 finalize + bias sums) was 7 ms of a 45 ms step.  The
+// blocks' operands (concat buffers, g, g_lff) are kept in slabs with the block index outermost, so the batch dimension
+// of the tensor maps runs over (block, sample) and ONE launch does every block: a CTA owns (block, tap group, M block)
+// with the full voxel range as its K loop — no split-K, no atomics, plain stores.
+namespace {
+struct TrunkLayout {
+  int nconv, gc, taps, wcin, wcout;
+  int cin[8];
+  long long off[8];        // offset of dw_i inside a block's gradient record (floats)
+  long long block_stride;  // floats between the gradient records of consecutive blocks
+  long long ws_stride;     // floats between the workspace results of consecutive blocks
+};
+// one CTA per (co, conv, block): the 27 taps' rows [ci] are contiguous in the workspace, the output row
+// dw[co][ci][tap] is contiguous too — transpose through shared memory
+__global__ void __launch_bounds__(256)
+wgrad_tc_finalize_trunk(const float* __restrict__ wsp, float* __restrict__ grads, const TrunkLayout t) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ float tile[];  // [taps][cin + 1]
+  const int co = blockIdx.x, i = blockIdx.y, r = blockIdx.z;
+  const int cin = t.cin[i], pitch = cin + 1;
+  const float* src = wsp + (long long)r * t.ws_stride;
+  for (int e = threadIdx.x; e < t.taps * cin; e += blockDim.x) {
+    const int tap = e / cin, ci = e % cin;
+    tile[tap * pitch + ci] = src[((long long)tap * t.wcout + (i * t.gc + co)) * t.wcin + ci];
+  }
+  __syncthreads();
+  float* dst = grads + (long long)r * t.block_stride + t.off[i] + (long long)co * cin * t.taps;
+  for (int e = threadIdx.x; e < t.taps * cin; e += blockDim.x) {
+    const int ci = e / t.taps, tap = e % t.taps;
+    dst[e] = tile[tap * pitch + ci];
+  }
+}
+}  // namespace
+
+size_t tc_trunk_wgrad_workspace_bytes(int nblocks, int taps, int cin_max, int nconv, int gc) {
+  return (size_t)nblocks * tc_rdb_wgrad_workspace_bytes(taps, cin_max, nconv, gc);
+}
+
+// gm / gl: the merged dense pseudo conv and the LFF conv of ONE block, with n = nblocks * samples.  buf / g / g_lff:
+// views of block 0; block r starts n_samples * nstride elements later.  grads: per block a record
+// [dw_0 | ... | dw_{nconv-1} | dw_lff | db_lff] (torch layouts), block_stride floats apart.
+int tc_trunk_wgrad(const ConvGeom& gm, const ConvGeom& gl, int nblocks, const View& buf, const View& g,
+                   const View& g_lff, const int* cin, int nconv, int gc, float* grads, long long block_stride,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const size_t need = tc_trunk_wgrad_workspace_bytes(nblocks, gm.taps(), gm.cin, nconv, gc);
+  WS_REQUIRE(workspace && workspace_bytes >= need, "trunk wgrad workspace too small: %zu < %zu", workspace_bytes, need);
+  WS_REQUIRE(nconv >= 1 && nconv <= 8 && gm.cout == nconv * gc && gm.cout <= 256, "trunk wgrad: bad channel layout");
+  WS_REQUIRE(gl.taps() == 1, "trunk wgrad: the batched LFF gradient is the 1x1x1 case");
+  TrunkLayout t;
+  memset(&t, 0, sizeof(t));
+  t.nconv = nconv; t.gc = gc; t.taps = gm.taps(); t.wcin = gm.cin; t.wcout = gm.cout;
+  long long off = 0;
+  int cmax = 0;
+  for (int i = 0; i < nconv; ++i) {
+    t.cin[i] = cin[i];
+    t.off[i] = off;
+    off += (long long)gc * cin[i] * gm.taps();
+    if (cin[i] > cmax) cmax = cin[i];
+  }
+  const long long off_lff = off;
+  t.block_stride = block_stride;
+  t.ws_stride = (long long)gm.taps() * gm.cin * gm.cout;
+  float* wsp = (float*)workspace;
+  // dense convs: M = concat-buffer channels (shifted operand), N = the nconv*gc gradient channels
+  WgBatch bd = {nblocks, t.ws_stride};
+  if (int e = launch_one(gm, buf, g, wsp, 1, gm.cin, 0, gm.cout, st, &bd)) return e;
+  // LFF (1x1x1): with M = cin the M-contiguous result [co][ci] IS torch's layout — straight into the record
+  WgBatch bl = {nblocks, block_stride};
+  for (int n0 = 0; n0 < gl.cout; n0 += 256) {
+    const int nc = gl.cout - n0 < 256 ? gl.cout - n0 : 256;
+    if (int e = launch_one(gl, buf, g_lff, grads + off_lff, 1, gl.cin, n0, nc, st, &bl)) return e;
+  }
+  const size_t smem = (size_t)gm.taps() * (cmax + 1) * sizeof(float);
+  WS_REQUIRE(smem <= 48 * 1024, "trunk wgrad finalize: tile too large");
+  WS_CHECK_CUDA(launch_pdl(wgrad_tc_finalize_trunk, dim3((unsigned)gc, (unsigned)nconv, (unsigned)nblocks), dim3(256),
+                           smem, st, 1, (const float*)wsp, grads, t));
   WS_POST_LAUNCH(1);
   return 0;
 }

@@ -869,6 +869,146 @@ class RDBFn(torch.autograd.Function):
         return (dx, douter, None, *grads)
 
 
+def trunk_batched_enabled() -> bool:
+    return os.environ.get("WINDSR_TRUNK_BATCH", "1") != "0"
+
+
+def trunk_supported(h: torch.Tensor, sig) -> bool:
+    """Does ``ws_trunk_wgrad`` cover blocks of this geometry (sig: torch_blocks._trunk_signature) at h's size?"""
+    f, gc, nconv, k = sig[0], sig[1], sig[2], sig[3]
+    n, c, X, Y, Z = h.shape
+    if c != f:
+        return False
+    desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, 1, 0.2, 1.0, 1.0, 0.0, math_mode(), 0)
+    return bool(load().ws_trunk_wgrad_supported(C.byref(desc)))
+
+
+class TrunkFn(torch.autograd.Function):
+    """A run of identical residual dense blocks — the RRDB trunk (torch_blocks.py:293-330, 16 x 3 RDBs in the shipped
+    generator) — as ONE autograd node.
+
+    Forward is the chain of ``ws_rdb_forward`` calls of ``RDBFn``, with every block's concat buffer living in one slab
+    (block index outermost).  Backward runs the blocks' data-gradient chains (``ws_rdb_backward`` with dw = NULL, g and
+    g_lff into slabs as well) and then ``ws_trunk_wgrad``: the weight gradients of ALL blocks as one set of batched
+    launches (a CTA owns (block, tap group) with the block's full voxel range as its K loop — no split-K, no atomics)
+    instead of 48 x (merged GEMM + LFF GEMM + finalize + bias sums).  The parameter gradients are views of one flat
+    fp32 tensor.
+
+    cfg: nconv, slope, blocks = [dict(alpha, beta1, beta2, outer = index of the block whose INPUT is the outer skip
+    of this block or None, state)].  params: per block w0..w{k-1}, w_lff, b_lff.
+    """
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        _require_cuda(x)
+        lib = load()
+        nconv, blocks = cfg["nconv"], cfg["blocks"]
+        R, per = len(blocks), nconv + 2
+        n, f, X, Y, Z = x.shape
+        gc = params[0].shape[0]
+        k, kl = params[0].shape[2], params[nconv].shape[2]
+        ctot = f + nconv * gc
+        cdt = act_dtype()
+        dev = x.device
+        _AUX_JOIN_QUEUED[0] = False
+        slab = torch.empty((R * n, X, Y, Z, ctot), dtype=cdt, device=dev).permute(0, 4, 1, 2, 3)
+        inputs = {}
+        want_in = {b["outer"] for b in blocks if b["outer"] is not None}
+        h = x
+        wsp = None
+        for r, b in enumerate(blocks):
+            if r in want_in:
+                inputs[r] = h
+            outer = inputs.pop(b["outer"]) if b["outer"] is not None else None
+            desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], b["alpha"], b["beta1"],
+                                  b["beta2"] if outer is not None else 0.0, math_mode(), 0)
+            p = params[r * per:(r + 1) * per]
+            packed, desc.repack = b["state"].buffers(desc, p, 0)
+            buf = slab[r * n:(r + 1) * n]
+            out = empty_cl(n, f, X, Y, Z, torch.float32, dev)
+            if wsp is None:
+                wsp = _workspace(int(lib.ws_rdb_forward_workspace_bytes(C.byref(desc))), dev)
+            xv, bv, ov = view(h), view(buf), view(out)
+            outer_v = view(outer) if outer is not None else null_view()
+            wd = [t.detach() for t in p[:nconv + 1]]
+            check(lib.ws_rdb_forward(C.byref(desc), C.byref(xv), C.byref(outer_v), C.byref(bv), C.byref(ov),
+                                     _ptr_array(wd), _ptr_array(packed), ptr(p[nconv + 1]), wsp.data_ptr(), wsp.numel(),
+                                     stream_ptr()), "ws_rdb_forward")
+            h = out
+        ctx.cfg = cfg
+        ctx.geom = (n, X, Y, Z, f, gc, nconv, k, kl)
+        ctx.save_for_backward(slab, *params)
+        return h
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = load()
+        slab, *params = ctx.saved_tensors
+        cfg = ctx.cfg
+        nconv, blocks = cfg["nconv"], cfg["blocks"]
+        R, per = len(blocks), nconv + 2
+        n, X, Y, Z, f, gc, nconv, k, kl = ctx.geom
+        ctot = f + nconv * gc
+        cdt = act_dtype()
+        dev = dy.device
+        need = ctx.needs_input_grad
+        need_params = any(need[2:])
+        if dy.dtype != torch.float32 or not _linear_voxels(dy):
+            dy = dy.float().contiguous(memory_format=torch.channels_last_3d)
+        dbuf = empty_cl(n, ctot, X, Y, Z, torch.float32, dev)
+        g_lff = torch.empty((R * n, X, Y, Z, f), dtype=cdt, device=dev).permute(0, 4, 1, 2, 3)
+        g = torch.empty((R * n, X, Y, Z, nconv * gc), dtype=cdt, device=dev).permute(0, 4, 1, 2, 3)
+        wsp = None
+        pending = {}  # block index -> gradient that reaches its INPUT through an outer skip
+        desc0 = None
+        for r in range(R - 1, -1, -1):
+            b = blocks[r]
+            has_outer = b["outer"] is not None
+            desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], b["alpha"], b["beta1"],
+                                  b["beta2"] if has_outer else 0.0, math_mode(), 0)
+            desc0 = desc
+            p = params[r * per:(r + 1) * per]
+            packed, desc.repack = b["state"].buffers(desc, p, 1)
+            if wsp is None:
+                wsp = _workspace(int(lib.ws_rdb_backward_workspace_bytes(C.byref(desc))), dev)
+            if has_outer:
+                pending[b["outer"]] = (dy, b["beta2"])
+            want_dx = r > 0 or need[0] or r in pending
+            dx = empty_cl(n, f, X, Y, Z, torch.float32, dev) if want_dx else None
+            dyv, bv, dbv = view(dy), view(slab[r * n:(r + 1) * n]), view(dbuf)
+            glv, gv = view(g_lff[r * n:(r + 1) * n]), view(g[r * n:(r + 1) * n])
+            dxv = view(dx) if dx is not None else null_view()
+            wd = [t.detach() for t in p[:nconv + 1]]
+            check(lib.ws_rdb_backward(C.byref(desc), C.byref(dyv), C.byref(bv), C.byref(dbv), C.byref(glv), C.byref(gv),
+                                      C.byref(dxv), _ptr_array(wd), _ptr_array(packed), None, None,
+                                      wsp.data_ptr(), wsp.numel(), stream_ptr(), None, None, 0), "ws_rdb_backward")
+            if r in pending and dx is not None:
+                skip, beta2 = pending.pop(r)
+                axpby(dx, 1.0, skip, float(beta2), dx)
+            dy = dx
+        grads = [None] * (R * per)
+        if need_params:
+            rec = int(lib.ws_trunk_wgrad_record_floats(C.byref(desc0)))
+            flat = torch.empty((R, rec), dtype=torch.float32, device=dev)
+            nbytes = int(lib.ws_trunk_wgrad_workspace_bytes(C.byref(desc0), R))
+            wws = _workspace(nbytes, dev)
+            bv, gv, glv = view(slab[:n]), view(g[:n]), view(g_lff[:n])
+            with _timed("trunk_wgrad", None):
+                check(lib.ws_trunk_wgrad(C.byref(desc0), R, C.byref(bv), C.byref(gv), C.byref(glv), flat.data_ptr(), rec,
+                                         wws.data_ptr(), wws.numel(), stream_ptr()), "ws_trunk_wgrad")
+            for r in range(R):
+                off = 0
+                for i in range(per):
+                    p = params[r * per + i]
+                    if p is None:
+                        continue
+                    cnt = p.numel()
+                    if need[2 + r * per + i]:
+                        grads[r * per + i] = flat[r, off:off + cnt].view(p.shape)
+                    off += cnt
+        return (dy if need[0] else None, None, *grads)
+
+
 # ------------------------------------------------------------------------------------------------------
 # autograd: nearest upsample, concat, elementwise
 # ------------------------------------------------------------------------------------------------------

@@ -193,6 +193,19 @@ int ws_rdb_backward(const ws_rdb_desc* d, const ws_tensor* dy, const ws_tensor* 
                     size_t workspace_bytes, void* stream, void* aux_stream, void* aux_workspace,
                     size_t aux_workspace_bytes);
 
+/* ---- weight gradients of a run of identical residual dense blocks, batched (torch_blocks.py:256-290 x 48) ------- */
+/* The weight-gradient half of convolution_backward for every conv of `nblocks` consecutive RDBs in ONE set of launches.
+ * The caller ran ws_rdb_backward with dw = NULL for each block, with buf / g / g_lff of block r living in slabs whose
+ * block index is the outermost dimension: the tensors passed here describe block 0 and block r starts
+ * r * d->n * nstride elements later.  grads: per block one record  [dw_0 | ... | dw_{nconv-1} | dw_lff | db_lff]
+ * (each in torch layout, ws_trunk_wgrad_record_floats floats, consecutive records block_stride floats apart; overwritten).
+ * Tensor-core BF16 path only (returns an error otherwise — the per-block path of ws_rdb_backward covers the rest). */
+int ws_trunk_wgrad_supported(const ws_rdb_desc* d); /* 1: this geometry / precision runs on the batched path */
+size_t ws_trunk_wgrad_record_floats(const ws_rdb_desc* d);
+size_t ws_trunk_wgrad_workspace_bytes(const ws_rdb_desc* d, int nblocks);
+int ws_trunk_wgrad(const ws_rdb_desc* d, int nblocks, const ws_tensor* buf, const ws_tensor* g, const ws_tensor* g_lff,
+                   float* grads, long long block_stride, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- nearest upsample (x2 in x and y, z untouched): nn.Upsample(scale_factor=(2,2,1)) torch_blocks.py:347 */
 /* in: (n, c, x, y, z) view, out: (n, c, 2x, 2y, z) view; bit-exact gather out[x,y,z] = in[x/2, y/2, z] */
 int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,

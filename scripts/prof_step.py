@@ -44,6 +44,19 @@ path = os.path.join(ROOT, "gpurun_out", "step_trace.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)
 prof.export_chrome_trace(path)
 tr = json.load(open(path))
+# kernel timeline (start, duration, stream) of the step, for offline phase / gap analysis
+tl = []
+for e in tr["traceEvents"]:
+    if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
+        nm = re.sub(r"ws::[^:]*::", "", e["name"].replace("void ", ""))
+        nm = re.sub(r"\(.*", "", nm)[:60]
+        tl.append((e["ts"], e["dur"], e.get("args", {}).get("stream", -1), nm, "x".join(map(str, e.get("args", {}).get("grid", [])))))
+tl.sort()
+t0_ = tl[0][0] if tl else 0
+with open(os.path.join(ROOT, "gpurun_out", os.environ.get("TIMELINE_NAME", "step_timeline.csv")), "w") as fh:
+    fh.write("start_us,dur_us,stream,kernel,grid\n")
+    for ts, dur, st_, nm, grid in tl:
+        fh.write(f"{ts - t0_:.1f},{dur:.1f},{st_},{nm},{grid}\n")
 agg = collections.defaultdict(lambda: [0, 0.0])
 tot = 0.0
 tmin, tmax = 1e30, 0

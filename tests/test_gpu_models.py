@@ -393,3 +393,68 @@ def test_trunk_size_rrdb_forward_backward_vs_oracle():
         worst = max(worst, err / lim)
         assert err <= lim, (k, err, lim)
     print(f"trunk RRDB bf16: fwd {rel_l2(y, y_ref):.2e}, dx {rel_l2(xg.grad, dx_ref):.2e}, worst grad/bound {worst:.2f}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups", ["1", "2"])
+def test_batched_trunk_equals_per_block_path(groups, monkeypatch):
+    """ops.TrunkFn (one autograd node for a run of RRDBs, weight gradients of all blocks as batched launches,
+    ws_trunk_wgrad) against the per-block path (ops.RDBFn: one merged + one LFF GEMM per block) on a 3-RRDB trunk at
+    the shipped trunk size.  The reference chain runs the RRDBs one at a time through the per-block path and hands
+    dL/dx from one to the next by hand: the forward and dL/dx must agree BIT FOR BIT (same kernels, same joins), the
+    parameter gradients to fp32-summation-order noise (both multiply the same bf16 operands; the batched GEMM has no
+    split-K).  The per-block path inside ONE autograd graph is compared too, more loosely: its joins of the RRDB skip
+    gradients are done by autograd."""
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models.torch_blocks import RRDB, run_trunk
+    torch.manual_seed(5)
+    mods = [RRDB(128, 32, 5, 1, lrelu_negative_slope=0.2, RDB_residual_scaling=0.2, RRDB_residual_scaling=0.2,
+                 mode="3D").cuda() for _ in range(3)]
+    x = torch.randn(2, 128, 16, 16, 10, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    gy = torch.randn(2, 128, 16, 16, 10, device="cuda")
+    params = [p for m in mods for p in m.parameters()]
+    monkeypatch.setenv("WINDSR_TRUNK_GROUPS", groups)
+
+    def run(batched):
+        monkeypatch.setenv("WINDSR_TRUNK_BATCH", "1" if batched else "0")
+        for p in params:
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        with ops.precision("bf16"):
+            y = run_trunk(mods, xi)
+            assert (type(y.grad_fn).__name__ == "TrunkFnBackward") == batched
+            y.backward(gy)
+        ops.aux_join()
+        torch.cuda.synchronize()
+        return y.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in params]
+
+    def chain():
+        monkeypatch.setenv("WINDSR_TRUNK_BATCH", "0")
+        for p in params:
+            p.grad = None
+        with ops.precision("bf16"):
+            hs = [x.clone()]
+            with torch.no_grad():
+                for m in mods:
+                    hs.append(run_trunk([m], hs[-1]))
+            d = gy
+            for i in range(len(mods) - 1, -1, -1):
+                xi = hs[i].clone().requires_grad_(True)
+                run_trunk([mods[i]], xi).backward(d)
+                ops.aux_join()
+                d = xi.grad
+        torch.cuda.synchronize()
+        return hs[-1], d, [p.grad.clone() for p in params]
+
+    y0, dx0, g0 = chain()
+    y1, dx1, g1 = run(True)
+    assert torch.equal(y0, y1)
+    assert torch.equal(dx1, dx0)
+    worst = max(rel_l2(a, b) for a, b in zip(g1, g0))
+    assert worst <= 2e-5, worst
+    for a, p in zip(g1, params):
+        assert a.shape == p.shape and a.is_contiguous()
+    y2, dx2, g2 = run(False)
+    assert torch.equal(y2, y1)
+    assert rel_l2(dx2, dx1) <= 1e-4
+    assert max(rel_l2(a, b) for a, b in zip(g2, g1)) <= 5e-3

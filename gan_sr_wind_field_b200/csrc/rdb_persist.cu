@@ -35,7 +35,12 @@ namespace {
 constexpr int kMaxPhases = WS_RDB_MAX_CONVS + 1;  // dense convs + LFF
 constexpr int kWSlots = 4;
 constexpr int kAStages = 2;
-constexpr int kThreads = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+// warp 0: TMA producer, warps 1-4: MMA issuers (warp 1 owns the TMEM allocation), warps 5-8: epilogue.
+// Several issuing warps because a tcgen05.mma occupies its issuing thread for about as long as it executes
+// (scripts/micro/mma_rate3.cu): with one issuer every barrier wait (~280 cycles), commit (~220) and descriptor
+// computation between two MMAs was tensor-pipe idle time — the dense-conv phases ran at 2-3x their MMA floor.
+constexpr int kThreads = 288;
+constexpr int kEpiThread0 = 160;  // first epilogue thread
 
 struct RdbMaps {
   CUtensorMap a[kMaxPhases];
@@ -49,6 +54,11 @@ struct RdbFwdParams {
   int slab_p;  // rows of one x-slab of the halo box: (DY + 2) * DZ
   int t_m;     // 128-row accumulator tiles per CTA
   int a_stage_bytes, w_slot_bytes;
+  int w_group;  // dense-conv weight tiles (taps) per ring slot = per barrier round trip of an issuer
+  int w_slots;  // ring slots (2..kWSlots)
+  int n_iss;    // issuing warps: issuer q owns the accumulator tiles m = q, q + n_iss, ...
+  int early;    // 1: the chunks of a phase that do not depend on the previous phase start before its grid barrier
+  int acc_stride;  // TMEM columns between the accumulator sets of even and odd phases (0: one set)
   int a_box_bytes_conv, a_box_bytes_lff;
   int kchunks[kMaxPhases], last_k16[kMaxPhases];
   int n_conv;  // UMMA N of a dense conv: 3 * gc
@@ -149,7 +159,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_base = smem_base + (uint32_t)kAStages * p.a_stage_bytes;
-  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)kWSlots * p.w_slot_bytes;
+  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)p.w_slots * p.w_slot_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kAStages + s); };
@@ -170,9 +180,10 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       ptx::prefetch_tmap(&maps.a[i]);
       ptx::prefetch_tmap(&maps.b[i]);
     }
-    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
-    ptx::mbar_init(accum_bar, 1);
+    // every issuing warp commits its own MMAs: "empty" / "accumulators complete" take n_iss arrivals
+    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), (uint32_t)p.n_iss); }
+    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), (uint32_t)p.n_iss); }
+    ptx::mbar_init(accum_bar, (uint32_t)p.n_iss);
     ptx::mbar_init(phase_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -192,28 +203,39 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
     for (int ph = 0; ph < nphases; ++ph) {
       const bool lff = ph == p.nconv;
       const int ntaps = lff ? 1 : 9;
+      const int wg = lff ? 1 : p.w_group;          // weight tiles per ring slot
+      const int gpc = (ntaps + wg - 1) / wg;       // tile groups per 64-channel chunk
       const int kch = p.kchunks[ph];
-      const int total_w = kch * ntaps;
+      const int total_w = kch * gpc;
       const uint32_t w_bytes = (uint32_t)(lff ? p.n_lff : p.n_conv) * 128u;
       int wi = 0;
       auto issue_w = [&]() {
-        const int ch = wi / ntaps, tap = wi - ch * ntaps;
+        const int ch = wi / gpc, t0 = (wi - ch * gpc) * wg;
+        const int cnt = min(wg, ntaps - t0);
         ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(w_full(wsl), w_bytes);
-          ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes, &maps.b[ph], w_full(wsl), ch * 64, 0, tap);
+          ptx::mbar_expect_tx(w_full(wsl), (uint32_t)cnt * w_bytes);
+          for (int j = 0; j < cnt; ++j)
+            ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes + j * w_bytes, &maps.b[ph], w_full(wsl), ch * 64, 0, t0 + j);
         }
         __syncwarp();
-        if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
         ++wi;
       };
       // weights do not depend on the previous phase: fill the ring before waiting for the grid barrier
-      while (wi < total_w && wi < kWSlots) issue_w();
-      // the activations do: wait until every CTA has published the previous phase's output (phase_bar is armed by this
-      // CTA's epilogue after the grid barrier), then order the generic-proxy writes before our async-proxy reads
-      ptx::mbar_wait(phase_bar, (uint32_t)(ph & 1));
-      fence_proxy_async_global();
+      while (wi < total_w && wi < p.w_slots) issue_w();
+      // Only the 64-channel chunks that contain the PREVIOUS phase's output depend on it (the last chunk: conv i reads
+      // channels [0, F + i*gc) and conv i-1 wrote the last gc of them).  The chunks before it were final one grid
+      // barrier earlier, so their loads — and their MMAs, into the other half of tensor memory — overlap the previous
+      // phase's epilogue and the grid barrier.  Before the first dependent chunk: wait until every CTA has published
+      // (phase_bar is armed by this CTA's epilogue after the grid barrier), then order the generic-proxy writes before
+      // our async-proxy reads.
+      const int dep_ch = (ph == 0 || !p.early) ? 0 : (p.F + (ph - 1) * p.gc) / 64;
       for (int ch = 0; ch < kch; ++ch) {
+        if (ch == dep_ch) {
+          ptx::mbar_wait(phase_bar, (uint32_t)(ph & 1));
+          fence_proxy_async_global();
+        }
         ptx::mbar_wait(a_empty(ab), aph ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t d = smem_base + ab * p.a_stage_bytes;
@@ -227,18 +249,22 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
         }
         __syncwarp();
         if (++ab == kAStages) { ab = 0; aph ^= 1u; }
-        const int upto = (ch + 1) * ntaps + kWSlots;
+        const int upto = (ch + 1) * gpc + p.w_slots;
         while (wi < total_w && wi < upto) issue_w();
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp <= 4) {
+    // ===== MMA issuers: warps 1 .. n_iss =====
+    const int q = warp - 1;
+    if (q < p.n_iss) {
     const uint64_t desc_hi = ptx::make_smem_desc_sw128(0, 16, 1024);
     int ab = 0, wsl = 0;
     uint32_t aph = 0, wph = 0;
     for (int ph = 0; ph < nphases; ++ph) {
       const bool lff = ph == p.nconv;
       const int ntaps = lff ? 1 : 9;
+      const int wg = lff ? 1 : p.w_group;
+      const uint32_t w_bytes = (uint32_t)(lff ? p.n_lff : p.n_conv) * 128u;
       const int n_umma = lff ? p.n_lff : p.n_conv;
       const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)n_umma, 0u, 0u);
       const int kch = p.kchunks[ph];
@@ -246,17 +272,20 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
         const int nk = (ch == kch - 1) ? p.last_k16[ph] : 4;
         ptx::mbar_wait(a_full(ab), aph);
         const uint32_t a_addr = smem_base + ab * p.a_stage_bytes;
+        int gpos = 0;  // position of the tap inside its weight group
         for (int tap = 0; tap < ntaps; ++tap) {
-          ptx::mbar_wait(w_full(wsl), wph);
-          ptx::tc_fence_after();
-          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes) >> 4) & 0x3fffu);
+          if (gpos == 0) {
+            ptx::mbar_wait(w_full(wsl), wph);
+            ptx::tc_fence_after();
+          }
+          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes + gpos * w_bytes) >> 4) & 0x3fffu);
           const uint32_t acc0 = (ch > 0 || tap > 0) ? 1u : 0u;
           // tap (kx, ky) -> first operand row: the output rows start one y line into the centre slab of the box
           const int roff = lff ? 0 : (tap / 3) * p.slab_p + (tap % 3) * p.DZ;
-          for (int m = 0; m < p.t_m; ++m) {
+          for (int m = q; m < p.t_m; m += p.n_iss) {
             const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * 128u;
             const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(m * 128);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((ph & 1) * p.acc_stride + m * 128);
             if (ptx::elect_one()) {
               ptx::mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc0);
               if (nk > 1) ptx::mma_f16_ss(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -265,9 +294,12 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
             }
             __syncwarp();
           }
-          if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
-          __syncwarp();
-          if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+          if (++gpos == wg || tap == ntaps - 1) {
+            gpos = 0;
+            if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+            __syncwarp();
+            if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+          }
         }
         if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
         __syncwarp();
@@ -276,10 +308,11 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       if (ptx::elect_one()) ptx::mma_commit(accum_bar);
       __syncwarp();
     }
+    }
   } else {
     // ===== epilogue warps =====
     const int sub = warp & 3;            // TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 64;     // 0..127
+    const int et = threadIdx.x - kEpiThread0;  // 0..127
     int stamp_i = 0;
     auto stamp = [&]() {
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
@@ -336,12 +369,13 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       ptx::mbar_wait(accum_bar, (uint32_t)(ph & 1));
       ptx::tc_fence_after();
       stamp();  // MMAs of this phase complete
+      const uint32_t acc_off = (uint32_t)((ph & 1) * p.acc_stride);  // this phase's half of tensor memory
       if (!lff) {
         const int c_out0 = p.F + ph * p.gc;  // first channel of this conv's slice of the concat buffer
         const int gc = p.gc;
         // pass 1: the rows a neighbouring warp (or the other tile) needs: u0 of lane 31, u2 of lane 0
         for (int m = 0; m < p.t_m; ++m) {
-          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc_off + (uint32_t)(m * 128);
           float* e0 = edge_s + ((m * 4 + sub) * 2 + 0) * 32;
           float* e2 = edge_s + ((m * 4 + sub) * 2 + 1) * 32;
           for (int c0 = 0; c0 < gc; c0 += 16) {
@@ -367,7 +401,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
           const bool row_ok = r < p.slab;
           const bool has_lo = z > 0, has_hi = z < p.DZ - 1;
           const int g = m * 4 + sub;
-          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc_off + (uint32_t)(m * 128);
           const long long v = (long long)x0 * p.slab + r;
           __nv_bfloat16* dst = (__nv_bfloat16*)buf.ptr + buf.off(n, c_out0, v);
           for (int c0 = 0; c0 < gc; c0 += 16) {
@@ -413,7 +447,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
           const int r0 = m * 128 + sub * 32;
           const int ok = p.slab - r0;  // valid rows of this warp's 32
           if (ok <= 0) break;
-          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * 128);
+          const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc_off + (uint32_t)(m * 128);
           rows_epilogue_f32(t_row, p.n_lff, stg, lane, ep_lff.bias, ep_lff.alpha, r1, ep_lff.beta1, r2, ep_lff.beta2, o,
                             out.vs, [&](int r) -> long long { return r < ok ? row_base + r0 + r : -1; });
         }
@@ -454,6 +488,10 @@ struct RdbBwdParams {
   int t_m;
   int ctot_pad;  // accumulator columns per tile
   int a_stage_bytes, w_slot_bytes;
+  int w_group;    // dense-conv weight tiles (taps) per ring slot
+  int w_slots;    // ring slots (2..kWSlots)
+  int n_iss_m;    // issuers across accumulator tiles
+  int tap_split;  // x issuers across the taps of a dense conv (they only ever ADD to the accumulators: any order works)
   int a_box_bytes_conv, a_box_bytes_lff;
   int kch_lff, last_k16_lff;
   int cin[kMaxPhases];
@@ -469,7 +507,7 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_base = smem_base + (uint32_t)kAStages * p.a_stage_bytes;
-  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)kWSlots * p.w_slot_bytes;
+  const uint32_t bar_off = (uint32_t)kAStages * p.a_stage_bytes + (uint32_t)p.w_slots * p.w_slot_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kAStages + s); };
@@ -490,9 +528,10 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
       ptx::prefetch_tmap(&maps.a[i]);
       ptx::prefetch_tmap(&maps.b[i]);
     }
-    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
-    ptx::mbar_init(accum_bar, 1);
+    const uint32_t n_iss = (uint32_t)(p.n_iss_m * p.tap_split);
+    for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), n_iss); }
+    for (int s = 0; s < kWSlots; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), n_iss); }
+    ptx::mbar_init(accum_bar, n_iss);
     ptx::mbar_init(phase_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -515,22 +554,26 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
       const int ci = lff ? 0 : p.nconv - ph;  // dense conv index
       const int mi = lff ? 0 : 1 + ci;
       const int ntaps = lff ? 1 : 27;
+      const int wg = lff ? 1 : p.w_group;      // weight tiles per ring slot
+      const int gpc = (ntaps + wg - 1) / wg;   // tile groups per K chunk
       const int kch = lff ? p.kch_lff : 1;
-      const int total_w = kch * ntaps;
+      const int total_w = kch * gpc;
       const uint32_t w_bytes = lff ? (uint32_t)p.ctot_pad * 128u : (uint32_t)p.cin[ci] * 64u;
       int wi = 0;
       auto issue_w = [&]() {
-        const int ch = wi / ntaps, tap = wi - ch * ntaps;
+        const int ch = wi / gpc, t0 = (wi - ch * gpc) * wg;
+        const int cnt = min(wg, ntaps - t0);
         ptx::mbar_wait(w_empty(wsl), wph ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(w_full(wsl), w_bytes);
-          ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes, &maps.b[mi], w_full(wsl), ch * 64, 0, tap);
+          ptx::mbar_expect_tx(w_full(wsl), (uint32_t)cnt * w_bytes);
+          for (int j = 0; j < cnt; ++j)
+            ptx::tma_load_3d(w_base + wsl * p.w_slot_bytes + j * w_bytes, &maps.b[mi], w_full(wsl), ch * 64, 0, t0 + j);
         }
         __syncwarp();
-        if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+        if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
         ++wi;
       };
-      while (wi < total_w && wi < kWSlots) issue_w();
+      while (wi < total_w && wi < p.w_slots) issue_w();
       ptx::mbar_wait(phase_bar, (uint32_t)(ph & 1));
       fence_proxy_async_global();
       for (int ch = 0; ch < kch; ++ch) {
@@ -547,12 +590,17 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
         }
         __syncwarp();
         if (++ab == kAStages) { ab = 0; aph ^= 1u; }
-        const int upto = (ch + 1) * ntaps + kWSlots;
+        const int upto = (ch + 1) * gpc + p.w_slots;
         while (wi < total_w && wi < upto) issue_w();
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp <= 4) {
+    // ===== MMA issuers: warps 1 .. n_iss_m * tap_split.  Issuer q owns the accumulator tiles m = qm, qm + n_iss_m, ...
+    // and, in the dense-conv phases (which only ever add to the accumulators), the taps with tap % tap_split == qt.
+    // Every issuer follows every barrier phase (waits and commits), whether or not it has MMAs in it. =====
+    const int q = warp - 1;
+    if (q < p.n_iss_m * p.tap_split) {
+    const int qm = q % p.n_iss_m, qt = q / p.n_iss_m;
     const uint64_t desc128 = ptx::make_smem_desc_sw128(0, 16, 1024);
     // SWIZZLE_64B operand rows (K = gc = 32 channels = 64 B): layout type 4, SBO = 8 rows x 64 B (scripts/micro/sw64.cu)
     const uint64_t desc64 = ((uint64_t)1 << 16) | ((uint64_t)(512u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
@@ -562,6 +610,8 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
       const bool lff = ph == 0;
       const int ci = lff ? 0 : p.nconv - ph;
       const int ntaps = lff ? 1 : 27;
+      const int wg = lff ? 1 : p.w_group;
+      const uint32_t w_bytes = lff ? (uint32_t)p.ctot_pad * 128u : (uint32_t)p.cin[ci] * 64u;
       const int kch = lff ? p.kch_lff : 1;
       const int n_umma = lff ? p.ctot_pad : p.cin[ci];
       const uint32_t idesc = ptx::make_idesc(1u, 128u, (uint32_t)n_umma, 0u, 0u);
@@ -571,15 +621,19 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
         const int nk = lff ? ((ch == kch - 1) ? p.last_k16_lff : 4) : 2;
         ptx::mbar_wait(a_full(ab), aph);
         const uint32_t a_addr = smem_base + ab * p.a_stage_bytes;
+        int gpos = 0;  // position of the tap inside its weight group
         for (int tap = 0; tap < ntaps; ++tap) {
-          ptx::mbar_wait(w_full(wsl), wph);
-          ptx::tc_fence_after();
-          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes) >> 4) & 0x3fffu);
+          if (gpos == 0) {
+            ptx::mbar_wait(w_full(wsl), wph);
+            ptx::tc_fence_after();
+          }
+          const bool mine = lff ? qt == 0 : (tap & (p.tap_split - 1)) == qt;
+          const uint64_t bdesc = desc_hi | (uint64_t)(((w_base + wsl * p.w_slot_bytes + gpos * w_bytes) >> 4) & 0x3fffu);
           // the LFF overwrites the accumulators, every dense conv adds to them
           const uint32_t acc0 = (!lff || ch > 0) ? 1u : 0u;
           const int ti = tap / 9, tj = (tap / 3) % 3, tl = tap % 3;
           const int roff = lff ? 0 : ti * p.slab_p + tj * p.pz + tl;
-          for (int m = 0; m < p.t_m; ++m) {
+          for (int m = qm; mine && m < p.t_m; m += p.n_iss_m) {
             const uint32_t am = a_addr + (uint32_t)(m * 128 + roff) * row_bytes;
             const uint64_t adesc = desc_hi | (uint64_t)((am >> 4) & 0x3fffu);
             const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.ctot_pad);
@@ -591,9 +645,12 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
             }
             __syncwarp();
           }
-          if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
-          __syncwarp();
-          if (++wsl == kWSlots) { wsl = 0; wph ^= 1u; }
+          if (++gpos == wg || tap == ntaps - 1) {
+            gpos = 0;
+            if (ptx::elect_one()) ptx::mma_commit(w_empty(wsl));
+            __syncwarp();
+            if (++wsl == p.w_slots) { wsl = 0; wph ^= 1u; }
+          }
         }
         if (ptx::elect_one()) ptx::mma_commit(a_empty(ab));
         __syncwarp();
@@ -602,10 +659,11 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
       if (ptx::elect_one()) ptx::mma_commit(accum_bar);
       __syncwarp();
     }
+    }
   } else {
     // ===== epilogue warps =====
     const int sub = warp & 3;
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - kEpiThread0;
     // ---- phase -1: g_lff = alpha * dy (bf16) for this CTA's rows; only this CTA reads them back (1x1x1 conv)
     {
       const int c8 = p.F / 8;
@@ -806,7 +864,20 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
   p.a_box_bytes_conv = 3 * p.slab_p * 128;
   p.a_box_bytes_lff = p.slab * 128;
   p.a_stage_bytes = (p.a_box_bytes_conv + 1023) / 1024 * 1024;
-  p.w_slot_bytes = ((p.n_conv > p.n_lff ? p.n_conv : p.n_lff) * 128 + 1023) / 1024 * 1024;
+  // dense-conv weight tiles share a ring slot (one barrier round trip of the issuers per group) in threes when the
+  // shared memory allows: 2 activation stages + 2 slots must fit
+  static const int env_wg = getenv("WS_RDB_WGROUP") ? atoi(getenv("WS_RDB_WGROUP")) : 3;
+  static const int env_niss = getenv("WS_RDB_NISS") ? atoi(getenv("WS_RDB_NISS")) : 4;
+  p.n_iss = p.t_m < 4 ? p.t_m : 4;
+  if (p.n_iss > env_niss) p.n_iss = env_niss < 1 ? 1 : env_niss;
+  const int conv_tile = p.n_conv * 128, lff_tile = p.n_lff * 128;
+  p.w_group = env_wg < 1 ? 1 : (env_wg > 9 ? 9 : env_wg);
+  auto slot_bytes = [&](int wg) { int b = wg * conv_tile; if (lff_tile > b) b = lff_tile; return (b + 1023) / 1024 * 1024; };
+  while (p.w_group > 1 && kAStages * p.a_stage_bytes + 2 * slot_bytes(p.w_group) + 2048 > 222 * 1024) --p.w_group;
+  p.w_slot_bytes = slot_bytes(p.w_group);
+  p.w_slots = (222 * 1024 - 2048 - kAStages * p.a_stage_bytes) / p.w_slot_bytes;
+  if (p.w_slots > kWSlots) p.w_slots = kWSlots;
+  WS_REQUIRE(p.w_slots >= 2, "rdb_persist: no room for two weight slots");
   RdbMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i <= d->nconv; ++i) {
@@ -818,13 +889,16 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
     const int k_pad = (cin + 7) / 8 * 8;
     if (int e = make_w_map(packed[i], k_pad, lff ? (d->f + 15) / 16 * 16 : p.n_conv, lff ? 1 : 9, &maps.b[i])) return e;
   }
+  static const bool no_early = env_off("WS_RDB_NO_EARLY");
+  p.early = (!no_early && 2 * p.t_m * 128 <= 512) ? 1 : 0;
+  p.acc_stride = p.early ? p.t_m * 128 : 0;
   uint32_t cols = 32;
-  while ((int)cols < p.t_m * 128) cols <<= 1;
+  while ((int)cols < (p.early ? 2 : 1) * p.t_m * 128) cols <<= 1;
   p.tmem_cols = cols;
   // the MMA rows of the last tile / the largest tap offset read past the loaded box (rows that are never stored):
   // they must still lie inside this CTA's shared memory
   const size_t reach = (size_t)(p.t_m * 128 + 2 * p.slab_p + 2 * p.DZ) * 128;
-  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)kWSlots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
+  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
   if (smem < (size_t)p.a_stage_bytes + reach + 1024) smem = (size_t)p.a_stage_bytes + reach + 1024;
   WS_REQUIRE(smem <= 224 * 1024, "rdb_persist: shared memory request %zu too large", smem);
   static std::once_flag once;
@@ -906,12 +980,32 @@ int rdb_persist_backward(const ws_rdb_desc* d, const View& dy, const View& buf, 
     if (int e = make_w_map(packed[i], (d->gc + 7) / 8 * 8, (p.cin[i] + 15) / 16 * 16, 27, &maps.b[1 + i], 32)) return e;
     if (p.cin[i] * 64 > w_bytes) w_bytes = p.cin[i] * 64;
   }
-  p.w_slot_bytes = (w_bytes + 1023) / 1024 * 1024;
+  {
+    static const int env_wg = getenv("WS_RDB_WGROUP") ? atoi(getenv("WS_RDB_WGROUP")) : 3;
+    static const int env_niss = getenv("WS_RDB_NISS") ? atoi(getenv("WS_RDB_NISS")) : 4;
+    p.n_iss_m = p.t_m < 4 ? p.t_m : 4;
+    if (p.n_iss_m > env_niss) p.n_iss_m = env_niss < 1 ? 1 : env_niss;
+    // (two issuers adding to ONE accumulator do so in a timing-dependent order: run-to-run fp32 noise in dL/dx — opt-in)
+    static const bool env_split = env_off("WS_RDB_TAP_SPLIT");
+    p.tap_split = (env_split && p.n_iss_m * 2 <= 4 && p.n_iss_m * 2 <= env_niss) ? 2 : 1;
+    const int lff_tile = p.ctot_pad * 128;
+    int conv_tile = 0;
+    for (int i = 0; i < d->nconv; ++i)
+      if (p.cin[i] * 64 > conv_tile) conv_tile = p.cin[i] * 64;
+    p.w_group = env_wg < 1 ? 1 : (env_wg > 27 ? 27 : env_wg);
+    auto slot_bytes = [&](int wg) { int b = wg * conv_tile; if (lff_tile > b) b = lff_tile; return (b + 1023) / 1024 * 1024; };
+    while (p.w_group > 1 && kAStages * p.a_stage_bytes + 2 * slot_bytes(p.w_group) + 2048 > 222 * 1024) --p.w_group;
+    p.w_slot_bytes = slot_bytes(p.w_group);
+    p.w_slots = (222 * 1024 - 2048 - kAStages * p.a_stage_bytes) / p.w_slot_bytes;
+    if (p.w_slots > kWSlots) p.w_slots = kWSlots;
+    WS_REQUIRE(p.w_slots >= 2, "rdb_persist backward: no room for two weight slots");
+    (void)w_bytes;
+  }
   uint32_t cols = 32;
   while ((int)cols < p.t_m * p.ctot_pad) cols <<= 1;
   p.tmem_cols = cols;
   const size_t reach = (size_t)(p.t_m * 128 + 2 * p.slab_p + 2 * p.pz + 2) * 128;  // rows x the wider (128 B) row
-  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)kWSlots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
+  size_t smem = (size_t)kAStages * p.a_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes + 8 * (2 * kAStages + 2 * kWSlots + 3) + 1024;
   if (smem < (size_t)p.a_stage_bytes + reach + 1024) smem = (size_t)p.a_stage_bytes + reach + 1024;
   WS_REQUIRE(smem <= 225 * 1024, "rdb_persist backward: shared memory request %zu too large", smem);
   static std::once_flag once;

@@ -6,6 +6,17 @@
 #include "../../gan_sr_wind_field_b200/csrc/ptx.cuh"
 using namespace ws;
 
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -27,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate3(int n_umma, int reps, int n_
     uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     // random bf16 pairs in [-2, 2): sign + exponent 0x3f/0x3e + random mantissa
-    ((uint32_t*)smem)[i] = random_data ? ((h & 0x80ff80ffu) | 0x3f003f00u) : 0x3c003c00u;
+    ((uint32_t*)smem)[i] = (random_data & 1) ? ((h & 0x80ff80ffu) | 0x3f003f00u) : 0x3c003c00u;
   }
   __shared__ uint64_t dummy_bar, ready_bar;
   if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&dummy_bar), 1); ptx::mbar_init(ptx::smem_u32(&ready_bar), 1); }
@@ -78,8 +89,9 @@ __global__ void __launch_bounds__(128, 1) mma_rate3(int n_umma, int reps, int n_
         }
         if (wait_every && (r + 1) % wait_every == 0) {
           // an already-completed barrier wait + fence, as at every tap of the conv kernel (ready_bar never flips: parity 1 passes)
-          ptx::mbar_wait(ptx::smem_u32(&ready_bar), 1u);
-          ptx::tc_fence_after();
+          if (random_data & 4) { while (!mbar_test_wait(ptx::smem_u32(&ready_bar), 1u)) {} }
+          else ptx::mbar_wait(ptx::smem_u32(&ready_bar), 1u);
+          if (wait_every > 0 && !(random_data & 2)) ptx::tc_fence_after();
         }
       }
       t1 = clock64();
@@ -147,6 +159,9 @@ int main() {
     for (int rnd : {0, 1}) { run<false>(n, 0, src, d, rnd); run<true>(n, 0, src, d, rnd); }
     for (int ce : {1, 3}) { run<false>(n, 0, src, d, 1, ce, 0); run<true>(n, 0, src, d, 1, ce, 0); }
     for (int we : {1, 3}) { run<false>(n, 0, src, d, 1, we, we); run<true>(n, 0, src, d, 1, we, we); }
+    // rnd & 2: the barrier wait WITHOUT the tcgen05 fence; commit 0: waits only
+    run<false>(n, 0, src, d, 3, 1, 1); run<false>(n, 0, src, d, 1, 0, 1); run<false>(n, 0, src, d, 3, 0, 1);
+    run<false>(n, 0, src, d, 7, 0, 1);  // rnd & 4: mbarrier.test_wait instead of try_wait
     run<true>(n, 16384, src, d, 1, 3, 3);
   }
   return 0;

@@ -57,6 +57,7 @@ struct RdbFwdParams {
   int w_group;  // dense-conv weight tiles (taps) per ring slot = per barrier round trip of an issuer
   int w_slots;  // ring slots (2..kWSlots)
   int n_iss;    // issuing warps: issuer q owns the accumulator tiles m = q, q + n_iss, ...
+  int nb_sync;  // 1: neighbour flags instead of grid-wide barriers between the phases
   int early;    // 1: the chunks of a phase that do not depend on the previous phase start before its grid barrier
   int acc_stride;  // TMEM columns between the accumulator sets of even and odd phases (0: one set)
   int a_box_bytes_conv, a_box_bytes_lff;
@@ -102,6 +103,46 @@ __device__ __forceinline__ void grid_barrier(int slot, unsigned int nblocks) {
     }
   }
   __threadfence();
+}
+// ---- neighbour synchronisation ----------------------------------------------------------------------------------
+// A CTA (sample n, x-slab x0) only ever reads what the CTAs (n, x0 - 1) and (n, x0 + 1) wrote in the previous phase
+// (the 3^3 halo), so a grid-wide barrier (~3 us: 128 atomics on one counter plus the slowest CTA of the whole grid)
+// is more than needed.  Each CTA publishes "phase k done" in its own flag word and waits for its two neighbours'.
+// Flag values are launch_epoch * 16 + k; the epoch lives in device memory and is advanced by the last CTA of a launch
+// to finish, so nothing has to be reset between launches and a CUDA-graph replay (frozen kernel arguments) just works.
+// Stale flags of earlier launches are always behind the current targets (signed wrap-around comparison).
+__device__ unsigned int g_rdb_epoch[2];
+__device__ unsigned int g_rdb_done[2];
+constexpr int kFlagStride = 32;  // one 128-byte line per flag: a poller must not share a line with another CTA's flag
+__device__ unsigned int g_rdb_flag[2][256 * kFlagStride];
+
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const unsigned int* p, unsigned int target) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire(p) - target) < 0) {
+    __nanosleep(32);
+    if (clock64() - t0 > (1ll << 32)) __trap();  // ~2 s at 2 GHz
+  }
+}
+// one thread per CTA: publish phase k and wait until both x-neighbours of the same sample have published it too
+__device__ __forceinline__ void neighbour_sync(int kind, unsigned int base, int k, int me, bool has_lo, bool has_hi) {
+  __threadfence();
+  st_release(&g_rdb_flag[kind][me * kFlagStride], base + (unsigned int)k);
+  if (has_lo) flag_wait(&g_rdb_flag[kind][(me - 1) * kFlagStride], base + (unsigned int)k);
+  if (has_hi) flag_wait(&g_rdb_flag[kind][(me + 1) * kFlagStride], base + (unsigned int)k);
+  __threadfence();
+}
+// one thread per CTA, after its last phase: the last CTA of the launch advances the epoch
+__device__ __forceinline__ void launch_done(int kind, unsigned int nblocks) {
+  __threadfence();
+  const unsigned int old = atomicAdd(&g_rdb_done[kind], 1u);
+  if (old == nblocks - 1) {
+    g_rdb_done[kind] = 0u;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_rdb_epoch[kind]) : "memory");
+  }
 }
 __device__ __forceinline__ void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -318,6 +359,9 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
       ++stamp_i;
     };
+    // (neighbour flags: this launch's epoch, read before anything is published)
+    const unsigned int sync_base = (p.nb_sync && et == 0) ? (ld_acquire(&g_rdb_epoch[0]) << 4) : 0u;
+    int sync_k = 0;
     auto publish = [&]() {
       // make this CTA's global writes visible grid-wide, wait for everybody else's, release the producer
       __threadfence();
@@ -325,7 +369,8 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       stamp();  // epilogue stores done
       if (et == 0) {
-        grid_barrier(p.bar_slot, gridDim.x);
+        if (p.nb_sync) neighbour_sync(0, sync_base, ++sync_k, (int)blockIdx.x, x0 > 0, x0 < p.DX - 1);
+        else grid_barrier(p.bar_slot, gridDim.x);
         ptx::mbar_arrive(phase_bar);
       }
       stamp();  // barrier passed
@@ -455,6 +500,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
         stamp();  // LFF epilogue done
       }
     }
+    if (p.nb_sync && et == 0) launch_done(0, gridDim.x);
   }
 
   __syncthreads();
@@ -490,6 +536,7 @@ struct RdbBwdParams {
   int a_stage_bytes, w_slot_bytes;
   int w_group;    // dense-conv weight tiles (taps) per ring slot
   int w_slots;    // ring slots (2..kWSlots)
+  int nb_sync;    // 1: neighbour flags instead of grid-wide barriers between the phases
   int n_iss_m;    // issuers across accumulator tiles
   int tap_split;  // x issuers across the taps of a dense conv (they only ever ADD to the accumulators: any order works)
   int a_box_bytes_conv, a_box_bytes_lff;
@@ -664,6 +711,8 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
     // ===== epilogue warps =====
     const int sub = warp & 3;
     const int et = threadIdx.x - kEpiThread0;
+    const unsigned int sync_base = (p.nb_sync && et == 0) ? (ld_acquire(&g_rdb_epoch[1]) << 4) : 0u;
+    int sync_k = 0;
     // ---- phase -1: g_lff = alpha * dy (bf16) for this CTA's rows; only this CTA reads them back (1x1x1 conv)
     {
       const int c8 = p.F / 8;
@@ -762,11 +811,13 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
         fence_proxy_async_global();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
-          grid_barrier(p.bar_slot, gridDim.x);
+          if (p.nb_sync) neighbour_sync(1, sync_base, ++sync_k, (int)blockIdx.x, x0 > 0, x0 < p.DX - 1);
+          else grid_barrier(p.bar_slot, gridDim.x);
           ptx::mbar_arrive(phase_bar);
         }
       }
     }
+    if (p.nb_sync && et == 0) launch_done(1, gridDim.x);
   }
 
   __syncthreads();
@@ -889,6 +940,8 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
     const int k_pad = (cin + 7) / 8 * 8;
     if (int e = make_w_map(packed[i], k_pad, lff ? (d->f + 15) / 16 * 16 : p.n_conv, lff ? 1 : 9, &maps.b[i])) return e;
   }
+  static const bool grid_bar = env_off("WS_RDB_GRID_BARRIER");
+  p.nb_sync = (!grid_bar && d->n * d->x <= 256) ? 1 : 0;
   static const bool no_early = env_off("WS_RDB_NO_EARLY");
   p.early = (!no_early && 2 * p.t_m * 128 <= 512) ? 1 : 0;
   p.acc_stride = p.early ? p.t_m * 128 : 0;
@@ -981,6 +1034,8 @@ int rdb_persist_backward(const ws_rdb_desc* d, const View& dy, const View& buf, 
     if (p.cin[i] * 64 > w_bytes) w_bytes = p.cin[i] * 64;
   }
   {
+    static const bool grid_bar = env_off("WS_RDB_GRID_BARRIER");
+    p.nb_sync = (!grid_bar && d->n * d->x <= 256) ? 1 : 0;
     static const int env_wg = getenv("WS_RDB_WGROUP") ? atoi(getenv("WS_RDB_WGROUP")) : 3;
     static const int env_niss = getenv("WS_RDB_NISS") ? atoi(getenv("WS_RDB_NISS")) : 4;
     p.n_iss_m = p.t_m < 4 ? p.t_m : 4;

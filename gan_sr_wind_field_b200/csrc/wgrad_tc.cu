@@ -59,6 +59,13 @@ struct WgParams {
   // workspace addressing: wsp[range * range_stride + tap * tap_stride + m * m_stride + n * n_stride]
   long long tap_stride, m_stride, n_stride;
   long long range_stride;  // batched launches (one tile range per residual dense block): a result per range
+  int xhalo;               // 1: a tap group = taps_per_cta consecutive kx taps of one (ky, kz); the shifted operand is ONE
+                           // box with an x halo (bx + taps_per_cta - 1 slabs) per voxel tile and the taps are row offsets
+                           // into it (rows are ordered (x, y, z): a shift by one x slab = by * bz rows) — the L2 -> SMEM
+                           // traffic of the shifted operand drops by ~taps_per_cta
+  int halo_rows;           // rows of the halo box, halo_blk_bytes = its padded size per channel block
+  int halo_blk_bytes;
+  int kx_groups;           // xhalo: tap groups per (ky, kz) = ceil(kx / taps_per_cta)
   int n_iss;               // MMA-issuing warps (1..4, <= taps_per_cta): issuer q owns the accumulators of taps q, q + n_iss, ...
                            // (a tcgen05.mma occupies its issuing thread about as long as it executes, so barrier waits,
                            // commits and descriptor arithmetic of ONE issuer are tensor-pipe idle time — conv_tc2.cu)
@@ -68,7 +75,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
-                const WgParams p, float* __restrict__ wsp) {
+                const __grid_constant__ CUtensorMap tmH, const WgParams p, float* __restrict__ wsp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -106,8 +113,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmM);
     ptx::prefetch_tmap(&tmN);
+    if (p.xhalo) ptx::prefetch_tmap(&tmH);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), (uint32_t)p.n_iss); }
-    for (int s = 0; s < p.b_slots; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
+    // (xhalo: every issuer reads every halo slot; otherwise a slot belongs to one issuer's private ring)
+    for (int s = 0; s < p.b_slots; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), p.xhalo ? (uint32_t)p.n_iss : 1u); }
     ptx::mbar_init(accum_bar, (uint32_t)p.n_iss);
     ptx::mbar_init(tmem_free, 4);  // one arrival per epilogue warp
     ptx::fence_mbar_init();
@@ -135,6 +144,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       // the ring of shifted-operand slots is split into one private ring per issuing warp (slots_per slots each): a
       // barrier then has exactly one consumer, which sees every one of its phases in order
       const int slots_per = p.b_slots / p.n_iss;
+      int hs = 0;           // xhalo: position / phase in the shared ring of halo slots
+      uint32_t hph = 0;
       uint32_t bstate = 0;  // per issuer q a nibble: position in its private ring (3 bits) | phase << 3
       // the unshifted operand (dy) is the one that is NOT x
       const CUtensorMap* tm_fix = p.shift_on_m ? &tmN : &tmM;
@@ -164,6 +175,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         }
         __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1u; }
+        if (p.xhalo) {
+          // one halo box for all taps of the group: x from the group's first kx tap, (ky, kz) fixed
+          const int g = (int)(sg % p.tap_groups);
+          const int yz = g / p.kx_groups, ti0 = (g - yz * p.kx_groups) * p.taps_per_cta;
+          const int tj = yz / p.kz, tl = yz - tj * p.kz;
+          const int cx = x0 - p.px + ti0, cy = y0 * p.sy - p.py + tj, cz = z0 * p.sz - p.pz + tl;
+          const int bs = hs;
+          ptx::mbar_wait(b_empty(bs), hph ^ 1u);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(b_full(bs), (uint32_t)p.halo_rows * 128u * sh_blocks);
+            for (int b = 0; b < sh_blocks; ++b)
+              ptx::tma_load_5d(b_base + bs * p.b_slot_bytes + b * p.halo_blk_bytes, &tmH, b_full(bs), sh_c0 + b * cblk, cz,
+                               cy, cx, n);
+          }
+          __syncwarp();
+          if (++hs == p.b_slots) { hs = 0; hph ^= 1u; }
+          continue;
+        }
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ti = tap / (p.ky * p.kz), tj = (tap / p.kz) % p.ky, tl = tap % p.kz;
           const int cx = x0 * p.sx - p.px + ti, cy = y0 * p.sy - p.py + tj, cz = z0 * p.sz - p.pz + tl;
@@ -200,8 +229,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       int as = 0;
       uint32_t aph = 0;
       const int slots_per = p.b_slots / p.n_iss;
-      int bpos = 0;  // position / phase in this issuer's private ring
+      int bpos = 0;  // position / phase in this issuer's private ring (xhalo: in the shared ring of halo slots)
       uint32_t bph = 0;
+      // the shifted operand's tile has its own row count (LBO = bytes of one channel block)
+      const uint64_t desc_hi_sh = (p.xhalo && !p.tf32) ? ptx::make_smem_desc_sw128(0, (uint32_t)p.halo_blk_bytes, 1024) : desc_hi;
+      const uint32_t slab_bytes = (uint32_t)(p.by * p.bz) * 128u;  // xhalo: one x slab of the halo box
       // one instruction consumes 16 voxel rows of bf16 (2048 B of the MN-major tile) or 8 rows of tf32 (1024 B)
       const int krows = p.tf32 ? 8 : 16;
       const int k16 = p.rows / krows;
@@ -211,8 +243,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
       for (long long item = item_lo; item < item_hi; ++item) {
         const long long sg = item / p.range_tiles;
         const long long tile = (sg / p.tap_groups) * p.range_tiles + item % p.range_tiles;
-        const int tap_lo = (int)(sg % p.tap_groups) * p.taps_per_cta;
-        const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+        int ntap;
+        if (p.xhalo) {
+          const int g = (int)(sg % p.tap_groups);
+          const int ti0 = (g % p.kx_groups) * p.taps_per_cta;
+          ntap = min(p.kx, ti0 + p.taps_per_cta) - ti0;
+        } else {
+          const int tap_lo = (int)(sg % p.tap_groups) * p.taps_per_cta;
+          ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+        }
         if (item > item_lo && item % p.range_tiles == 0) {
           // group boundary: hand the finished accumulators to the epilogue, then wait until it has drained them
           if (ptx::elect_one()) ptx::mma_commit(accum_bar);
@@ -225,6 +264,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
         if (tile >= p.total_tiles) continue;  // tail of the last range (never the first item of a segment)
         ptx::mbar_wait(a_full(as), aph);
         const uint32_t fix_addr = a_base + as * p.a_slot_bytes;
+        if (p.xhalo) {
+          // every issuer follows every halo slot; its taps are row offsets into the box
+          const int bs = bpos;
+          ptx::mbar_wait(b_full(bs), bph);
+          ptx::tc_fence_after();
+          for (int tp = q; tp < ntap; tp += p.n_iss) {
+            const uint32_t sh_addr = b_base + bs * p.b_slot_bytes + (uint32_t)tp * slab_bytes;
+            const uint64_t sh_desc = desc_hi_sh | (uint64_t)((sh_addr >> 4) & 0x3fffu);
+            const uint64_t fx_desc = desc_hi | (uint64_t)((fix_addr >> 4) & 0x3fffu);
+            const uint64_t adesc = p.shift_on_m ? sh_desc : fx_desc;
+            const uint64_t bdesc = p.shift_on_m ? fx_desc : sh_desc;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(tp * p.n_umma);
+            if (ptx::elect_one()) {
+              for (int k = 0; k < k16; ++k)
+                ptx::mma_f16_ss(d_tmem, adesc + kadv * k, bdesc + kadv * k, idesc, (acc_tile | (uint32_t)k) ? 1u : 0u);
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) ptx::mma_commit(b_empty(bs));
+          __syncwarp();
+          if (++bpos == p.b_slots) { bpos = 0; bph ^= 1u; }
+        } else
         for (int tp = q; tp < ntap; tp += p.n_iss) {  // the other taps belong to other issuers (and their rings)
           const int bs = q * slots_per + bpos;
           ptx::mbar_wait(b_full(bs), bph);
@@ -265,14 +326,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__
     ptx::griddep_wait();  // the workspace memset / earlier reductions precede the atomics
     int seg = 0;
     for (long long item = item_lo; item < item_hi; ++seg) {
-      const int tap_lo = (int)((item / p.range_tiles) % p.tap_groups) * p.taps_per_cta;
-      const int ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+      // accumulator tp of this segment belongs to tap  tap_lo + tp * tap_step
+      int tap_lo, ntap, tap_step = 1;
+      if (p.xhalo) {
+        const int g = (int)((item / p.range_tiles) % p.tap_groups);
+        const int yz = g / p.kx_groups, ti0 = (g - yz * p.kx_groups) * p.taps_per_cta;
+        ntap = min(p.kx, ti0 + p.taps_per_cta) - ti0;
+        tap_step = p.ky * p.kz;
+        tap_lo = ti0 * tap_step + yz;  // (ti * ky + tj) * kz + tl with yz = tj * kz + tl
+      } else {
+        tap_lo = (int)((item / p.range_tiles) % p.tap_groups) * p.taps_per_cta;
+        ntap = min(p.taps, tap_lo + p.taps_per_cta) - tap_lo;
+      }
       const long long seg_end = min(item_hi, (item / p.range_tiles + 1) * p.range_tiles);
       float* wrange = wsp + ((item / p.range_tiles) / p.tap_groups) * p.range_stride;
       ptx::mbar_wait(accum_bar, (uint32_t)(seg & 1));
       ptx::tc_fence_after();
       for (int tp = 0; tp < ntap; ++tp) {
-        const int tap = tap_lo + tp;
+        const int tap = tap_lo + tp * tap_step;
         for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
           if (c0 >= p.n_valid) break;
           uint32_t r[16];
@@ -393,10 +464,14 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   const int sh_alloc = swap ? 128 / cblk : p.n_blocks;
   p.a_slot_bytes = fix_alloc * blk;
   p.b_slot_bytes = sh_alloc * blk;
-  int budget = 220 * 1024 - 1024 - 512 - 2 * p.a_slot_bytes;
-  p.b_slots = budget / p.b_slot_bytes;
-  if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
-  WS_REQUIRE(p.b_slots >= 2, "wgrad: shared memory budget too small for 2 operand slots");
+  const int budget = 220 * 1024 - 1024 - 512 - 2 * p.a_slot_bytes;
+  // x-halo mode (WgParams::xhalo): stride-1 bf16 layers with kx >= 2 whose tap groups are runs of kx taps
+  static const bool env_no_xhalo = getenv("WS_WGRAD_XHALO") && atoi(getenv("WS_WGRAD_XHALO")) == 0;
+  const bool xh_ok = !tf32 && g.sx == 1 && g.kx >= 2 && !env_no_xhalo;
+  auto halo_blk = [&](int tpc) { return ((p.bx + tpc - 1) * p.by * p.bz * 128 + 1023) / 1024 * 1024; };
+  auto xh_for = [&](int tpc) {
+    return xh_ok && tpc >= 2 && tpc <= g.kx && (p.bx + tpc - 1) <= 256 && 2 * sh_alloc * halo_blk(tpc) <= budget;
+  };
 
   // Work split: (tap group, voxel tile) items of an M block dealt out in equal contiguous runs to `ncta` CTAs
   // (grid.x), M blocks in grid.z.  Modelled cost per CTA =
@@ -411,8 +486,12 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   double best = 1e30;
   int best_tpc = 1, best_gpc = 1;
   long long best_range = p.total_tiles;
+  bool best_xh = false;
   for (int tpc = 1; tpc <= max_tpc && tpc <= p.taps; ++tpc) {
-    const int tg = (p.taps + tpc - 1) / tpc;
+    const bool xh = xh_for(tpc);
+    if (xh_ok && tpc > g.kx) break;  // (with an x halo available, groups that mix (ky, kz) are never better)
+    const int tg = xh ? g.ky * g.kz * ((g.kx + tpc - 1) / tpc) : (p.taps + tpc - 1) / tpc;
+    if (!xh && budget / p.b_slot_bytes < 2) continue;
     for (int gpc : {1, 2, 3, 4, 6, 8}) {          // tap groups (= segments) per CTA
       if (gpc > tg) break;
       // candidates: every range count up to 32, a coarser ladder above, and the counts that fill exactly 1 / 2 / 3
@@ -446,11 +525,12 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
         const double wave_ctas = ctas < 148 ? (double)ctas : 148.0;
         const double atom_chip = wave_ctas * gpc * tpc * 128.0 * p.n_umma / 512.0;
         const double atom_t = gpc * tpc * atom > atom_chip ? gpc * tpc * atom : atom_chip;
-        const double item_load = hot * (tpc * unit_load + (double)fix_alloc * blk / 33.0);
+        const double sh_load = xh ? (double)sh_alloc * halo_blk(tpc) / 33.0 : tpc * unit_load;
+        const double item_load = hot * (sh_load + (double)fix_alloc * blk / 33.0);
         const double item_mma = tpc * unit_mma;
         const double t =
             (double)waves * (per * (item_mma > item_load ? item_mma : item_load) + atom_t + 8000.0);
-        if (t < best) { best = t; best_tpc = tpc; best_gpc = gpc; best_range = R; }
+        if (t < best) { best = t; best_tpc = tpc; best_gpc = gpc; best_range = R; best_xh = xh; }
       }
     }
   }
@@ -462,12 +542,14 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
       if (sscanf(f, "%d,%d", &ftpc, &fgpc) == 2 && ftpc >= 1 && ftpc <= max_tpc && ftpc <= p.taps && fgpc >= 1) {
         best_tpc = ftpc;
         best_gpc = fgpc;
+        best_xh = xh_for(ftpc);
       }
     }
     best_range = p.total_tiles / batch->ranges;
   } else if (const char* f = getenv("WS_WGRAD_FORCE")) {
     int ftpc = 0, fgpc = 0, fs = 0;
     if (sscanf(f, "%d,%d,%d", &ftpc, &fgpc, &fs) == 3 && ftpc >= 1 && ftpc <= max_tpc && fgpc >= 1 && fs >= 1) {
+      best_xh = xh_for(ftpc);
       best_tpc = ftpc;
       best_gpc = fgpc;
       best_range = (p.total_tiles + fs - 1) / fs;
@@ -475,6 +557,17 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   }
   p.taps_per_cta = best_tpc;
   p.tap_groups = (p.taps + p.taps_per_cta - 1) / p.taps_per_cta;
+  p.xhalo = best_xh ? 1 : 0;
+  if (p.xhalo) {
+    p.kx_groups = (g.kx + best_tpc - 1) / best_tpc;
+    p.tap_groups = g.ky * g.kz * p.kx_groups;
+    p.halo_rows = (p.bx + best_tpc - 1) * p.by * p.bz;
+    p.halo_blk_bytes = halo_blk(best_tpc);
+    p.b_slot_bytes = sh_alloc * p.halo_blk_bytes;
+  }
+  p.b_slots = budget / p.b_slot_bytes;
+  if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
+  WS_REQUIRE(p.b_slots >= 2, "wgrad: shared memory budget too small for 2 operand slots");
   p.range_tiles = best_range < 1 ? 1 : best_range;
   const long long ranges = (p.total_tiles + p.range_tiles - 1) / p.range_tiles;
   p.items = ranges * p.tap_groups * p.range_tiles;
@@ -488,7 +581,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   static const int env_niss = getenv("WS_WGRAD_NISS") ? atoi(getenv("WS_WGRAD_NISS")) : 4;
   p.n_iss = p.taps_per_cta < 4 ? p.taps_per_cta : 4;
   if (p.n_iss > env_niss) p.n_iss = env_niss < 1 ? 1 : env_niss;
-  while (p.n_iss > 1 && p.b_slots / p.n_iss < 2) --p.n_iss;  // two slots of its private ring per issuer
+  if (!p.xhalo)
+    while (p.n_iss > 1 && p.b_slots / p.n_iss < 2) --p.n_iss;  // two slots of its private ring per issuer
 
   // workspace layout: the M index is always the contiguous one, so that the 32 lanes of an epilogue warp (one
   // accumulator row each) hit consecutive floats with every red.global.add — [tap][cout][cin] when M = cin
@@ -504,7 +598,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     p.mz = mz;
   }
 
-  auto make_map = [&](const View& v, int channels, int X, int Y, int Z, bool strided, CUtensorMap* out) -> int {
+  auto make_map = [&](const View& v, int channels, int X, int Y, int Z, bool strided, CUtensorMap* out,
+                      int x_halo) -> int {
     MapKey k;
     memset(&k, 0, sizeof(k));
     k.ptr = reinterpret_cast<uintptr_t>(v.ptr);
@@ -519,14 +614,17 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     k.box[0] = (uint32_t)cblk;
     k.box[1] = (uint32_t)((p.bz - 1) * ssz + 1);
     k.box[2] = (uint32_t)((p.by - 1) * ssy + 1);
-    k.box[3] = (uint32_t)((p.bx - 1) * ssx + 1);
+    k.box[3] = (uint32_t)((p.bx - 1) * ssx + 1 + x_halo);
     k.box[4] = 1;
     k.estr[0] = 1; k.estr[1] = (uint32_t)ssz; k.estr[2] = (uint32_t)ssy; k.estr[3] = (uint32_t)ssx; k.estr[4] = 1;
     return get_tensor_map(k, out);
   };
-  CUtensorMap tm_x, tm_dy;
-  if (int e = make_map(x, g.cin, g.x, g.y, g.z, true, &tm_x)) return e;
-  if (int e = make_map(dy, g.cout, g.xo, g.yo, g.zo, false, &tm_dy)) return e;
+  CUtensorMap tm_x, tm_dy, tm_halo;
+  if (int e = make_map(x, g.cin, g.x, g.y, g.z, true, &tm_x, 0)) return e;
+  if (int e = make_map(dy, g.cout, g.xo, g.yo, g.zo, false, &tm_dy, 0)) return e;
+  tm_halo = tm_x;
+  if (p.xhalo)
+    if (int e = make_map(x, g.cin, g.x, g.y, g.z, true, &tm_halo, p.taps_per_cta - 1)) return e;
 
   size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 8 * (7 + 2 * kMaxBSlots) + 1024;
   static std::once_flag* once = new std::once_flag;
@@ -538,8 +636,8 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
   WS_REQUIRE(smem <= 227 * 1024, "wgrad smem %zu too large", smem);
   dim3 grid((unsigned)ncta, 1u, (unsigned)mz);
   if (batch) grid = dim3((unsigned)(ncta * mz), 1u, 1u);
-  if (!swap) WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_dy, tm_x, p, wsp));
-  else WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_x, tm_dy, p, wsp));
+  if (!swap) WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_dy, tm_x, tm_halo, p, wsp));
+  else WS_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, grid, dim3(kThreads), smem, st, 1, tm_x, tm_dy, tm_halo, p, wsp));
   WS_POST_LAUNCH(1);
   return 0;
 }

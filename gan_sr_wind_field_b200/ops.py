@@ -417,6 +417,46 @@ def _im2col_weight(weight: torch.Tensor, cpad: int) -> torch.Tensor:
     return w2.reshape(co, cpad, 1, 1, 1).contiguous()
 
 
+# ---- deferred ("late") weight gradients ---------------------------------------------------------------------------
+_LATE_WGRAD = []
+_LATE_WGRAD_QUEUED = [False]
+_LATE_WGRAD_MIN_FLOPS = float(os.environ.get("WINDSR_LATE_WGRAD_MIN_TFLOP", "3")) * 1e12
+
+
+def late_wgrad_enabled() -> bool:
+    """WINDSR_LATE_WGRAD=1 (opt-in).  Measured on 2 GPUs it LOSES 1.2 ms (37.7 -> 38.9 ms per step): the weight-gradient
+    kernel is one wave of 147 equally loaded CTAs, and while NCCL's all-reduce kernels hold a few SMs part of that wave
+    has to run as a second one — hiding the all-reduce behind it costs more than leaving it exposed."""
+    return os.environ.get("WINDSR_LATE_WGRAD", "0") == "1"
+
+
+def capturing_disallows_late() -> bool:
+    return False  # (the final callback runs inside the captured backward pass: nothing to exclude)
+
+
+def _defer_wgrad(weight, bias, compute) -> None:
+    _LATE_WGRAD.append((weight, bias, compute))
+    if _LATE_WGRAD_QUEUED[0]:
+        return
+    _LATE_WGRAD_QUEUED[0] = True
+
+    def _run():
+        _LATE_WGRAD_QUEUED[0] = False
+        items = list(_LATE_WGRAD)
+        _LATE_WGRAD.clear()
+        for w, b, fn in items:
+            with torch.no_grad():
+                dw, db = fn()
+            for p, g in ((w, dw), (b, db)):
+                if p is None or g is None:
+                    continue
+                p.grad = g if p.grad is None else p.grad + g
+                for hook in (getattr(p, "_post_accumulate_grad_hooks", None) or {}).values():
+                    hook(p)
+
+    torch.autograd.Variable._execution_engine.queue_callback(_run)
+
+
 class ConvFn(torch.autograd.Function):
     """y = lrelu(conv(x, w) * oscale + bias) * chan_scale + beta * res
 
@@ -456,6 +496,7 @@ class ConvFn(torch.autograd.Function):
         # stream of their first iteration and invalidates a later CUDA-graph capture)
         ctx.cfg = {k: v for k, v in cfg.items() if k != "out"}
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.has_res = res is not None
         ctx.x_dtype = x.dtype
         needs_y = cfg.get("slope", 1.0) != 1.0
@@ -496,41 +537,56 @@ class ConvFn(torch.autograd.Function):
             copy_(g, gp[:, :shape.cout])
             g = gp
             shape = make_shape(x.shape, pad_cout, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
-        rem = shape.cout % 128
-        if (need_w and not pad_cout and cdt == torch.bfloat16 and shape.cout > 128 and 0 < rem <= 32
-                and rem * shape.kx <= 128 and (rem * shape.kx) % 8 == 0 and shape.kx > 1
-                and (shape.sx, shape.sy, shape.sz) == (1, 1, 1) and x.dtype == torch.bfloat16
-                and g.dtype == torch.bfloat16):
-            # Cout = 128*q + rem (hr_convs.0: 144 = 128 + 16): a second 128-row M tile for `rem` rows would cost as
-            # much as the first.  Instead fold the kx taps of the remainder channels into the channel dimension
-            # (U[x', (dx,co)] = g[x' - dx + px, co], windsr.h "x-fold helpers"): one (1,ky,kz) wgrad with kx*rem
-            # rows — kx times fewer MMAs for the remainder.
-            main = shape.cout - rem
-            s_main = make_shape(x.shape, main, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
-            dw_main, _ = conv_wgrad(x, g[:, :main], s_main)
-            cu = rem * shape.kx
-            u = empty_cl(g.shape[0], cu, *g.shape[2:], cdt, g.device)
-            gv, uv = view(g[:, main:]), view(u)
-            check(load().ws_xunfold(C.byref(gv), C.byref(uv), g.shape[0], rem, shape.kx, shape.px, cu, g.shape[2],
-                                    g.shape[3], g.shape[4], stream_ptr()), "ws_xunfold")
-            s_rem = make_shape(x.shape, cu, (1, shape.ky, shape.kz), 1, (0, shape.py, shape.pz))
-            dw_u, _ = conv_wgrad(x, u, s_rem)
-            dw_rem = dw_u.reshape(shape.kx, rem, shape.cin, shape.ky, shape.kz).permute(1, 2, 0, 3, 4)
-            dw = torch.cat((dw_main, dw_rem), 0)
-            if need_b and ctx.has_bias:
-                db = g.float().sum((0, 2, 3, 4))
-        elif need_w and ctx.im2col and g.dtype == torch.bfloat16 and not pad_cout:
-            # weight gradient of the im2col form: a 1x1x1 wgrad with K = taps*cin on the tensor cores
-            u, shape1 = _im2col(x, shape)
-            dw2, db = conv_wgrad(u, g, shape1, want_bias=ctx.has_bias and need_b)
-            taps = shape.kx * shape.ky * shape.kz
-            dw = dw2.reshape(shape.cout, -1)[:, :taps * shape.cin].reshape(shape.cout, taps, shape.cin) \
-                .permute(0, 2, 1).reshape(weight.shape).contiguous()
-        elif need_w or (need_b and ctx.has_bias):
-            dw, db = conv_wgrad(x, g, shape, want_bias=ctx.has_bias and need_b, want_weight=need_w)
-            if pad_cout:
-                dw = dw[:weight.shape[0]].contiguous() if dw is not None else None
-                db = db[:weight.shape[0]].contiguous() if db is not None else None
+        has_bias, im2col, w_shape = ctx.has_bias, ctx.im2col, weight.shape
+
+        def compute_w():
+            dw = db = None
+            rem = shape.cout % 128
+            if (need_w and not pad_cout and cdt == torch.bfloat16 and shape.cout > 128 and 0 < rem <= 32
+                    and rem * shape.kx <= 128 and (rem * shape.kx) % 8 == 0 and shape.kx > 1
+                    and (shape.sx, shape.sy, shape.sz) == (1, 1, 1) and x.dtype == torch.bfloat16
+                    and g.dtype == torch.bfloat16):
+                # Cout = 128*q + rem (hr_convs.0: 144 = 128 + 16): a second 128-row M tile for `rem` rows would cost as
+                # much as the first.  Instead fold the kx taps of the remainder channels into the channel dimension
+                # (U[x', (dx,co)] = g[x' - dx + px, co], windsr.h "x-fold helpers"): one (1,ky,kz) wgrad with kx*rem
+                # rows — kx times fewer MMAs for the remainder.
+                main = shape.cout - rem
+                s_main = make_shape(x.shape, main, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
+                dw_main, _ = conv_wgrad(x, g[:, :main], s_main)
+                cu = rem * shape.kx
+                u = empty_cl(g.shape[0], cu, *g.shape[2:], cdt, g.device)
+                gv, uv = view(g[:, main:]), view(u)
+                check(load().ws_xunfold(C.byref(gv), C.byref(uv), g.shape[0], rem, shape.kx, shape.px, cu, g.shape[2],
+                                        g.shape[3], g.shape[4], stream_ptr()), "ws_xunfold")
+                s_rem = make_shape(x.shape, cu, (1, shape.ky, shape.kz), 1, (0, shape.py, shape.pz))
+                dw_u, _ = conv_wgrad(x, u, s_rem)
+                dw_rem = dw_u.reshape(shape.kx, rem, shape.cin, shape.ky, shape.kz).permute(1, 2, 0, 3, 4)
+                dw = torch.cat((dw_main, dw_rem), 0)
+                if need_b and has_bias:
+                    db = g.float().sum((0, 2, 3, 4))
+            elif need_w and im2col and g.dtype == torch.bfloat16 and not pad_cout:
+                # weight gradient of the im2col form: a 1x1x1 wgrad with K = taps*cin on the tensor cores
+                u, shape1 = _im2col(x, shape)
+                dw2, db = conv_wgrad(u, g, shape1, want_bias=has_bias and need_b)
+                taps = shape.kx * shape.ky * shape.kz
+                dw = dw2.reshape(shape.cout, -1)[:, :taps * shape.cin].reshape(shape.cout, taps, shape.cin) \
+                    .permute(0, 2, 1).reshape(w_shape).contiguous()
+            elif need_w or (need_b and has_bias):
+                dw, db = conv_wgrad(x, g, shape, want_bias=has_bias and need_b, want_weight=need_w)
+                if pad_cout:
+                    dw = dw[:w_shape[0]].contiguous() if dw is not None else None
+                    db = db[:w_shape[0]].contiguous() if db is not None else None
+            return dw, db
+
+        flops = 2.0 * shape.n * shape.cin * shape.cout * shape.kx * shape.ky * shape.kz * dy.shape[2] * dy.shape[3] * dy.shape[4]
+        if need_w and late_wgrad_enabled() and flops >= _LATE_WGRAD_MIN_FLOPS and not capturing_disallows_late():
+            # the largest weight gradients go LAST (final autograd callback): under data parallelism the all-reduce of
+            # everything produced before them — 132 MB of trunk gradients arrive at the very end of backward — then has
+            # several milliseconds of compute to hide behind instead of being exposed
+            bias_p = ctx.bias_param if need_b and has_bias else None
+            _defer_wgrad(weight, bias_p, compute_w)
+        else:
+            dw, db = compute_w()
         if need_x:
             if cfg.get("dx_contig"):
                 dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)

@@ -303,13 +303,20 @@ sdD = {k: v.detach().clone() for k, v in gan.D.state_dict().items()}
 gan.optimize_parameters(LRg[sl], HRg[sl], Zg[sl], 3)
 mine = {k: p.grad.detach().clone() for k, p in gan.D.named_parameters() if p.grad is not None}
 acc = None
+noise = 0.0
 for r in range(world):
-    ref, _ = make(False)
-    ref.G.load_state_dict(sdG); ref.D.load_state_dict(sdD)
-    ref.feed_xy_niter(x, y, torch.tensor(100, device=dev), 1, 1)
-    s2 = slice(r * b, (r + 1) * b)
-    ref.optimize_parameters(LRg[s2], HRg[s2], Zg[s2], 3)
-    gr = {k: p.grad.detach().clone() for k, p in ref.D.named_parameters() if p.grad is not None}
+    grs = []
+    for rep in range(2):  # twice: the run-to-run spread of ONE single-rank step is the noise floor of this comparison
+        ref, _ = make(False)
+        ref.G.load_state_dict(sdG); ref.D.load_state_dict(sdD)
+        ref.feed_xy_niter(x, y, torch.tensor(100, device=dev), 1, 1)
+        s2 = slice(r * b, (r + 1) * b)
+        ref.optimize_parameters(LRg[s2], HRg[s2], Zg[s2], 3)
+        grs.append({k: p.grad.detach().clone() for k, p in ref.D.named_parameters() if p.grad is not None})
+    sc = max(float(v.double().norm()) for v in grs[0].values())
+    noise = max(noise, max(float((grs[0][k].double() - grs[1][k].double()).norm()) /
+                           max(float(grs[0][k].double().norm()), 1e-4 * sc) for k in grs[0]))
+    gr = grs[0]
     acc = gr if acc is None else {k: acc[k] + gr[k] for k in acc}
 assert set(mine) == set(acc)
 # (a gradient that is analytically ~0 — the last classifier bias under the symmetric RaGAN loss — has no meaningful
@@ -320,13 +327,17 @@ worst = max(float((mine[k].double() - acc[k].double() / world).norm()) / max(flo
 chk = torch.stack([p.double().sum() for p in gan.D.parameters()]).sum()
 dist.all_gather(chks, chk)
 res["D step vs average of shards"] = (worst, all(bool(c == chks[0]) for c in chks))
+d_noise = noise
 if rank == 0:
-    print("DDP_RESULT", {k: (float(v[0]), v[1]) for k, v in res.items()}, flush=True)
+    print("DDP_RESULT", {k: (float(v[0]), v[1]) for k, v in res.items()}, "D run-to-run noise", d_noise, flush=True)
 for name, (worst, same) in res.items():
     # G: every kernel on its path is deterministic in FP32 mode (the concatenated batch only re-associates the batch
     # sums of the weight gradients); D: BatchNorm batch statistics are reduced with fp32 atomics (order varies run to
     # run at the 1e-7 level) and pass through ten normalisations
-    assert worst <= (5e-6 if name.startswith("G") else 2e-5), (name, worst)
+    # (D: BatchNorm batch statistics are reduced with fp32 atomics; the tiny fixture's batch-of-2 BatchNorm layers
+    # amplify that noise — measured 1e-5 .. 9e-3 from run to run — so the bound is the measured run-to-run spread of a
+    # single-rank step, with the flat 2e-5 as its floor)
+    assert worst <= (5e-6 if name.startswith("G") else max(2e-5, 10.0 * d_noise)), (name, worst, d_noise)
     assert same, name
 dist.destroy_process_group()
 '''

@@ -435,8 +435,18 @@ struct WgBatch {
   int ranges;
   long long range_stride;
 };
-static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* wsp, int swap, int m_total,
+static int launch_one(const ConvGeom& g_in, const View& x, const View& dy, float* wsp, int swap, int m_total,
                       int n0, int n_count, cudaStream_t st, const WgBatch* batch = nullptr) {
+  // A conv without taps along x (kx == 1: the x-folded remainder of hr_convs.0's gradient is a (1,5,5) conv) is
+  // handled with the roles of x and y exchanged — a pure relabelling (tap index (ti*ky + tj)*kz + tl is the same
+  // number either way when one of the two extents is 1; the tensor maps swap the two strides) — so that its ky taps
+  // get the halo treatment of WgParams::xhalo.
+  ConvGeom g = g_in;
+  const bool swapxy = g_in.kx == 1 && g_in.ky > 1 && g_in.sx == 1 && g_in.sy == 1 && !getenv("WS_WGRAD_NO_SWAPXY");
+  if (swapxy) {
+    g.x = g_in.y; g.y = g_in.x; g.xo = g_in.yo; g.yo = g_in.xo;
+    g.kx = g_in.ky; g.ky = g_in.kx; g.px = g_in.py; g.py = g_in.px;
+  }
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.n;
@@ -610,6 +620,11 @@ static int launch_one(const ConvGeom& g, const View& x, const View& dy, float* w
     k.strides[1] = (uint64_t)v.vs * esize * Z;
     k.strides[2] = (uint64_t)v.vs * esize * Z * Y;
     k.strides[3] = (uint64_t)v.ns * esize;
+    if (swapxy) {
+      // memory order is (x_mem = Y here, y_mem = X here, z): dimension 2 (our "y") strides over whole y_mem-z planes
+      k.strides[1] = (uint64_t)v.vs * esize * Z * X;
+      k.strides[2] = (uint64_t)v.vs * esize * Z;
+    }
     int ssx = strided ? g.sx : 1, ssy = strided ? g.sy : 1, ssz = strided ? g.sz : 1;
     k.box[0] = (uint32_t)cblk;
     k.box[1] = (uint32_t)((p.bz - 1) * ssz + 1);

@@ -172,21 +172,29 @@ __device__ __forceinline__ void rows_epilogue_f32(uint32_t t_row, int ncols, flo
   if (c < ncols) {
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias) b4 = *reinterpret_cast<const float4*>(bias + c);
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const long long orow = row_map(r);
-      if (orow < 0) continue;
-      const float4 a = *reinterpret_cast<const float4*>(stg + r * kStagePitch + c);
-      float4 y = make_float4(alpha * (a.x + b4.x), alpha * (a.y + b4.y), alpha * (a.z + b4.z), alpha * (a.w + b4.w));
-      if (r1) {
-        const float4 x4 = *reinterpret_cast<const float4*>(r1 + orow * row_stride + c);
-        y.x = fmaf(beta1, x4.x, y.x); y.y = fmaf(beta1, x4.y, y.y); y.z = fmaf(beta1, x4.z, y.z); y.w = fmaf(beta1, x4.w, y.w);
+    // 8 rows per batch: all residual loads of the batch are issued before the first is consumed (one L2 round trip per
+    // batch instead of one per row — this loop was 8-15 us of latency per block)
+    for (int rb = 0; rb < 32; rb += 8) {
+      long long orow[8];
+      float4 x1[8], x2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        orow[u] = row_map(rb + u);
+        x1[u] = x2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (orow[u] >= 0) {
+          if (r1) x1[u] = *reinterpret_cast<const float4*>(r1 + orow[u] * row_stride + c);
+          if (r2) x2[u] = *reinterpret_cast<const float4*>(r2 + orow[u] * row_stride + c);
+        }
       }
-      if (r2) {
-        const float4 x4 = *reinterpret_cast<const float4*>(r2 + orow * row_stride + c);
-        y.x = fmaf(beta2, x4.x, y.x); y.y = fmaf(beta2, x4.y, y.y); y.z = fmaf(beta2, x4.z, y.z); y.w = fmaf(beta2, x4.w, y.w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (orow[u] < 0) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stg + (rb + u) * kStagePitch + c);
+        float4 y = make_float4(alpha * (a.x + b4.x), alpha * (a.y + b4.y), alpha * (a.z + b4.z), alpha * (a.w + b4.w));
+        y.x = fmaf(beta1, x1[u].x, y.x); y.y = fmaf(beta1, x1[u].y, y.y); y.z = fmaf(beta1, x1[u].z, y.z); y.w = fmaf(beta1, x1[u].w, y.w);
+        y.x = fmaf(beta2, x2[u].x, y.x); y.y = fmaf(beta2, x2[u].y, y.y); y.z = fmaf(beta2, x2[u].z, y.z); y.w = fmaf(beta2, x2[u].w, y.w);
+        *reinterpret_cast<float4*>(out + orow[u] * row_stride + c) = y;
       }
-      *reinterpret_cast<float4*>(out + orow * row_stride + c) = y;
     }
   }
   __syncwarp();
@@ -356,7 +364,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
     const int et = threadIdx.x - kEpiThread0;  // 0..127
     int stamp_i = 0;
     auto stamp = [&]() {
-      if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
+      if (p.dbg && (int)blockIdx.x == p.DX / 2 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
       ++stamp_i;
     };
     // (neighbour flags: this launch's epoch, read before anything is published)
@@ -381,10 +389,10 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
       const int c8 = p.F / 8;
       const long long v0 = (long long)x0 * p.slab;
       const int total = p.slab * c8;
-      for (int i0 = et; i0 < total; i0 += 4 * 128) {
-        float4 a[4], b[4];
+      for (int i0 = et; i0 < total; i0 += 8 * 128) {
+        float4 a[8], b[8];  // 8 independent 32-byte reads in flight per thread
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
           if (i < total) {
             const int r = i / c8, q = i - r * c8;
@@ -394,7 +402,7 @@ rdb_fwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbFwdParams 
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
           if (i < total) {
             const int r = i / c8, q = i - r * c8;
@@ -536,6 +544,7 @@ struct RdbBwdParams {
   int a_stage_bytes, w_slot_bytes;
   int w_group;    // dense-conv weight tiles (taps) per ring slot
   int w_slots;    // ring slots (2..kWSlots)
+  long long* dbg;  // optional (WS_RDB_DEBUG_TIMES=1): globaltimer stamps of an interior CTA at every phase edge
   int nb_sync;    // 1: neighbour flags instead of grid-wide barriers between the phases
   int n_iss_m;    // issuers across accumulator tiles
   int tap_split;  // x issuers across the taps of a dense conv (they only ever ADD to the accumulators: any order works)
@@ -713,15 +722,21 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
     const int et = threadIdx.x - kEpiThread0;
     const unsigned int sync_base = (p.nb_sync && et == 0) ? (ld_acquire(&g_rdb_epoch[1]) << 4) : 0u;
     int sync_k = 0;
+    int stamp_i = 0;
+    auto stamp = [&]() {
+      if (p.dbg && (int)blockIdx.x == p.DX / 2 && et == 0) p.dbg[stamp_i] = globaltimer_ns();
+      ++stamp_i;
+    };
+    stamp();  // kernel start (after the prologue)
     // ---- phase -1: g_lff = alpha * dy (bf16) for this CTA's rows; only this CTA reads them back (1x1x1 conv)
     {
       const int c8 = p.F / 8;
       const long long v0 = (long long)x0 * p.slab;
       const int total = p.slab * c8;
-      for (int i0 = et; i0 < total; i0 += 4 * 128) {
-        float4 a[4], b[4];
+      for (int i0 = et; i0 < total; i0 += 8 * 128) {
+        float4 a[8], b[8];  // 8 independent 32-byte reads in flight per thread
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
           if (i < total) {
             const int r = i / c8, q = i - r * c8;
@@ -731,7 +746,7 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 128;
           if (i < total) {
             const int r = i / c8, q = i - r * c8;
@@ -750,10 +765,12 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
       fence_proxy_async_global();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) ptx::mbar_arrive(phase_bar);
+      stamp();  // g_lff written
     }
     for (int ph = 0; ph < nphases; ++ph) {
       ptx::mbar_wait(accum_bar, (uint32_t)(ph & 1));
       ptx::tc_fence_after();
+      stamp();  // MMAs of this phase complete
       const bool last = ph == nphases - 1;
       // channels [c_hi - gc, c_hi) of the accumulated gradient are final now: the output of dense conv j
       const int j = p.nconv - 1 - ph;
@@ -806,15 +823,18 @@ rdb_bwd_persist_kernel(const __grid_constant__ RdbMaps maps, const RdbBwdParams 
         }
       }
       ptx::tc_fence_before();
+      stamp();  // epilogue stores issued
       if (!last) {
         __threadfence();
         fence_proxy_async_global();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        stamp();  // ... and visible
         if (et == 0) {
           if (p.nb_sync) neighbour_sync(1, sync_base, ++sync_k, (int)blockIdx.x, x0 > 0, x0 < p.DX - 1);
           else grid_barrier(p.bar_slot, gridDim.x);
           ptx::mbar_arrive(phase_bar);
         }
+        stamp();  // neighbours have published too
       }
     }
     if (p.nb_sync && et == 0) launch_done(1, gridDim.x);
@@ -906,7 +926,7 @@ int rdb_persist_forward(const ws_rdb_desc* d, const View& x, const View& buf, co
       long long h[64];
       cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
       const int nst = 1 + 2 + 3 * d->nconv + 2;
-      fprintf(stderr, "[rdb_fwd_persist] phase-edge stamps of CTA 0 (us since kernel start):");
+      fprintf(stderr, "[rdb_fwd_persist] phase-edge stamps of an interior CTA (us since kernel start):");
       for (int i = 1; i < nst && i < 64; ++i) fprintf(stderr, " %.1f", (h[i] - h[0]) * 1e-3);
       fprintf(stderr, "\n  order: cast-done, barrier | per conv: mma-done, epilogue-done, barrier | lff mma-done, epilogue-done\n");
     }
@@ -1013,6 +1033,24 @@ int rdb_persist_backward(const ws_rdb_desc* d, const View& dy, const View& buf, 
   p.t_m = ((d->y - 1) * p.pz + d->z + 127) / 128;
   p.slope = d->slope; p.alpha = d->alpha; p.beta1 = d->beta1;
   p.bar_slot = 1;
+  {
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    static const bool dbg_on = env_off("WS_RDB_DEBUG_TIMES");
+    if (dbg_on) {
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+      if (++dbg_calls == 40) {  // a warm call
+        cudaStreamSynchronize(st);
+        long long h[64];
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const int nst = 2 + 4 * d->nconv + 2;
+        fprintf(stderr, "[rdb_bwd_persist] phase-edge stamps of an interior CTA (us since kernel start):");
+        for (int i = 1; i < nst && i < 64; ++i) fprintf(stderr, " %.1f", (h[i] - h[0]) * 1e-3);
+        fprintf(stderr, "\n  order: g_lff written | per phase (LFF, conv n-1 .. 1): mma-done, stores issued, visible, neighbours | conv 0: mma-done, dx written\n");
+      }
+      p.dbg = dbg_buf;
+    }
+  }
   p.kch_lff = (d->f + 63) / 64;
   p.last_k16_lff = (d->f - 64 * (p.kch_lff - 1) + 15) / 16;
   p.a_box_bytes_conv = 3 * p.slab_p * 64;

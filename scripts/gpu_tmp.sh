@@ -1,15 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py -m gpu -q -x --tb=short 2>&1 | tail -3
-for st in 1 0; do
-  if [ $st = 0 ]; then export WS_TC2_NO_STAGED_EPI=1; fi
-  echo "== staged=$st"
-  for l in g7 g5; do
-    timeout 120 python scripts/prof_conv.py 5 $l 2>&1 | tail -1
-    WS_TC2_DEBUG_TIMES=1 timeout 120 python scripts/prof_conv.py 1 $l 2>&1 | grep "tc2 dbg" | tail -1 | sed 's/.*accumulators/accumulators/'
-  done
-done
-unset WS_TC2_NO_STAGED_EPI
-timeout 300 python bench.py --quick > gpurun_out/r02_bench_h.json 2> gpurun_out/r02_bench_h.err; echo "bench exit $?"
+WS_RDB_DEBUG_TIMES=1 timeout 200 python scripts/prof_rdb.py 2>&1 | grep -A1 "rdb_fwd_persist\|rdb_bwd_persist\|default" | grep -v "^--" | head -8
+timeout 300 python bench.py --quick > gpurun_out/r02_bench_i.json 2> gpurun_out/r02_bench_i.err; echo "bench exit $?"
 python -c "
-import json;d=json.load(open('gpurun_out/r02_bench_h.json'));print(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['roofline_step']['frac'], d['config']['per_step_ms']['resident'])"
+import json;d=json.load(open('gpurun_out/r02_bench_i.json'));print(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['roofline_step']['frac'], d['config']['per_step_ms']['resident'])"

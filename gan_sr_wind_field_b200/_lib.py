@@ -88,6 +88,8 @@ SYMBOLS = [
     ("ws_trunk_wgrad_record_floats", _Z, [C.POINTER(WsRdbDesc)]),
     ("ws_trunk_wgrad_workspace_bytes", _Z, [C.POINTER(WsRdbDesc), _I]),
     ("ws_trunk_wgrad", _I, [C.POINTER(WsRdbDesc), _I, _TP, _TP, _TP, _P, _L, _P, _Z, _P]),
+    ("ws_trunk_repack_fwd", _I, [C.POINTER(WsRdbDesc), _I, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P]),
+    ("ws_trunk_repack_bwd", _I, [C.POINTER(WsRdbDesc), _I, _TP, _TP, _TP, _TP, _TP, C.POINTER(_P), C.POINTER(_P), _P]),
     ("ws_upsample_nearest_xy_fwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_upsample_nearest_xy_bwd", _I, [_TP, _TP, _I, _I, _I, _I, _I, _P]),
     ("ws_xfold_sum", _I, [_TP, _P, _TP, _I, _I, _I, _I, _I, _I, _I, _P]),

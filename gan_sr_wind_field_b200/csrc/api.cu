@@ -59,6 +59,7 @@ size_t tc_trunk_wgrad_workspace_bytes(int, int, int, int, int);
 int tc_trunk_wgrad(const ConvGeom&, const ConvGeom&, int, const View&, const View&, const View&, const int*, int, int,
                    float*, long long, void*, size_t, cudaStream_t);
 int bias_grad_batched(const View&, float*, int, long long, int, int, long long, cudaStream_t);
+int pack_tc_trunk_launch(int, int, const ConvGeom*, const int*, int, const float* const*, void* const*, cudaStream_t, int);
 int pack_weights_launch(const float*, const ConvGeom&, int, void*, cudaStream_t);
 bool rdb_persist_ok(const ws_rdb_desc*, const View&, const View&, int);
 int rdb_persist_forward(const ws_rdb_desc*, const View&, const View&, const View&, void* const*, const Epi&,
@@ -890,4 +891,51 @@ extern "C" int ws_trunk_wgrad(const ws_rdb_desc* d, int nblocks, const ws_tensor
   const long long off_bias = (long long)ws_trunk_wgrad_record_floats(d) - r.lff.cout;
   return bias_grad_batched(View(g_lff), grads + off_bias, nblocks, block_stride, d->n, r.lff.cout,
                            (long long)d->x * d->y * d->z, st);
+}
+
+// ---- weight packing for a whole run of identical residual dense blocks (one launch per direction) ------------------
+// Returns 0 when the packings of every block have been enqueued, 1 when this geometry / layout does not take the
+// persistent per-block kernels (the caller then lets ws_rdb_forward / ws_rdb_backward repack block by block), another
+// value on error.  w / packed: [block][conv 0 .. nconv-1, LFF].
+extern "C" int ws_trunk_repack_fwd(const ws_rdb_desc* d, int nblocks, const ws_tensor* x, const ws_tensor* buf,
+                                   const ws_tensor* out, const float* const* w, void* const* packed, void* stream) {
+  RdbGeom r;
+  if (int e = rdb_geom(d, r)) return e;
+  WS_REQUIRE(nblocks >= 1 && x && buf && out && w && packed, "ws_trunk_repack_fwd: null pointer");
+  const bool rows_ok = out->dtype == WS_F32 && out->cstride == 1 && x->vstride == out->vstride &&
+                       x->nstride == out->nstride && !(reinterpret_cast<uintptr_t>(out->ptr) & 15);
+  if (!(device_cc_major() == 10 && rows_ok && rdb_persist_ok(d, View(x), View(buf), device_sm_count()) &&
+        fwd_path(ConvGeom(r.lff), View(buf), d->math) == WS_PATH_TCGEN05))
+    return 1;
+  if (nblocks * (d->nconv + 1) > 64 * (WS_RDB_MAX_CONVS + 1)) return 1;
+  ConvGeom g[WS_RDB_MAX_CONVS + 1];
+  int fold[WS_RDB_MAX_CONVS + 1];
+  for (int i = 0; i <= d->nconv; ++i) {
+    g[i] = ConvGeom(i < d->nconv ? r.dense[i] : r.lff);
+    if (fwd_path(g[i], View(buf), d->math) != WS_PATH_TCGEN05) return 1;
+    fold[i] = i < d->nconv ? 2 : 0;  // dense convs: z-folded (rdb_persist.cu)
+  }
+  return pack_tc_trunk_launch(nblocks, d->nconv + 1, g, fold, 0, w, packed, (cudaStream_t)stream, 0);
+}
+
+extern "C" int ws_trunk_repack_bwd(const ws_rdb_desc* d, int nblocks, const ws_tensor* dy, const ws_tensor* buf,
+                                   const ws_tensor* g_lff, const ws_tensor* gbuf, const ws_tensor* dx,
+                                   const float* const* w, void* const* packed, void* stream) {
+  RdbGeom r;
+  if (int e = rdb_geom(d, r)) return e;
+  WS_REQUIRE(nblocks >= 1 && dy && buf && g_lff && gbuf && dx && w && packed, "ws_trunk_repack_bwd: null pointer");
+  if (!(device_cc_major() == 10 && d->nconv > 0 && dx->ptr && dx->vstride == dy->vstride && dx->nstride == dy->nstride &&
+        rdb_persist_bwd_ok(d, View(dy), View(buf), View(g_lff), View(gbuf), View(dx), device_sm_count()) &&
+        dgrad_path(ConvGeom(r.lff), View(g_lff), d->math) == WS_PATH_TCGEN05))
+    return 1;
+  if (nblocks * (d->nconv + 1) > 64 * (WS_RDB_MAX_CONVS + 1)) return 1;
+  ConvGeom g[WS_RDB_MAX_CONVS + 1];
+  for (int i = 0; i <= d->nconv; ++i) {
+    g[i] = ConvGeom(i < d->nconv ? r.dense[i] : r.lff);
+    if (i < d->nconv) {
+      ws_tensor gs = slice(*gbuf, i * d->gc);
+      if (dgrad_path(g[i], View(&gs), d->math) != WS_PATH_TCGEN05) return 1;
+    }
+  }
+  return pack_tc_trunk_launch(nblocks, d->nconv + 1, g, nullptr, 1, w, packed, (cudaStream_t)stream, 0);
 }

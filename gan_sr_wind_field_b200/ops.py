@@ -542,7 +542,10 @@ class ConvFn(torch.autograd.Function):
         def compute_w():
             dw = db = None
             rem = shape.cout % 128
-            if (need_w and not pad_cout and cdt == torch.bfloat16 and shape.cout > 128 and 0 < rem <= 32
+            # (a narrow layer as a whole — terrain_convs.1, 16 -> 16 — is all "remainder": its M = 16 GEMM would use an
+            # eighth of every MMA)
+            narrow = 8 <= shape.cout <= 32 and shape.cin >= 16 and os.environ.get("WINDSR_NARROW_XFOLD", "1") != "0"
+            if (need_w and not pad_cout and cdt == torch.bfloat16 and ((shape.cout > 128 and 0 < rem <= 32) or narrow)
                     and rem * shape.kx <= 128 and (rem * shape.kx) % 8 == 0 and shape.kx > 1
                     and (shape.sx, shape.sy, shape.sz) == (1, 1, 1) and x.dtype == torch.bfloat16
                     and g.dtype == torch.bfloat16):
@@ -551,8 +554,10 @@ class ConvFn(torch.autograd.Function):
                 # (U[x', (dx,co)] = g[x' - dx + px, co], windsr.h "x-fold helpers"): one (1,ky,kz) wgrad with kx*rem
                 # rows — kx times fewer MMAs for the remainder.
                 main = shape.cout - rem
-                s_main = make_shape(x.shape, main, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
-                dw_main, _ = conv_wgrad(x, g[:, :main], s_main)
+                dw_main = None
+                if main > 0:
+                    s_main = make_shape(x.shape, main, (shape.kx, shape.ky, shape.kz), 1, (shape.px, shape.py, shape.pz))
+                    dw_main, _ = conv_wgrad(x, g[:, :main], s_main)
                 cu = rem * shape.kx
                 u = empty_cl(g.shape[0], cu, *g.shape[2:], cdt, g.device)
                 gv, uv = view(g[:, main:]), view(u)
@@ -561,7 +566,7 @@ class ConvFn(torch.autograd.Function):
                 s_rem = make_shape(x.shape, cu, (1, shape.ky, shape.kz), 1, (0, shape.py, shape.pz))
                 dw_u, _ = conv_wgrad(x, u, s_rem)
                 dw_rem = dw_u.reshape(shape.kx, rem, shape.cin, shape.ky, shape.kz).permute(1, 2, 0, 3, 4)
-                dw = torch.cat((dw_main, dw_rem), 0)
+                dw = torch.cat((dw_main, dw_rem), 0) if dw_main is not None else dw_rem.contiguous()
                 if need_b and has_bias:
                     db = g.float().sum((0, 2, 3, 4))
             elif need_w and im2col and g.dtype == torch.bfloat16 and not pad_cout:
@@ -972,6 +977,21 @@ class TrunkFn(torch.autograd.Function):
         want_in = {b["outer"] for b in blocks if b["outer"] is not None}
         h = x
         wsp = None
+        # weights of ALL blocks packed by one launch (ws_trunk_repack_fwd) when any of them changed
+        geo = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], 1.0, 1.0, 0.0, math_mode(), 0)
+        packs = [b["state"].buffers(geo, params[r * per:(r + 1) * per], 0) for r, b in enumerate(blocks)]
+        repack = [rp for _, rp in packs]
+        out_next = empty_cl(n, f, X, Y, Z, torch.float32, dev)
+        if any(repack):
+            w_all = [t.detach() for r in range(R) for t in params[r * per:r * per + nconv + 1]]
+            p_all = [t for pk, _ in packs for t in pk]
+            xv0, bv0, ov0 = view(x), view(slab[:n]), view(out_next)
+            rc = lib.ws_trunk_repack_fwd(C.byref(geo), R, C.byref(xv0), C.byref(bv0), C.byref(ov0), _ptr_array(w_all),
+                                         _ptr_array(p_all), stream_ptr())
+            if rc == 0:
+                repack = [0] * R
+            elif rc != 1:
+                check(rc, "ws_trunk_repack_fwd")
         for r, b in enumerate(blocks):
             if r in want_in:
                 inputs[r] = h
@@ -979,9 +999,9 @@ class TrunkFn(torch.autograd.Function):
             desc = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], b["alpha"], b["beta1"],
                                   b["beta2"] if outer is not None else 0.0, math_mode(), 0)
             p = params[r * per:(r + 1) * per]
-            packed, desc.repack = b["state"].buffers(desc, p, 0)
+            packed, desc.repack = packs[r][0], int(repack[r])
             buf = slab[r * n:(r + 1) * n]
-            out = empty_cl(n, f, X, Y, Z, torch.float32, dev)
+            out = out_next if r == 0 else empty_cl(n, f, X, Y, Z, torch.float32, dev)
             if wsp is None:
                 wsp = _workspace(int(lib.ws_rdb_forward_workspace_bytes(C.byref(desc))), dev)
             xv, bv, ov = view(h), view(buf), view(out)
@@ -1017,6 +1037,20 @@ class TrunkFn(torch.autograd.Function):
         wsp = None
         pending = {}  # block index -> gradient that reaches its INPUT through an outer skip
         desc0 = None
+        geo = _lib.WsRdbDesc(n, X, Y, Z, f, gc, nconv, k, kl, cfg["slope"], 1.0, 1.0, 0.0, math_mode(), 0)
+        packs = [b["state"].buffers(geo, params[r * per:(r + 1) * per], 1) for r, b in enumerate(blocks)]
+        repack = [rp for _, rp in packs]
+        dx_first = empty_cl(n, f, X, Y, Z, torch.float32, dev)
+        if any(repack):
+            w_all = [t.detach() for r in range(R) for t in params[r * per:r * per + nconv + 1]]
+            p_all = [t for pk, _ in packs for t in pk]
+            dyv0, bv0, glv0, gv0, dxv0 = view(dy), view(slab[:n]), view(g_lff[:n]), view(g[:n]), view(dx_first)
+            rc = lib.ws_trunk_repack_bwd(C.byref(geo), R, C.byref(dyv0), C.byref(bv0), C.byref(glv0), C.byref(gv0),
+                                         C.byref(dxv0), _ptr_array(w_all), _ptr_array(p_all), stream_ptr())
+            if rc == 0:
+                repack = [0] * R
+            elif rc != 1:
+                check(rc, "ws_trunk_repack_bwd")
         for r in range(R - 1, -1, -1):
             b = blocks[r]
             has_outer = b["outer"] is not None
@@ -1024,13 +1058,16 @@ class TrunkFn(torch.autograd.Function):
                                   b["beta2"] if has_outer else 0.0, math_mode(), 0)
             desc0 = desc
             p = params[r * per:(r + 1) * per]
-            packed, desc.repack = b["state"].buffers(desc, p, 1)
+            packed, desc.repack = packs[r][0], int(repack[r])
             if wsp is None:
                 wsp = _workspace(int(lib.ws_rdb_backward_workspace_bytes(C.byref(desc))), dev)
             if has_outer:
                 pending[b["outer"]] = (dy, b["beta2"])
             want_dx = r > 0 or need[0] or r in pending
-            dx = empty_cl(n, f, X, Y, Z, torch.float32, dev) if want_dx else None
+            dx = None
+            if want_dx:
+                dx = dx_first if dx_first is not None else empty_cl(n, f, X, Y, Z, torch.float32, dev)
+                dx_first = None
             dyv, bv, dbv = view(dy), view(slab[r * n:(r + 1) * n]), view(dbuf)
             glv, gv = view(g_lff[r * n:(r + 1) * n]), view(g[r * n:(r + 1) * n])
             dxv = view(dx) if dx is not None else null_view()

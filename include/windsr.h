@@ -206,6 +206,17 @@ size_t ws_trunk_wgrad_workspace_bytes(const ws_rdb_desc* d, int nblocks);
 int ws_trunk_wgrad(const ws_rdb_desc* d, int nblocks, const ws_tensor* buf, const ws_tensor* g, const ws_tensor* g_lff,
                    float* grads, long long block_stride, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight (re)packing for ALL blocks of such a run in one launch per direction (the persistent per-block kernels'
+ * layouts: z-folded forward packing / data-gradient packing); the caller then runs ws_rdb_forward / ws_rdb_backward with
+ * repack = 0.  The tensors describe block 0 (only layouts are examined).  w / packed: [block][conv 0..nconv-1, LFF],
+ * packed[i] of ws_rdb_packed_bytes.  Returns 0 = enqueued, 1 = this geometry does not take the persistent kernels (repack
+ * block by block instead), anything else = error. */
+int ws_trunk_repack_fwd(const ws_rdb_desc* d, int nblocks, const ws_tensor* x, const ws_tensor* buf, const ws_tensor* out,
+                        const float* const* w, void* const* packed, void* stream);
+int ws_trunk_repack_bwd(const ws_rdb_desc* d, int nblocks, const ws_tensor* dy, const ws_tensor* buf,
+                        const ws_tensor* g_lff, const ws_tensor* g, const ws_tensor* dx, const float* const* w,
+                        void* const* packed, void* stream);
+
 /* ---- nearest upsample (x2 in x and y, z untouched): nn.Upsample(scale_factor=(2,2,1)) torch_blocks.py:347 */
 /* in: (n, c, x, y, z) view, out: (n, c, 2x, 2y, z) view; bit-exact gather out[x,y,z] = in[x/2, y/2, z] */
 int ws_upsample_nearest_xy_fwd(const ws_tensor* in, const ws_tensor* out, int n, int c, int x, int y, int z,

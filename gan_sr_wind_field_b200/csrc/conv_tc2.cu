@@ -314,6 +314,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after();
     const long long dbg_e1 = p.dbg ? clock64() : 0;
+    long long dbg_ld = 0;  // cycles inside tcgen05.ld + wait
     const EpiVec ev = make_epi_vec(dst, ep);
     const bool simple = epi_is_simple(ep);
     for (int m = 0; m < p.t_m; ++m) {
@@ -345,8 +346,10 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c0 = 16 * part; c0 < p.n_umma; c0 += 16 * kParts) {
           if (n0 + c0 >= p.cn) break;
           uint32_t rr[16];
+          const long long dbg_c0 = p.dbg ? clock64() : 0;
           ptx::tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(m * p.n_umma + c0), rr);
           ptx::tmem_ld_wait();
+          if (p.dbg) dbg_ld += clock64() - dbg_c0;
           if (simple) epilogue16_simple(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr);
           else epilogue16(ep, ev, dst, n, v, n0 + c0, p.cn, row_ok, rr, lane, ep.stat_sum ? stat_s : nullptr, n0);
         }
@@ -361,6 +364,7 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.dbg && warp == 2 && lane == 0) {
       p.dbg[8 * blockIdx.x + 3] = dbg_e1 - dbg_e0;    // prologue end -> accumulators complete
       p.dbg[8 * blockIdx.x + 4] = clock64() - dbg_e1;  // epilogue
+      p.dbg[8 * blockIdx.x + 7] = dbg_ld;              // ... of which TMEM loads
     }
   }
 
@@ -759,15 +763,15 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
     long long n_mma = 0, n_all = 0;
     for (size_t c = 0; c < dbg_ctas; ++c) {
       if (h[8 * c + 0]) { ++n_mma; for (int j = 0; j < 3; ++j) sum[j] += (double)h[8 * c + j]; }
-      if (h[8 * c + 4]) { ++n_all; for (int j = 3; j < 7; ++j) sum[j] += (double)h[8 * c + j]; }
+      if (h[8 * c + 4]) { ++n_all; for (int j = 3; j < 8; ++j) sum[j] += (double)h[8 * c + j]; }
     }
     if (n_mma && n_all)
       fprintf(stderr,
               "[tc2 dbg] pair=%d by=%d tx=%d t_m=%d a_bufs=%d w_slots=%d w_group=%d merged=%d n_iss=%d kchunks=%d grid=%u | issue loop %.0f cyc (wait halo %.0f, "
-              "wait weights %.0f) | accumulators ready after %.0f, epilogue %.0f | producer waits: halo slot %.0f, weight "
+              "wait weights %.0f) | accumulators ready after %.0f, epilogue %.0f (TMEM loads %.0f) | producer waits: halo slot %.0f, weight "
               "slot %.0f | MMA floor %.0f\n",
               (int)pair, p.by, p.tx, p.t_m, p.a_bufs, p.w_slots, p.w_group, p.merged, p.n_iss, p.kchunks, tiles, sum[0] / n_mma, sum[1] / n_mma,
-              sum[2] / n_mma, sum[3] / n_all, sum[4] / n_all, sum[5] / n_all, sum[6] / n_all,
+              sum[2] / n_mma, sum[3] / n_all, sum[4] / n_all, sum[7] / n_all, sum[5] / n_all, sum[6] / n_all,
               (double)p.t_m * p.kx * p.ky * p.kz * (4.0 * (p.kchunks - 1) + p.last_k16) * (p.n_umma / 2.0 > 72.0 ? p.n_umma / 2.0 : 72.0));
   }
   return 0;

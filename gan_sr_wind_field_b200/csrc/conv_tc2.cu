@@ -66,6 +66,7 @@ struct Tc2Params {
                      // with +150 cycles of scalar work per 4 MMAs ran 110 instead of 73 cycles per MMA): whatever the
                      // thread does between two MMAs — descriptor arithmetic, elect / reconvergence, barrier waits, commits —
                      // is tensor-pipe idle time unless ANOTHER warp has MMAs queued meanwhile
+  int lean;          // 1: the streamlined issue loop (WS_TC2_LEAN=0 keeps the general one)
   int chunk_major;  // 1: K loop ordered (chunk, ky, kz) instead of (ky, kz, chunk): the short tail chunk of a channel count
                     // that is not a multiple of 64 (144 = 64 + 64 + 16) runs as one block at the end — its quarter-length
                     // MMA bursts no longer have to hide the load of a full-size halo tile
@@ -226,6 +227,72 @@ conv3d_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     long long dbg_wa = 0, dbg_ww = 0;
     const bool dbg = p.dbg && q == 0;
     const long long dbg_t0 = dbg ? clock64() : 0;
+    if (!p.vol && !p.tf32 && !p.dbg && p.lean) {
+      // ---- lean issue loop (the common case).  The issuing warp is a single latency chain: the ncu source page of the
+      // general loop below showed ~90 dependent instructions per tap, a dozen of them re-loads of kernel parameters
+      // from the constant bank, against 4 MMAs.  Here every loop invariant is pinned in a register (keep(): the
+      // compiler cannot rematerialise it from the constant bank) and the descriptors advance by additions.
+      const int t_m = ptx::keep(p.t_m), n_iss = ptx::keep(p.n_iss), w_group = ptx::keep(p.w_group), merged = ptx::keep(p.merged);
+      const int a_bufs = ptx::keep(p.a_bufs), w_slots = ptx::keep(p.w_slots), kchunks = ptx::keep(p.kchunks);
+      const int kfull = ptx::keep(k_per_row), klast = ptx::keep(p.last_k16), cmaj = ptx::keep(p.chunk_major), nyz_k = ptx::keep(nyz);
+      const uint32_t a_buf_bytes = (uint32_t)ptx::keep(p.a_buf_bytes), w_bytes16 = (uint32_t)ptx::keep(p.w_bytes >> 4);
+      const uint32_t slab16 = (uint32_t)ptx::keep((p.slabrows * p.row_bytes) >> 4);   // descriptor units (16 B) per kx tap
+      const uint32_t tile16 = (uint32_t)ptx::keep((128 * p.row_bytes) >> 4);          // ... per accumulator tile
+      const uint32_t acc_cols = (uint32_t)ptx::keep(p.n_umma);
+      const uint32_t hi32 = (uint32_t)(desc_hi >> 32), lo_const = (uint32_t)desc_hi;
+      const uint32_t wslot16 = (uint32_t)ptx::keep((int)(w_slot_bytes >> 4)), wbase16 = (w_base >> 4);
+      for (int it = 0; it < iters; ++it) {
+        const int ch = cmaj ? it / nyz_k : it % kchunks;
+        const int nk = (ch == kchunks - 1) ? klast : kfull;
+        ptx::mbar_wait(a_full(ab), aph);
+        ptx::tc_fence_after();
+        const uint32_t a16 = (smem_base + (uint32_t)ab * a_buf_bytes) >> 4;
+        uint32_t a_tap16 = a16 + (uint32_t)q * tile16;  // this issuer's first accumulator tile, tap 0
+        int gpos = 0;
+        uint32_t b16 = wbase16 + (uint32_t)(merged ? ab : wsl) * wslot16;
+        for (int tt = 0; tt < ntaps; ++tt) {
+          if (!merged && gpos == 0) {
+            ptx::mbar_wait(w_full(wsl), wph);
+            ptx::tc_fence_after();
+            b16 = wbase16 + (uint32_t)wsl * wslot16;
+          }
+          const uint32_t acc0 = (it > 0 || tt > 0) ? 1u : 0u;
+          const uint32_t b_lo = lo_const | (b16 & 0x3fffu);
+          uint32_t am16 = a_tap16;
+          for (int m = q; m < t_m; m += n_iss) {
+            const uint32_t a_lo = lo_const | (am16 & 0x3fffu);
+            const uint32_t d_tmem = tmem_base + (uint32_t)m * acc_cols;
+            if (ptx::elect_one()) {
+              if (kPair) {
+                ptx::mma_f16_ss2_lohi(d_tmem, a_lo, b_lo, hi32, idesc, acc0);
+                if (nk > 1) ptx::mma_f16_ss2_lohi(d_tmem, a_lo + 2, b_lo + 2, hi32, idesc, 1u);
+                if (nk > 2) ptx::mma_f16_ss2_lohi(d_tmem, a_lo + 4, b_lo + 4, hi32, idesc, 1u);
+                if (nk > 3) ptx::mma_f16_ss2_lohi(d_tmem, a_lo + 6, b_lo + 6, hi32, idesc, 1u);
+              } else {
+                ptx::mma_f16_ss_lohi(d_tmem, a_lo, b_lo, hi32, idesc, acc0);
+                if (nk > 1) ptx::mma_f16_ss_lohi(d_tmem, a_lo + 2, b_lo + 2, hi32, idesc, 1u);
+                if (nk > 2) ptx::mma_f16_ss_lohi(d_tmem, a_lo + 4, b_lo + 4, hi32, idesc, 1u);
+                if (nk > 3) ptx::mma_f16_ss_lohi(d_tmem, a_lo + 6, b_lo + 6, hi32, idesc, 1u);
+              }
+            }
+            __syncwarp();
+            am16 += (uint32_t)n_iss * tile16;
+          }
+          a_tap16 += slab16;
+          b16 += w_bytes16;
+          if (++gpos == w_group) gpos = 0;
+          if (!merged && (gpos == 0 || tt == ntaps - 1)) {
+            gpos = 0;
+            if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(w_empty(wsl)); else ptx::mma_commit(w_empty(wsl)); }
+            __syncwarp();
+            if (++wsl == w_slots) { wsl = 0; wph ^= 1u; }
+          }
+        }
+        if (ptx::elect_one()) { if (kPair) ptx::mma_commit2(a_empty(ab)); else ptx::mma_commit(a_empty(ab)); }
+        __syncwarp();
+        if (++ab == a_bufs) { ab = 0; aph ^= 1u; }
+      }
+    } else
     for (int it = 0; it < iters; ++it) {
       const int ch = p.chunk_major ? it / (p.vol ? 1 : nyz) : it % p.kchunks;
       const int nk = (ch == p.kchunks - 1) ? p.last_k16 : k_per_row;
@@ -677,6 +744,8 @@ int tc2_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pa
   uint32_t cols = 32;
   while ((int)cols < p.t_m * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
+  static const bool env_no_lean = getenv("WS_TC2_LEAN") && atoi(getenv("WS_TC2_LEAN")) == 0;
+  p.lean = env_no_lean ? 0 : 1;
   static const int env_niss = getenv("WS_TC2_NISS") ? atoi(getenv("WS_TC2_NISS")) : 4;
   p.n_iss = p.t_m < 4 ? p.t_m : 4;
   if (p.n_iss > env_niss) p.n_iss = env_niss < 1 ? 1 : env_niss;

@@ -203,6 +203,36 @@ __device__ __forceinline__ void mma_commit2(uint32_t bar) {
       : "memory");
 }
 
+// The same with the descriptors given as (low word, shared high word): only the start-address field of the low word
+// changes between the MMAs of a kernel, so the issuing thread keeps 32-bit values and the 64-bit operands are assembled
+// here.  keep(): launder a loop invariant through an asm statement so that it stays in a register.
+__device__ __forceinline__ void mma_f16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss2_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ int keep(int v) {
+  asm volatile("mov.b32 %0, %1;" : "=r"(v) : "r"(v));
+  return v;
+}
+
 // ---- programmatic dependent launch ----------------------------------------------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
 // stream is still running; griddep_wait() blocks until that predecessor has completed and its writes are visible,

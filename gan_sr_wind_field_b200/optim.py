@@ -87,13 +87,14 @@ class WindAdam(torch.optim.Adam):
                 raise _lib.WindSRError("WindAdam.step inside a CUDA-graph capture needs prepare_capture() first")
             self._pending.append((blob, raw.copy()))
         else:
-            host = self._staging.get(gi)
-            if host is None or host.numel() < raw.size:
-                host = torch.empty(max(raw.size, 1 << 16), dtype=torch.uint8).pin_memory()
-                self._staging[gi] = host
-            host[:raw.size].copy_(torch.from_numpy(raw))
+            # a FRESH pinned block per upload (torch's caching host allocator does not hand it out again before the
+            # asynchronous copy below has executed).  A reused staging buffer was a race: eager steps re-allocate the
+            # gradients, so the table is rebuilt every step, and when the stream lagged the host the next table was
+            # written into the staging buffer before the previous copy had read it — the earlier step then updated
+            # through the later step's pointers (seen as a 5e-5 mismatch of the Adam test inside the full suite).
+            host = torch.from_numpy(raw).pin_memory()
             blob = torch.empty(raw.size, dtype=torch.uint8, device=dev)
-            blob.copy_(host[:raw.size], non_blocking=True)
+            blob.copy_(host, non_blocking=True)
         lr_dev = hit[5] if hit is not None and hit[5].device == dev else \
             torch.zeros((), dtype=torch.float32, device=dev)
         hit = (key, blob, blob[n * 48:], n, int(chunks.shape[0]), lr_dev)

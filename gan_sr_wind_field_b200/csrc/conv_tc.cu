@@ -61,7 +61,7 @@ struct TcParams {
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)  // two CTAs per SM when the ring is short enough: two MMA issuers
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const TcParams p, const View dst, const Epi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -364,6 +364,14 @@ int tc_conv_launch(const ConvGeom& g, int mode, const View& src, const void* pac
   p.stage_bytes = kABytes + p.n_umma * 128;
   p.stages = (int)((220 * 1024 - 1024 - 256) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  {
+    // This kernel's single issuing thread pays a barrier wait + a commit per stage of 4 MMAs (scripts/micro/
+    // mma_rate3.cu: ~500 cycles against 288 of tensor-pipe work): with a ring short enough for TWO CTAs per SM the second
+    // CTA's issuer fills the gaps of the first (and one CTA's epilogue overlaps the other's main loop).
+    static const bool env_single = getenv("WS_TC1_SINGLE") != nullptr;
+    const int half = (int)(((227 * 1024) / 2 - 2048 - 1024 - 256) / p.stage_bytes);
+    if (!env_single && half >= 3 && p.n_umma <= 256) p.stages = half < p.stages ? half : p.stages;
+  }
   int iters = p.kx * p.ky * p.kz * p.kchunks;
   if (p.stages > iters) p.stages = iters < 2 ? 2 : iters;
   uint32_t cols = 32;

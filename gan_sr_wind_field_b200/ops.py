@@ -568,7 +568,7 @@ class ConvFn(torch.autograd.Function):
                 dw_rem = dw_u.reshape(shape.kx, rem, shape.cin, shape.ky, shape.kz).permute(1, 2, 0, 3, 4)
                 dw = torch.cat((dw_main, dw_rem), 0) if dw_main is not None else dw_rem.contiguous()
                 if need_b and has_bias:
-                    db = g.float().sum((0, 2, 3, 4))
+                    _, db = conv_wgrad(x, g, shape, want_bias=True, want_weight=False)  # one pass over g (bias kernel)
             elif need_w and im2col and g.dtype == torch.bfloat16 and not pad_cout:
                 # weight gradient of the im2col form: a 1x1x1 wgrad with K = taps*cin on the tensor cores
                 u, shape1 = _im2col(x, shape)

@@ -359,3 +359,52 @@ def test_device_dataset_sampling_follows_reference_distributions(monkeypatch):
     plain = DeviceWindDataset(f, f, f, f, f, f, -2.71, 550.44, 32.33, 9e4, 1.05e5, 68.46, data_aug_rot=False,
                               data_aug_flip=False, device="cpu")
     assert not plain.sample_augmentation(5).any() and len(plain) == 3
+
+
+def test_trunk_batching_host_logic():
+    """Host side of the batched trunk path (ops.TrunkFn / ws_trunk_wgrad): which runs of RRDBs are recognised as
+    batchable, how the blocks' epilogue constants and outer-skip links are laid out, and that CPU tensors never take it
+    (torch_blocks.py:217-330 of the reference define the structure being matched)."""
+    import torch
+    from gan_sr_wind_field_b200 import ops
+    from gan_sr_wind_field_b200.CNN_models import torch_blocks as tb
+    from gan_sr_wind_field_b200.CNN_models.Generator_3D_Resnet_ESRGAN import Generator_3D
+    G = Generator_3D(4, 3, 128, 2, upscale=8, hr_kern_size=5, number_of_RDB_convs=5, RDB_gc=32, lff_kern_size=1,
+                     terrain_number_of_features=16)
+    rrdbs = [m for m in G.model[1].module if isinstance(m, tb.RRDB)]
+    assert len(rrdbs) == 2
+    sig = tb._trunk_signature(rrdbs[0])
+    assert sig is not None and sig == tb._trunk_signature(rrdbs[1])
+    assert sig[:4] == (128, 32, 4, 3)                       # features, growth channels, dense convs, kernel size
+    assert tb._trunk_signature(G.model[1].module[-1]) is None  # lr_conv is not an RRDB
+    odd = tb.RRDB(128, 32, 5, 3, mode="3D")                  # 3x3x3 LFF: not the batched 1x1x1 case
+    assert tb._trunk_signature(odd) is None
+    other = tb.RRDB(128, 16, 5, 1, mode="3D")                # different growth channels: a different signature
+    assert tb._trunk_signature(other) not in (None, sig)
+    # block table of one RRDB: RDB 0/1 plain, the last one carries the RRDB scale and the outer skip to block 0's input
+    captured = {}
+
+    class _Stop(Exception):
+        pass
+
+    def fake_apply(x, cfg, *params):
+        captured["cfg"], captured["n"] = cfg, len(params)
+        raise _Stop()
+
+    real = ops.TrunkFn.apply
+    ops.TrunkFn.apply = staticmethod(fake_apply)
+    try:
+        try:
+            tb._trunk_apply(rrdbs, torch.zeros(1, 128, 4, 4, 2), sig)
+        except _Stop:
+            pass
+    finally:
+        ops.TrunkFn.apply = real
+    blocks = captured["cfg"]["blocks"]
+    assert len(blocks) == 6 and captured["n"] == 6 * 6     # per block: 4 dense weights, LFF weight, LFF bias
+    assert [b["outer"] for b in blocks] == [None, None, 0, None, None, 3]
+    assert abs(blocks[2]["alpha"] - 0.2 * 0.2) < 1e-12 and blocks[2]["beta1"] == 0.2 and blocks[2]["beta2"] == 1.0
+    assert blocks[0]["alpha"] == 0.2 and blocks[0]["beta1"] == 1.0 and blocks[0]["beta2"] == 0.0
+    # a CPU tensor goes through the modules' own forward, which refuses (no CPU fallback) instead of batching
+    with pytest.raises(Exception):
+        tb.run_trunk(rrdbs, torch.zeros(1, 128, 4, 4, 2))
